@@ -1,0 +1,156 @@
+// brownian.cpp — host side of the Brownian-increment generator: seeding (commons-math3 MersenneTwister.setSeed),
+// block decomposition of the path-major stream, jump-ahead of the block start states, launch.
+// API shape it serves: BrownianMotion.getBrownianIncrement(timeIndex, factor) returning one vector per (t, f)
+// (BrownianMotionCudaWithRandomVariableCuda.java:123-136, 168-177).
+#include <algorithm>
+#include <cstring>
+
+#include "runtime.h"
+#include "mt_jump_table.inc"
+
+namespace fmc {
+
+namespace {
+
+static_assert((1 << MT_JUMP_LOG2_CHUNK) == MT_CHUNK_WORDS, "jump table granularity must match the kernels");
+
+// commons-math3 MersenneTwister.setSeed(int) == mt19937ar init_genrand
+void seed_int(uint32_t* mt, uint32_t s) {
+    mt[0] = s;
+    for (int i = 1; i < MT_N; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+}
+// commons-math3 MersenneTwister.setSeed(int[]) == init_by_array; setSeed(long) passes {high 32 bits, low 32 bits}
+void seed_array(uint32_t* mt, const uint32_t* key, int len) {
+    seed_int(mt, 19650218u);
+    int i = 1, j = 0;
+    for (int k = std::max(MT_N, len); k != 0; k--) {
+        mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+        i++; j++;
+        if (i >= MT_N) { mt[0] = mt[MT_N - 1]; i = 1; }
+        if (j >= len) j = 0;
+    }
+    for (int k = MT_N - 1; k != 0; k--) {
+        mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+        i++;
+        if (i >= MT_N) { mt[0] = mt[MT_N - 1]; i = 1; }
+    }
+    mt[0] = 0x80000000u;
+}
+
+struct DeviceTable { uint32_t* polys = nullptr; };
+DeviceTable g_table;
+
+const uint32_t* device_polys(Runtime& rt) {
+    if (!g_table.polys) {
+        FMC_CUDA(cudaMalloc(&g_table.polys, sizeof(kMtJumpTable)));
+        FMC_CUDA(cudaMemcpyAsync(g_table.polys, kMtJumpTable, sizeof(kMtJumpTable), cudaMemcpyHostToDevice, rt.stream));
+        FMC_CUDA(cudaStreamSynchronize(rt.stream));
+    }
+    return g_table.polys;
+}
+
+// scratch owner: frees pooled device buffers when leaving scope
+struct Scratch {
+    Runtime& rt; std::vector<void*> bufs;
+    explicit Scratch(Runtime& r) : rt(r) {}
+    void* get(size_t bytes) { void* p = rt.pool.alloc(bytes); bufs.push_back(p); return p; }
+    ~Scratch() { for (void* p : bufs) rt.pool.free(p); }     // stream ordered: later users run after our kernels
+};
+
+// computes the start state of every block: seeded state advanced to chunk_of_block[b]
+void prepare_states(Runtime& rt, Scratch& sc, int seed_mode, int64_t seed, const std::vector<long long>& chunks,
+                    uint32_t** d_states, long long** d_chunks) {
+    uint32_t mt[MT_N];
+    if (seed_mode == 1) seed_int(mt, (uint32_t)seed);
+    else {
+        const uint32_t key[2] = {(uint32_t)((uint64_t)seed >> 32), (uint32_t)((uint64_t)seed & 0xffffffffu)};
+        seed_array(mt, key, 2);
+    }
+    const long long max_chunk = *std::max_element(chunks.begin(), chunks.end());
+    if (max_chunk >> MT_JUMP_NPOLY) fail(FMC_ERR_UNSUPPORTED, "random stream offset beyond the jump table (chunk %lld)", max_chunk);
+    const int nb = (int)chunks.size();
+    uint32_t* d_base = (uint32_t*)sc.get(sizeof(mt));
+    *d_states = (uint32_t*)sc.get(sizeof(uint32_t) * MT_N * (size_t)nb);
+    *d_chunks = (long long*)sc.get(sizeof(long long) * (size_t)nb);
+    // small synchronous uploads from pageable memory (2.5 KB + 8 B per block)
+    FMC_CUDA(cudaMemcpyAsync(d_base, mt, sizeof(mt), cudaMemcpyHostToDevice, rt.stream));
+    FMC_CUDA(cudaMemcpyAsync(*d_chunks, chunks.data(), sizeof(long long) * (size_t)nb, cudaMemcpyHostToDevice, rt.stream));
+    FMC_CUDA(cudaStreamSynchronize(rt.stream));
+    FMC_CUDA(launch_mt_jump(d_base, device_polys(rt), MT_JUMP_NPOLY, *d_chunks, *d_states, nb, rt.stream));
+    rt.stats.n_kernels++;
+}
+
+}  // namespace
+
+void brownian_release_caches(Runtime&) {
+    if (g_table.polys) { cudaFree(g_table.polys); g_table.polys = nullptr; }
+}
+
+void brownian_generate(Runtime& rt, int seed_mode, int64_t seed, int T, int F, int64_t p0, int64_t p1,
+                       const double* sqrt_dt, int32_t* out_nodes) {
+    const int64_t np = p1 - p0;
+    const int TF = T * F;
+    for (int i = 0; i < TF; i++) out_nodes[i] = -1;
+    try {
+        for (int i = 0; i < TF; i++) out_nodes[i] = rt.new_leaf(np);
+        if (np == 0) return;
+        // tile geometry: PT paths per tile (odd -> conflict-free transposition), T*F*PT floats per tile, two tiles
+        const int64_t tile_budget = 6144;                        // floats per tile (24 KB), 2 tiles
+        int64_t PT = std::max<int64_t>(tile_budget / TF, 1);
+        if (PT * TF < 320) PT = (320 + TF - 1) / TF;             // a regeneration (312 elements) may span at most 2 tiles
+        if (PT % 2 == 0) PT += 1;
+        if ((size_t)(2 * PT * TF) * sizeof(float) > 200 * 1024) fail(FMC_ERR_UNSUPPORTED, "T*F = %d too large for the Brownian tile buffer", TF);
+        // block decomposition: contiguous path ranges, about 4 blocks per SM
+        int64_t target_blocks = (int64_t)rt.sm_count * 4;
+        int64_t ppb = (np + target_blocks - 1) / target_blocks;
+        ppb = std::max<int64_t>((ppb + PT - 1) / PT * PT, PT);
+        // keep the block-relative element index inside 32 bits
+        while (ppb * TF >= (1ll << 31)) ppb = std::max<int64_t>(ppb / 2 / PT * PT, PT);
+        const int64_t nb = (np + ppb - 1) / ppb;
+        std::vector<long long> chunks((size_t)nb);
+        for (int64_t b = 0; b < nb; b++) {
+            const unsigned long long first_word = 2ull * (unsigned long long)TF * (unsigned long long)(p0 + b * ppb);
+            chunks[(size_t)b] = (long long)(first_word / MT_CHUNK_WORDS);
+        }
+        Scratch sc(rt);
+        uint32_t* d_states; long long* d_chunks;
+        prepare_states(rt, sc, seed_mode, seed, chunks, &d_states, &d_chunks);
+        double* d_sqrt = (double*)sc.get(sizeof(double) * (size_t)T);
+        float** d_out = (float**)sc.get(sizeof(float*) * (size_t)TF);
+        std::vector<float*> h_out((size_t)TF);
+        for (int i = 0; i < TF; i++) h_out[(size_t)i] = rt.nodes[out_nodes[i]].buf;
+        FMC_CUDA(cudaMemcpyAsync(d_sqrt, sqrt_dt, sizeof(double) * (size_t)T, cudaMemcpyHostToDevice, rt.stream));
+        FMC_CUDA(cudaMemcpyAsync(d_out, h_out.data(), sizeof(float*) * (size_t)TF, cudaMemcpyHostToDevice, rt.stream));
+        FMC_CUDA(cudaStreamSynchronize(rt.stream));              // pageable sources must stay valid until copied
+        BrownianParams P{};
+        P.block_states = d_states; P.chunk_of_block = d_chunks; P.n_blocks = (int)nb; P.paths_per_block = ppb;
+        P.p0 = p0; P.np = np; P.T = T; P.F = F; P.PT = (int)PT; P.sqrt_dt = d_sqrt; P.out = d_out;
+        FMC_CUDA(launch_brownian(P, rt.stream));
+        rt.stats.n_kernels++;
+    } catch (...) {
+        for (int i = 0; i < TF; i++) if (out_nodes[i] >= 0) rt.release_ext(out_nodes[i]);
+        throw;
+    }
+}
+
+void mt19937_raw(Runtime& rt, int seed_mode, int64_t seed, uint64_t skip, int64_t count, uint32_t* host_out) {
+    if (count < 0) fail(FMC_ERR_INVALID, "negative count");
+    if (count == 0) return;
+    Scratch sc(rt);
+    const int64_t target_blocks = (int64_t)rt.sm_count * 4;
+    int64_t wpb = (count + target_blocks - 1) / target_blocks;
+    wpb = std::max<int64_t>((wpb + MT_N - 1) / MT_N * MT_N, MT_N);
+    const int64_t nb = (count + wpb - 1) / wpb;
+    std::vector<long long> chunks((size_t)nb);
+    for (int64_t b = 0; b < nb; b++) chunks[(size_t)b] = (long long)((skip + (uint64_t)(b * wpb)) / MT_CHUNK_WORDS);
+    uint32_t* d_states; long long* d_chunks;
+    prepare_states(rt, sc, seed_mode, seed, chunks, &d_states, &d_chunks);
+    uint32_t* d_out = (uint32_t*)sc.get(sizeof(uint32_t) * (size_t)count);
+    FMC_CUDA(launch_mt_raw(d_states, d_chunks, (int)nb, wpb, skip, count, d_out, rt.stream));
+    rt.stats.n_kernels++;
+    FMC_CUDA(cudaMemcpyAsync(host_out, d_out, sizeof(uint32_t) * (size_t)count, cudaMemcpyDeviceToHost, rt.stream));
+    FMC_CUDA(cudaStreamSynchronize(rt.stream));
+    rt.stats.d2h += sizeof(uint32_t) * (uint64_t)count;
+}
+
+}  // namespace fmc

@@ -1,0 +1,569 @@
+// capi.cpp — the extern "C" surface declared in include/fmcuda.h.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "runtime.h"
+
+using namespace fmc;
+
+namespace {
+
+template <typename F>
+int guarded(F&& f) {
+    Runtime& rt = Runtime::get();
+    std::lock_guard<std::mutex> lock(rt.mu);
+    try {
+        f(rt);
+        return FMC_OK;
+    } catch (const Fail& e) {
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        set_error("host out of memory");
+        return FMC_ERR_OOM;
+    } catch (const std::exception& e) {
+        set_error("internal error: %s", e.what());
+        return FMC_ERR_INVALID;
+    }
+}
+
+void check_same_size(Runtime& rt, int32_t a, int32_t b) {
+    if (rt.nodes[a].n != rt.nodes[b].n)
+        fail(FMC_ERR_SIZE, "operand sizes differ: %lld vs %lld", (long long)rt.nodes[a].n, (long long)rt.nodes[b].n);
+}
+
+Operand N(int32_t idx) { return Operand{idx, 0.f}; }
+Operand S(double s) { return Operand{-1, (float)s}; }     // (float)value: RandomVariableCuda.java:521, RVF:789
+
+// a temporary created inside a compound op: owned only by its consumer
+int32_t temp(Runtime& rt, int32_t idx) {
+    Node& nd = rt.nodes[idx];
+    nd.ext_refs = 0;
+    rt.n_live_handles--;
+    return idx;
+}
+
+void finish(Runtime& rt, int32_t idx, fmc_vec* out) {
+    *out = rt.handle_of(idx);
+    rt.auto_flush();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fmc_last_error(void) { return get_error(); }
+
+int fmc_init(int device_index) { return guarded([&](Runtime& rt) { rt.init(device_index); }); }
+int fmc_shutdown(void) { return guarded([&](Runtime& rt) { rt.shutdown(); }); }
+int fmc_is_initialized(void) { return Runtime::get().initialized ? 1 : 0; }
+
+int fmc_device_count(int* count) {
+    return guarded([&](Runtime&) {
+        int c = 0;
+        if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); c = 0; }
+        *count = c;
+    });
+}
+
+int fmc_device_info(char* name, size_t name_len, int* sm_count, uint64_t* total_mem, int* cc_major, int* cc_minor) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        if (name && name_len) { std::strncpy(name, rt.prop.name, name_len - 1); name[name_len - 1] = 0; }
+        if (sm_count) *sm_count = rt.prop.multiProcessorCount;
+        if (total_mem) *total_mem = rt.prop.totalGlobalMem;
+        if (cc_major) *cc_major = rt.prop.major;
+        if (cc_minor) *cc_minor = rt.prop.minor;
+    });
+}
+
+// ---- vectors ----
+int fmc_vec_from_f64(const double* host, int64_t n, fmc_vec* out) {
+    return guarded([&](Runtime& rt) { rt.require_init(); *out = rt.handle_of(rt.upload_f64(host, n)); });
+}
+int fmc_vec_from_f32(const float* host, int64_t n, fmc_vec* out) {
+    return guarded([&](Runtime& rt) { rt.require_init(); *out = rt.handle_of(rt.upload_f32(host, n)); });
+}
+int fmc_vec_alloc(int64_t n, fmc_vec* out) {
+    return guarded([&](Runtime& rt) { rt.require_init(); *out = rt.handle_of(rt.new_leaf(n)); });
+}
+int fmc_vec_fill(double value, int64_t n, fmc_vec* out) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        if (n < 0) fail(FMC_ERR_INVALID, "negative size");
+        const int32_t r = rt.record(N_CONST, n, S(value));
+        finish(rt, r, out);
+    });
+}
+int fmc_vec_retain(fmc_vec v) { return guarded([&](Runtime& rt) { rt.retain(rt.resolve(v)); }); }
+int fmc_vec_release(fmc_vec v) { return guarded([&](Runtime& rt) { rt.release_ext(rt.resolve(v)); }); }
+int fmc_vec_size(fmc_vec v, int64_t* n) { return guarded([&](Runtime& rt) { *n = rt.nodes[rt.resolve(v)].n; }); }
+int fmc_vec_to_f64(fmc_vec v, double* host, int64_t n) {
+    return guarded([&](Runtime& rt) { rt.require_init(); rt.download_f64(rt.resolve(v), host, n); });
+}
+int fmc_vec_to_f32(fmc_vec v, float* host, int64_t n) {
+    return guarded([&](Runtime& rt) { rt.require_init(); rt.download_f32(rt.resolve(v), host, n); });
+}
+int fmc_vec_get(fmc_vec v, int64_t i, double* out) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        const int32_t idx = rt.resolve(v);
+        if (i < 0 || i >= rt.nodes[idx].n) fail(FMC_ERR_SIZE, "index %lld out of range [0,%lld)", (long long)i, (long long)rt.nodes[idx].n);
+        rt.materialize(idx);
+        float f;
+        FMC_CUDA(cudaMemcpyAsync(&f, rt.nodes[idx].buf + i, sizeof(float), cudaMemcpyDeviceToHost, rt.stream));
+        FMC_CUDA(cudaStreamSynchronize(rt.stream));
+        *out = (double)f;
+    });
+}
+int fmc_vec_device_ptr(fmc_vec v, void** device_ptr) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        const int32_t idx = rt.resolve(v);
+        rt.materialize(idx);
+        FMC_CUDA(cudaStreamSynchronize(rt.stream));
+        *device_ptr = rt.nodes[idx].buf;
+    });
+}
+
+// ---- recorded elementwise operations ----
+int fmc_op_vs(int opcode, fmc_vec a, double s, fmc_vec* out) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        const int32_t x = rt.resolve(a);
+        const int64_t n = rt.nodes[x].n;
+        int32_t r;
+        switch (opcode) {
+        case FMC_CAP:   r = rt.record(N_MIN, n, N(x), S(s)); break;       // RVF:757-760
+        case FMC_FLOOR: r = rt.record(N_MAX, n, N(x), S(s)); break;       // RVF:772-775
+        case FMC_ADD:   r = rt.record(N_ADD, n, N(x), S(s)); break;       // RVF:787-790
+        case FMC_SUB:   r = rt.record(N_SUB, n, N(x), S(s)); break;       // RVF:802-805
+        case FMC_BUS:   r = rt.record(N_SUB, n, S(s), N(x)); break;       // kernel busScalar: -a + b
+        case FMC_MULT:  r = rt.record(N_MUL, n, N(x), S(s)); break;       // RVF:817-820
+        case FMC_DIV:   r = rt.record(N_DIV, n, N(x), S(s)); break;       // RVF:832-835
+        case FMC_VID:   r = rt.record(N_DIV, n, S(s), N(x)); break;       // kernel vidScalar: b / a
+        case FMC_POW:   r = rt.record(N_POW, n, N(x), S(s)); break;       // RVF:847-850
+        default: fail(FMC_ERR_INVALID, "fmc_op_vs: unknown opcode %d", opcode);
+        }
+        finish(rt, r, out);
+    });
+}
+
+int fmc_op_v(int opcode, fmc_vec a, fmc_vec* out) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        const int32_t x = rt.resolve(a);
+        const int64_t n = rt.nodes[x].n;
+        int32_t r;
+        switch (opcode) {
+        case FMC_SQUARED: r = rt.record(N_MUL, n, N(x), N(x)); break;     // RVF:873-876, RVC:1290
+        case FMC_SQRT:    r = rt.record(N_SQRT, n, N(x)); break;
+        case FMC_EXP:     r = rt.record(N_EXP, n, N(x)); break;
+        case FMC_LOG:     r = rt.record(N_LOG, n, N(x)); break;
+        case FMC_SIN:     r = rt.record(N_SIN, n, N(x)); break;
+        case FMC_COS:     r = rt.record(N_COS, n, N(x)); break;
+        case FMC_INVERT:  r = rt.record(N_INV, n, N(x)); break;
+        case FMC_ABS:     r = rt.record(N_ABS, n, N(x)); break;
+        case FMC_ISNAN:   r = rt.record(N_ISNAN, n, N(x)); break;
+        default: fail(FMC_ERR_INVALID, "fmc_op_v: unknown opcode %d", opcode);
+        }
+        finish(rt, r, out);
+    });
+}
+
+int fmc_op_vv(int opcode, fmc_vec a, fmc_vec b, fmc_vec* out) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        const int32_t x = rt.resolve(a), y = rt.resolve(b);
+        check_same_size(rt, x, y);
+        const int64_t n = rt.nodes[x].n;
+        int32_t r;
+        switch (opcode) {
+        case FMC_ADD:   r = rt.record(N_ADD, n, N(x), N(y)); break;       // RVF:981-984
+        case FMC_SUB:   r = rt.record(N_SUB, n, N(x), N(y)); break;       // RVF:1011-1014
+        case FMC_BUS:   r = rt.record(N_SUB, n, N(y), N(x)); break;       // RVF:1041-1044
+        case FMC_MULT:  r = rt.record(N_MUL, n, N(x), N(y)); break;       // RVF:1073-1076
+        case FMC_DIV:   r = rt.record(N_DIV, n, N(x), N(y)); break;       // RVF:1106-1109
+        case FMC_VID:   r = rt.record(N_DIV, n, N(y), N(x)); break;       // RVF:1136-1139 (double division of floats == float division)
+        case FMC_CAP:   r = rt.record(N_MIN, n, N(x), N(y)); break;       // RVF:1165-1168
+        case FMC_FLOOR: r = rt.record(N_MAX, n, N(x), N(y)); break;       // RVF:1194-1197
+        default: fail(FMC_ERR_INVALID, "fmc_op_vv: unknown opcode %d", opcode);
+        }
+        finish(rt, r, out);
+    });
+}
+
+int fmc_op_vvs(int opcode, fmc_vec a, fmc_vec b, double s, fmc_vec* out) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        const int32_t x = rt.resolve(a), y = rt.resolve(b);
+        check_same_size(rt, x, y);
+        const int64_t n = rt.nodes[x].n;
+        int32_t r;
+        switch (opcode) {
+        case FMC_ACCRUE: {        // x * (1.0f + y * p)      RVF:1222-1225, kernel.cu:224-231
+            const int32_t t1 = temp(rt, rt.record(N_MUL, n, N(y), S(s)));
+            const int32_t t2 = temp(rt, rt.record(N_ADD, n, N(t1), S(1.0)));
+            r = rt.record(N_MUL, n, N(x), N(t2));
+            break;
+        }
+        case FMC_DISCOUNT: {      // x / (1.0f + y * p)      RVF:1250-1253, kernel.cu:234-244
+            const int32_t t1 = temp(rt, rt.record(N_MUL, n, N(y), S(s)));
+            const int32_t t2 = temp(rt, rt.record(N_ADD, n, N(t1), S(1.0)));
+            r = rt.record(N_DIV, n, N(x), N(t2));
+            break;
+        }
+        case FMC_ADDPRODUCT: {    // x + y * s               RVF:1345-1348, kernel.cu:257-264
+            const int32_t t1 = temp(rt, rt.record(N_MUL, n, N(y), S(s)));
+            r = rt.record(N_ADD, n, N(x), N(t1));
+            break;
+        }
+        default: fail(FMC_ERR_INVALID, "fmc_op_vvs: unknown opcode %d", opcode);
+        }
+        finish(rt, r, out);
+    });
+}
+
+int fmc_op_vvv(int opcode, fmc_vec a, fmc_vec b, fmc_vec c, fmc_vec* out) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        const int32_t x = rt.resolve(a), y = rt.resolve(b), z = rt.resolve(c);
+        check_same_size(rt, x, y);
+        check_same_size(rt, x, z);
+        const int64_t n = rt.nodes[x].n;
+        int32_t r;
+        switch (opcode) {
+        case FMC_ADDPRODUCT: {    // x + y * z               RVF:1374-1377, kernel.cu:247-254
+            const int32_t t1 = temp(rt, rt.record(N_MUL, n, N(y), N(z)));
+            r = rt.record(N_ADD, n, N(x), N(t1));
+            break;
+        }
+        case FMC_CHOOSE:          // x >= 0 ? y : z          RVF:1280-1282
+            r = rt.record(N_CHOOSE, n, N(x), N(y), N(z));
+            break;
+        case FMC_ADDRATIO: {      // x + y / z               RVF:1409-1412
+            const int32_t t1 = temp(rt, rt.record(N_DIV, n, N(y), N(z)));
+            r = rt.record(N_ADD, n, N(x), N(t1));
+            break;
+        }
+        case FMC_SUBRATIO: {      // x - y / z               RVF:1432-1435
+            const int32_t t1 = temp(rt, rt.record(N_DIV, n, N(y), N(z)));
+            r = rt.record(N_SUB, n, N(x), N(t1));
+            break;
+        }
+        default: fail(FMC_ERR_INVALID, "fmc_op_vvv: unknown opcode %d", opcode);
+        }
+        finish(rt, r, out);
+    });
+}
+
+int fmc_op_choose(fmc_vec trigger, fmc_vec if_nonneg, double s_nonneg, fmc_vec if_neg, double s_neg, fmc_vec* out) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        const int32_t x = rt.resolve(trigger);
+        const int64_t n = rt.nodes[x].n;
+        Operand A = S(s_nonneg), B = S(s_neg);
+        if (if_nonneg) { const int32_t y = rt.resolve(if_nonneg); check_same_size(rt, x, y); A = N(y); }
+        if (if_neg) { const int32_t z = rt.resolve(if_neg); check_same_size(rt, x, z); B = N(z); }
+        finish(rt, rt.record(N_CHOOSE, n, N(x), A, B), out);
+    });
+}
+
+// ---- reductions ----
+namespace {
+
+// merge (count, value, M2) triples of the ranks in rank order (deterministic)
+void merge_ranks(Runtime& rt, int mode, double part[3]) {
+    if (rt.comm_size <= 1) return;
+    // all-gather through an all-reduce of a zero-padded [size][4] table (tiny: <= 8*4 doubles)
+    const int R = rt.comm_size;
+    for (int i = 0; i < 4 * R; i++) rt.h_result[i] = 0.0;
+    rt.h_result[4 * rt.comm_rank + 0] = part[0];
+    rt.h_result[4 * rt.comm_rank + 1] = part[1];
+    rt.h_result[4 * rt.comm_rank + 2] = part[2];
+    FMC_CUDA(cudaMemcpyAsync(rt.d_result + 8, rt.h_result, sizeof(double) * 4 * R, cudaMemcpyHostToDevice, rt.stream));
+    rt.allreduce_sum(rt.d_result + 8, 4 * R);
+    FMC_CUDA(cudaMemcpyAsync(rt.h_result, rt.d_result + 8, sizeof(double) * 4 * R, cudaMemcpyDeviceToHost, rt.stream));
+    FMC_CUDA(cudaStreamSynchronize(rt.stream));
+    double c = 0.0, v = 0.0, m = 0.0;
+    for (int r = 0; r < R; r++) {
+        const double bc = rt.h_result[4 * r], bv = rt.h_result[4 * r + 1], bm = rt.h_result[4 * r + 2];
+        if (bc == 0.0) continue;
+        if (c == 0.0) { c = bc; v = bv; m = bm; continue; }
+        const double tot = c + bc;
+        if (mode == RM_MOMENTS) {
+            const double delta = bv - v, w = bc / tot;
+            m = m + bm + delta * delta * c * w;
+            v = v + delta * w;
+        } else if (mode == RM_MIN) v = (v != v || bv != bv) ? NAN : std::min(v, bv);
+        else if (mode == RM_MAX) v = (v != v || bv != bv) ? NAN : std::max(v, bv);
+        else v += bv;
+        c = tot;
+    }
+    part[0] = c; part[1] = v; part[2] = m;
+}
+
+}  // namespace
+
+int fmc_reduce(int kind, fmc_vec a, fmc_vec weights, double* out) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        const int32_t x = rt.resolve(a);
+        int32_t w = -1;
+        if (kind == FMC_RED_AVERAGE_W || kind == FMC_RED_VARIANCE_W) {
+            if (!weights) fail(FMC_ERR_INVALID, "weighted reduction needs a weight vector");
+            w = rt.resolve(weights);
+            check_same_size(rt, x, w);
+        }
+        ReduceSpec spec;
+        double p[3];
+        switch (kind) {
+        case FMC_RED_SUM:
+        case FMC_RED_AVERAGE:
+            spec.mode = RM_SUM;
+            rt.reduce(x, spec, p); merge_ranks(rt, RM_SUM, p);
+            if (kind == FMC_RED_SUM) *out = (p[0] == 0.0) ? 0.0 : p[1];
+            else *out = (p[0] == 0.0) ? NAN : p[1] / p[0];                       // RVF:318-320, 333
+            break;
+        case FMC_RED_VARIANCE:
+        case FMC_RED_SAMPLE_VARIANCE:
+            spec.mode = RM_MOMENTS;
+            rt.reduce(x, spec, p); merge_ranks(rt, RM_MOMENTS, p);
+            if (p[0] == 0.0) *out = NAN;                                         // RVF:364-366
+            else if (p[0] == 1.0) *out = 0.0;                                    // RVF:361-363
+            else {
+                const double var = p[2] / p[0];                                  // RVF:381
+                *out = (kind == FMC_RED_VARIANCE) ? var : var * p[0] / (p[0] - 1.0);   // RVF:418
+            }
+            break;
+        case FMC_RED_MIN:
+        case FMC_RED_MAX:
+            spec.mode = (kind == FMC_RED_MIN) ? RM_MIN : RM_MAX;
+            rt.reduce(x, spec, p); merge_ranks(rt, spec.mode, p);
+            if (p[0] == 0.0) *out = (kind == FMC_RED_MIN) ? 1.7976931348623157e308 : -1.7976931348623157e308;  // RVF:288, 303
+            else *out = p[1];
+            break;
+        case FMC_RED_AVERAGE_W:
+            spec.mode = RM_DOT; spec.weight = w;
+            rt.reduce(x, spec, p); merge_ranks(rt, RM_SUM, p);
+            *out = (p[0] == 0.0) ? NAN : p[1] / p[0];                            // RVF:356
+            break;
+        case FMC_RED_VARIANCE_W: {
+            rt.materialize(x);                                                   // two passes over x: keep it
+            spec.mode = RM_DOT; spec.weight = w;
+            rt.reduce(x, spec, p); merge_ranks(rt, RM_SUM, p);
+            if (p[0] == 0.0) { *out = NAN; break; }
+            const double avg = p[1] / p[0];                                      // RVF:393
+            ReduceSpec s2; s2.mode = RM_WSQ; s2.weight = w; s2.param = avg;
+            rt.reduce(x, s2, p); merge_ranks(rt, RM_SUM, p);
+            *out = p[1];                                                         // RVF:406 (not divided by n)
+            break;
+        }
+        default: fail(FMC_ERR_INVALID, "fmc_reduce: unknown kind %d", kind);
+        }
+    });
+}
+
+// ---- execution control ----
+int fmc_flush(void) { return guarded([&](Runtime& rt) { rt.require_init(); rt.flush_all(); }); }
+int fmc_sync(void) {
+    return guarded([&](Runtime& rt) { rt.require_init(); rt.flush_all(); FMC_CUDA(cudaStreamSynchronize(rt.stream)); });
+}
+int fmc_set_option(const char* key, double value) {
+    return guarded([&](Runtime& rt) {
+        if (!std::strcmp(key, "flush_threshold")) rt.opt.flush_threshold = (int64_t)value;
+        else if (!std::strcmp(key, "fuse")) { rt.opt.fuse = value != 0.0; if (rt.initialized) rt.flush_all(); }
+        else fail(FMC_ERR_INVALID, "unknown option '%s'", key);
+    });
+}
+int fmc_get_option(const char* key, double* value) {
+    return guarded([&](Runtime& rt) {
+        if (!std::strcmp(key, "flush_threshold")) *value = (double)rt.opt.flush_threshold;
+        else if (!std::strcmp(key, "fuse")) *value = rt.opt.fuse ? 1.0 : 0.0;
+        else fail(FMC_ERR_INVALID, "unknown option '%s'", key);
+    });
+}
+
+int fmc_get_stats(fmc_stats* out) {
+    return guarded([&](Runtime& rt) {
+        std::memset(out, 0, sizeof(*out));
+        out->bytes_in_use = rt.pool.bytes_in_use; out->bytes_cached = rt.pool.bytes_cached;
+        out->bytes_reserved = rt.pool.bytes_reserved; out->bytes_high_water = rt.pool.high_water;
+        out->n_alloc = rt.pool.n_alloc; out->n_alloc_reused = rt.pool.n_reused;
+        out->n_ops_recorded = rt.stats.n_ops; out->n_kernels = rt.stats.n_kernels;
+        out->n_tape_kernels = rt.stats.n_tape_kernels; out->n_tape_instr = rt.stats.n_tape_instr;
+        out->n_nodes_stored = rt.stats.n_stored; out->n_nodes_fused = rt.stats.n_fused; out->n_flushes = rt.stats.n_flushes;
+        out->h2d_bytes = rt.stats.h2d; out->d2h_bytes = rt.stats.d2h;
+        out->live_handles = (uint64_t)rt.n_live_handles; out->pending_nodes = (uint64_t)rt.n_lazy;
+    });
+}
+int fmc_reset_stats(void) {
+    return guarded([&](Runtime& rt) { rt.stats = Stats{}; rt.pool.n_alloc = rt.pool.n_reused = 0; rt.pool.high_water = rt.pool.bytes_in_use; });
+}
+int fmc_pool_trim(void) {
+    return guarded([&](Runtime& rt) { rt.require_init(); FMC_CUDA(cudaStreamSynchronize(rt.stream)); rt.pool.trim(); });
+}
+int fmc_pool_purge(void) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        FMC_CUDA(cudaStreamSynchronize(rt.stream));
+        brownian_release_caches(rt);
+        rt.pool.purge();
+    });
+}
+
+int fmc_timer_start(void) { return guarded([&](Runtime& rt) { rt.require_init(); FMC_CUDA(cudaEventRecord(rt.ev_start, rt.stream)); }); }
+int fmc_timer_stop(float* ms) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        FMC_CUDA(cudaEventRecord(rt.ev_stop, rt.stream));
+        FMC_CUDA(cudaEventSynchronize(rt.ev_stop));
+        FMC_CUDA(cudaEventElapsedTime(ms, rt.ev_start, rt.ev_stop));
+    });
+}
+
+// ---- regression ----
+int fmc_regression_normal_eq(const fmc_vec* basis, const double* scalars, int k, fmc_vec y, double* XtX, double* Xty) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        if (k < 1 || k > REG_MAX_K) fail(FMC_ERR_INVALID, "regression: k=%d outside [1,%d]", k, REG_MAX_K);
+        const int32_t yi = rt.resolve(y);
+        const int64_t n = rt.nodes[yi].n;
+        RegressionParams P{};
+        std::vector<int32_t> need;
+        need.push_back(yi);
+        int32_t bidx[REG_MAX_K];
+        for (int i = 0; i < k; i++) {
+            bidx[i] = -1;
+            if (basis[i]) {
+                bidx[i] = rt.resolve(basis[i]);
+                check_same_size(rt, yi, bidx[i]);
+                need.push_back(bidx[i]);
+            }
+        }
+        std::vector<int32_t> lazy;
+        for (int32_t v : need) if (rt.nodes[v].state == NS_LAZY) lazy.push_back(v);
+        if (!lazy.empty()) rt.run_cone(lazy, nullptr);
+        const int m = k * (k + 1) / 2 + k;
+        if (n == 0) { for (int i = 0; i < k * k; i++) XtX[i] = NAN; for (int i = 0; i < k; i++) Xty[i] = NAN; return; }
+        P.n = n; P.k = k; P.y = rt.nodes[yi].buf;
+        for (int i = 0; i < k; i++) {
+            P.basis[i] = bidx[i] >= 0 ? rt.nodes[bidx[i]].buf : nullptr;
+            P.scalars[i] = bidx[i] >= 0 ? 0.f : (float)scalars[i];
+        }
+        P.partials = rt.d_partials; P.counter = rt.d_counter + 1; P.result = rt.d_result + 64;
+        static int per_sm = 0;
+        if (!per_sm) per_sm = regression_max_blocks_per_sm();
+        const int64_t tiles = (n + 1023) / 1024;
+        int grid = (int)std::min<int64_t>(tiles, (int64_t)per_sm * rt.sm_count);
+        grid = std::max(1, std::min(grid, rt.max_grid));
+        FMC_CUDA(launch_regression(P, grid, rt.stream));
+        rt.stats.n_kernels++;
+        double cnt = (double)n;
+        if (rt.comm_size > 1) {
+            // one all-reduce of the k(k+1)/2 + k sums plus the path count
+            FMC_CUDA(cudaMemcpyAsync(rt.d_result + 64 + m, &cnt, sizeof(double), cudaMemcpyHostToDevice, rt.stream));
+            rt.allreduce_sum(rt.d_result + 64, m + 1);
+        }
+        FMC_CUDA(cudaMemcpyAsync(rt.h_result + 64, rt.d_result + 64, sizeof(double) * (m + 1), cudaMemcpyDeviceToHost, rt.stream));
+        FMC_CUDA(cudaStreamSynchronize(rt.stream));
+        if (rt.comm_size > 1) cnt = rt.h_result[64 + m];
+        const double* s = rt.h_result + 64;
+        int t = 0;
+        for (int i = 0; i < k; i++)
+            for (int j = i; j < k; j++, t++) {
+                double v;
+                if (bidx[i] < 0 && bidx[j] < 0) v = scalars[i] * scalars[j];      // deterministic x deterministic: double (RVF:1059-1061)
+                else v = s[t] / cnt;
+                XtX[i * k + j] = v; XtX[j * k + i] = v;
+            }
+        for (int i = 0; i < k; i++, t++) Xty[i] = s[t] / cnt;
+    });
+}
+
+// ---- Brownian ----
+int fmc_brownian_generate(int seed_mode, int64_t seed, int T, int F, int64_t p0, int64_t p1, const double* sqrt_dt, fmc_vec* out) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        if (T < 1 || F < 1 || p0 < 0 || p1 < p0 || !sqrt_dt || !out) fail(FMC_ERR_INVALID, "fmc_brownian_generate: bad arguments");
+        std::vector<int32_t> nodes((size_t)T * F);
+        brownian_generate(rt, seed_mode, seed, T, F, p0, p1, sqrt_dt, nodes.data());
+        for (size_t i = 0; i < nodes.size(); i++) out[i] = rt.handle_of(nodes[i]);
+    });
+}
+int fmc_mt19937_raw(int seed_mode, int64_t seed, uint64_t skip, int64_t count, uint32_t* host_out) {
+    return guarded([&](Runtime& rt) { rt.require_init(); mt19937_raw(rt, seed_mode, seed, skip, count, host_out); });
+}
+
+// ---- order statistics (RVF:472-602) ----
+// Round 1: the vector is downloaded through the pinned staging path and sorted on the host exactly like the
+// reference does (RandomVariableCuda.java:970-1091); an on-device radix select is the "next" item n2 of SURVEY §8f.
+namespace {
+std::vector<float> sorted_host_copy(Runtime& rt, int32_t idx) {
+    std::vector<float> v((size_t)rt.nodes[idx].n);
+    rt.download_f32(idx, v.data(), (int64_t)v.size());
+    // java.util.Arrays.sort(float[]) order: -0.0f < 0.0f, NaN last
+    std::sort(v.begin(), v.end(), [](float a, float b) {
+        if (a != a) return false;
+        if (b != b) return true;
+        if (a == 0.f && b == 0.f) return std::signbit(a) && !std::signbit(b);
+        return a < b;
+    });
+    return v;
+}
+int64_t quantile_index(int64_t n, double q) {                                    // RVF:484
+    long long idx = (long long)std::floor((double)(n + 1) * q - 1.0 + 0.5);
+    return std::min<long long>(std::max<long long>(idx, 0), n - 1);
+}
+}  // namespace
+
+int fmc_quantile(fmc_vec a, double q, double* out) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        if (rt.comm_size > 1) fail(FMC_ERR_UNSUPPORTED, "quantile of a sharded vector is not implemented");
+        const int32_t x = rt.resolve(a);
+        if (rt.nodes[x].n == 0) { *out = NAN; return; }
+        auto v = sorted_host_copy(rt, x);
+        *out = v[(size_t)quantile_index((int64_t)v.size(), q)];
+    });
+}
+int fmc_quantile_expectation(fmc_vec a, double q0, double q1, double* out) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        if (rt.comm_size > 1) fail(FMC_ERR_UNSUPPORTED, "quantile of a sharded vector is not implemented");
+        const int32_t x = rt.resolve(a);
+        if (rt.nodes[x].n == 0) { *out = NAN; return; }
+        if (q0 > q1) std::swap(q0, q1);                                          // RVF:509-511
+        auto v = sorted_host_copy(rt, x);
+        const int64_t i0 = quantile_index((int64_t)v.size(), q0), i1 = quantile_index((int64_t)v.size(), q1);
+        double e = 0.0;
+        for (int64_t i = i0; i <= i1; i++) e += v[(size_t)i];                    // RVF:519-523
+        *out = e / (double)(i1 - i0 + 1);
+    });
+}
+int fmc_histogram(fmc_vec a, const double* pts, int m, double* out) {
+    return guarded([&](Runtime& rt) {
+        rt.require_init();
+        if (rt.comm_size > 1) fail(FMC_ERR_UNSUPPORTED, "histogram of a sharded vector is not implemented");
+        const int32_t x = rt.resolve(a);
+        auto v = sorted_host_copy(rt, x);
+        size_t si = 0;
+        for (int k = 0; k < m; k++) {                                            // RVF:558-569
+            size_t c = 0;
+            while (si < v.size() && (double)v[si] <= pts[k]) { si++; c++; }
+            out[k] = (double)c;
+        }
+        out[m] = (double)(v.size() - si);
+        if (!v.empty()) for (int k = 0; k <= m; k++) out[k] /= (double)v.size();
+    });
+}
+
+// ---- multi GPU ----
+int fmc_comm_get_unique_id(char* id) { return guarded([&](Runtime&) { comm_get_unique_id(id); }); }
+int fmc_comm_init(int rank, int nranks, const char* id) { return guarded([&](Runtime& rt) { rt.require_init(); comm_init(rt, rank, nranks, id); }); }
+int fmc_comm_destroy(void) { return guarded([&](Runtime& rt) { comm_destroy(rt); }); }
+int fmc_comm_info(int* rank, int* nranks) {
+    return guarded([&](Runtime& rt) { if (rank) *rank = rt.comm_rank; if (nranks) *nranks = rt.comm_size; });
+}
+
+}  // extern "C"

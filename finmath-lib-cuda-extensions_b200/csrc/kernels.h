@@ -1,0 +1,52 @@
+// kernels.h — host-callable launchers of the sm_100a kernels (internal to libfmcuda.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tape_isa.h"
+
+namespace fmc {
+
+// tape_kernel.cu
+cudaError_t launch_tape(const TapeParams& P, int grid, int regs_used, cudaStream_t stream);
+cudaError_t tape_kernel_setup();
+int tape_max_blocks_per_sm(int regs_used);
+
+// regression_kernel.cu — fused normal equations: one pass over k basis vectors + y.
+constexpr int REG_MAX_K = 12;
+struct RegressionParams {
+    long long n;
+    int k;
+    const float* basis[REG_MAX_K];   // nullptr -> deterministic scalar
+    float scalars[REG_MAX_K];
+    const float* y;
+    double* partials;                // [gridDim.x][REG_MAX_K*(REG_MAX_K+1)/2 + REG_MAX_K]
+    unsigned int* counter;
+    double* result;                  // [k*(k+1)/2 + k] sums (not yet divided by n)
+};
+cudaError_t launch_regression(const RegressionParams& P, int grid, cudaStream_t stream);
+int regression_max_blocks_per_sm();
+
+// brownian_kernel.cu — MT19937 (commons-math3 stream) with jump-ahead + AS241 inverse normal.
+constexpr int MT_N = 624;
+constexpr int MT_CHUNK_WORDS = 1 << 15;          // jump granularity: block start states sit on multiples of this
+struct BrownianParams {
+    const uint32_t* block_states;   // [n_blocks][624] generator state (window x[cW .. cW+623]) at each block's start chunk
+    const long long* chunk_of_block;// [n_blocks] start chunk index c of each block
+    int n_blocks;
+    long long paths_per_block;
+    long long p0, np;               // first path and number of paths of the slice this process owns
+    int T, F;
+    int PT;                         // paths per shared-memory tile (odd; T*F*PT >= 312)
+    const double* sqrt_dt;          // [T] device
+    float* const* out;              // [T*F] device array of device pointers, each np floats
+};
+cudaError_t launch_brownian(const BrownianParams& P, cudaStream_t stream);
+// out_states[b] = seeded state advanced by chunk_of_block[b] * MT_CHUNK_WORDS words
+cudaError_t launch_mt_jump(const uint32_t* base_state, const uint32_t* polys, int npoly, const long long* chunk_of_block,
+                           uint32_t* out_states, int n_blocks, cudaStream_t stream);
+// tempered stream words [skip, skip+count); block b emits words_per_block words starting at skip + b*words_per_block
+cudaError_t launch_mt_raw(const uint32_t* block_states, const long long* chunk_of_block, int n_blocks, long long words_per_block,
+                          unsigned long long skip, long long count, uint32_t* out, cudaStream_t stream);
+
+}  // namespace fmc

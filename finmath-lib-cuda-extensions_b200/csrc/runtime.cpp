@@ -1,0 +1,255 @@
+// runtime.cpp — device lifecycle, handles, recording of operations, host<->device copies.
+// (the scheduler / code generator that turns pending nodes into interpreter tapes is in codegen.cpp)
+#include <algorithm>
+#include <cstring>
+
+#include "runtime.h"
+
+namespace fmc {
+
+Runtime& Runtime::get() {
+    static Runtime* rt = new Runtime();   // intentionally leaked: no static-destruction order problems at exit
+    return *rt;
+}
+
+void Runtime::require_init() const {
+    if (!initialized) fail(FMC_ERR_NOT_INIT, "fmcuda runtime not initialised: call fmc_init() (a CUDA device is required; there is no CPU fallback)");
+}
+
+void Runtime::init(int device_index) {
+    if (initialized) return;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        fail(FMC_ERR_NOT_INIT, "no CUDA device available (%s); this backend has no CPU fallback",
+             e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    // negative index counts from the end, -1 = last device (RandomVariableCuda.java:161,177)
+    int dev = device_index >= 0 ? device_index : count + device_index;
+    if (dev < 0 || dev >= count) fail(FMC_ERR_INVALID, "device index %d out of range (device count %d)", device_index, count);
+    FMC_CUDA(cudaSetDevice(dev));
+    FMC_CUDA(cudaGetDeviceProperties(&prop, dev));
+    device = dev;
+    sm_count = prop.multiProcessorCount;
+    FMC_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    FMC_CUDA(cudaEventCreate(&ev_start));
+    FMC_CUDA(cudaEventCreate(&ev_stop));
+    FMC_CUDA(cudaEventCreateWithFlags(&ev_copy[0], cudaEventDisableTiming));
+    FMC_CUDA(cudaEventCreateWithFlags(&ev_copy[1], cudaEventDisableTiming));
+    FMC_CUDA(tape_kernel_setup());
+    max_grid = sm_count * 8;
+    FMC_CUDA(cudaMalloc(&d_partials, sizeof(double) * 128 * (size_t)max_grid));
+    FMC_CUDA(cudaMalloc(&d_counter, sizeof(unsigned int) * 4));
+    FMC_CUDA(cudaMemset(d_counter, 0, sizeof(unsigned int) * 4));
+    FMC_CUDA(cudaMalloc(&d_result, sizeof(double) * 256));
+    FMC_CUDA(cudaMallocHost(&h_result, sizeof(double) * 256));
+    nodes.reserve(1 << 16);
+    initialized = true;
+}
+
+void Runtime::shutdown() {
+    if (!initialized) return;
+    cudaStreamSynchronize(stream);
+    comm_destroy(*this);
+    brownian_release_caches(*this);
+    for (auto& nd : nodes) {
+        if (nd.state == NS_MAT && nd.buf) pool.free(nd.buf);
+        nd = Node{};
+    }
+    nodes.clear(); free_nodes.clear(); pending.clear();
+    n_lazy = 0; n_live_handles = 0;
+    pool.purge();
+    staging.release();
+    cudaFree(d_partials); cudaFree(d_counter); cudaFree(d_result); cudaFreeHost(h_result);
+    d_partials = nullptr; d_counter = nullptr; d_result = nullptr; h_result = nullptr;
+    cudaEventDestroy(ev_start); cudaEventDestroy(ev_stop); cudaEventDestroy(ev_copy[0]); cudaEventDestroy(ev_copy[1]);
+    cudaStreamDestroy(stream);
+    stream = nullptr;
+    initialized = false;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// handles and nodes
+// ---------------------------------------------------------------------------------------------------------
+int32_t Runtime::resolve(fmc_vec h) const {
+    const uint32_t lo = (uint32_t)(h & 0xffffffffu), gen = (uint32_t)(h >> 32);
+    if (lo == 0 || lo > nodes.size()) fail(FMC_ERR_INVALID, "invalid vector handle 0x%llx", (unsigned long long)h);
+    const int32_t idx = (int32_t)lo - 1;
+    const Node& nd = nodes[idx];
+    if (nd.state == NS_FREE || nd.gen != gen || nd.ext_refs == 0)
+        fail(FMC_ERR_INVALID, "stale or released vector handle 0x%llx", (unsigned long long)h);
+    return idx;
+}
+
+int32_t Runtime::new_node() {
+    int32_t idx;
+    if (!free_nodes.empty()) { idx = free_nodes.back(); free_nodes.pop_back(); }
+    else { nodes.emplace_back(); idx = (int32_t)nodes.size() - 1; }
+    Node& nd = nodes[idx];
+    const uint32_t gen = nd.gen;
+    nd = Node{};
+    nd.gen = gen;
+    nd.seq = next_seq++;
+    return idx;
+}
+
+int32_t Runtime::new_leaf(int64_t n) {
+    if (n < 0) fail(FMC_ERR_INVALID, "negative vector size %lld", (long long)n);
+    const int32_t idx = new_node();
+    Node& nd = nodes[idx];
+    nd.op = N_LEAF; nd.state = NS_MAT; nd.n = n; nd.ext_refs = 1;
+    nd.buf = (float*)pool.alloc(sizeof(float) * (size_t)std::max<int64_t>(n, 1));
+    n_live_handles++;
+    return idx;
+}
+
+int32_t Runtime::record(NodeOp op, int64_t n, Operand a, Operand b, Operand c) {
+    const int32_t idx = new_node();
+    Node& nd = nodes[idx];
+    nd.op = op; nd.state = NS_LAZY; nd.n = n; nd.ext_refs = 1;
+    const Operand ops[3] = {a, b, c};
+    for (int k = 0; k < 3; k++) {
+        nd.in[k] = ops[k].node;
+        nd.imm[k] = ops[k].imm;
+        if (ops[k].node >= 0) nodes[ops[k].node].int_refs++;
+    }
+    n_lazy++; n_live_handles++;
+    pending.push_back(idx);
+    stats.n_ops++;
+    return idx;
+}
+
+void Runtime::retain(int32_t idx) { nodes[idx].ext_refs++; }
+
+void Runtime::maybe_free(int32_t first) {
+    // iterative cascade: freeing a lazy node releases its operands
+    std::vector<int32_t> work{first};
+    while (!work.empty()) {
+        const int32_t idx = work.back(); work.pop_back();
+        Node& nd = nodes[idx];
+        if (nd.state == NS_FREE || nd.ext_refs != 0 || nd.int_refs != 0) continue;
+        if (nd.state == NS_LAZY) {
+            n_lazy--;
+            for (int k = 0; k < 3; k++) if (nd.in[k] >= 0) {
+                Node& in = nodes[nd.in[k]];
+                if (in.int_refs > 0) in.int_refs--;
+                work.push_back(nd.in[k]);
+            }
+        } else if (nd.buf) {
+            pool.free(nd.buf);
+        }
+        nd.buf = nullptr; nd.state = NS_FREE; nd.gen++;
+        if (nd.gen == 0) nd.gen = 1;
+        free_nodes.push_back(idx);
+    }
+}
+
+void Runtime::release_ext(int32_t idx) {
+    Node& nd = nodes[idx];
+    if (nd.ext_refs == 0) fail(FMC_ERR_INVALID, "release of a handle with zero references");
+    nd.ext_refs--;
+    if (nd.ext_refs == 0) { n_live_handles--; maybe_free(idx); }
+}
+
+void Runtime::release_int(int32_t idx) {
+    Node& nd = nodes[idx];
+    if (nd.int_refs > 0) nd.int_refs--;
+    maybe_free(idx);
+}
+
+void Runtime::auto_flush() {
+    if (!opt.fuse || n_lazy > opt.flush_threshold) flush_all();
+}
+
+void Runtime::flush_all() {
+    if (n_lazy == 0) { pending.clear(); return; }
+    std::vector<int32_t> targets;
+    targets.reserve(pending.size());
+    for (int32_t idx : pending) {
+        const Node& nd = nodes[idx];
+        if (nd.state == NS_LAZY && nd.ext_refs > 0) targets.push_back(idx);
+    }
+    pending.clear();
+    if (!targets.empty()) run_cone(targets, nullptr);
+}
+
+void Runtime::materialize(int32_t idx) {
+    if (nodes[idx].state == NS_MAT) return;
+    std::vector<int32_t> t{idx};
+    run_cone(t, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host <-> device copies through pinned staging (double buffered, chunked)
+// ---------------------------------------------------------------------------------------------------------
+static constexpr size_t kChunkElems = 4u << 20;   // 16 MiB of floats per staging half
+
+template <typename T>
+static int32_t upload_impl(Runtime& rt, const T* h, int64_t n) {
+    if (n > 0 && !h) fail(FMC_ERR_INVALID, "null host pointer");
+    const int32_t idx = rt.new_leaf(n);
+    float* dst = rt.nodes[idx].buf;
+    rt.staging.ensure(2 * kChunkElems * sizeof(float));
+    float* stage[2] = {(float*)rt.staging.host, (float*)rt.staging.host + kChunkElems};
+    cudaEvent_t done[2] = {rt.ev_copy[0], rt.ev_copy[1]};
+    bool used[2] = {false, false};
+    int64_t off = 0; int which = 0;
+    try {
+        while (off < n) {
+            const int64_t m = std::min<int64_t>(kChunkElems, n - off);
+            if (used[which]) FMC_CUDA(cudaEventSynchronize(done[which]));
+            float* s = stage[which];
+            for (int64_t i = 0; i < m; i++) s[i] = (float)h[off + i];      // RandomVariableCuda.java:768-774
+            FMC_CUDA(cudaMemcpyAsync(dst + off, s, sizeof(float) * (size_t)m, cudaMemcpyHostToDevice, rt.stream));
+            FMC_CUDA(cudaEventRecord(done[which], rt.stream));
+            used[which] = true;
+            which ^= 1; off += m;
+        }
+        for (int w = 0; w < 2; w++) if (used[w]) FMC_CUDA(cudaEventSynchronize(done[w]));
+    } catch (...) {
+        rt.release_ext(idx);
+        throw;
+    }
+    rt.stats.h2d += sizeof(float) * (uint64_t)n;
+    return idx;
+}
+int32_t Runtime::upload_f64(const double* h, int64_t n) { return upload_impl(*this, h, n); }
+int32_t Runtime::upload_f32(const float* h, int64_t n) { return upload_impl(*this, h, n); }
+
+template <typename T>
+static void download_impl(Runtime& rt, int32_t idx, T* h, int64_t n) {
+    if (n != rt.nodes[idx].n) fail(FMC_ERR_SIZE, "host buffer has %lld elements, vector has %lld", (long long)n, (long long)rt.nodes[idx].n);
+    if (n > 0 && !h) fail(FMC_ERR_INVALID, "null host pointer");
+    rt.materialize(idx);
+    const float* src = rt.nodes[idx].buf;
+    rt.staging.ensure(2 * kChunkElems * sizeof(float));
+    float* stage[2] = {(float*)rt.staging.host, (float*)rt.staging.host + kChunkElems};
+    cudaEvent_t done[2] = {rt.ev_copy[0], rt.ev_copy[1]};
+    // software pipeline: copy chunk c+1 while widening chunk c
+    int64_t off = 0; int which = 0;
+    int64_t pend_off[2] = {0, 0}, pend_m[2] = {0, 0};
+    bool used[2] = {false, false};
+    auto drain = [&](int w) {
+        FMC_CUDA(cudaEventSynchronize(done[w]));
+        const float* s = stage[w];
+        T* d = h + pend_off[w];
+        for (int64_t i = 0; i < pend_m[w]; i++) d[i] = (T)s[i];            // RandomVariableCuda.java:776-782
+        used[w] = false;
+    };
+    while (off < n) {
+        const int64_t m = std::min<int64_t>(kChunkElems, n - off);
+        if (used[which]) drain(which);
+        FMC_CUDA(cudaMemcpyAsync(stage[which], src + off, sizeof(float) * (size_t)m, cudaMemcpyDeviceToHost, rt.stream));
+        FMC_CUDA(cudaEventRecord(done[which], rt.stream));
+        pend_off[which] = off; pend_m[which] = m; used[which] = true;
+        which ^= 1; off += m;
+    }
+    if (used[which]) drain(which);
+    if (used[which ^ 1]) drain(which ^ 1);
+    rt.stats.d2h += sizeof(float) * (uint64_t)n;
+}
+void Runtime::download_f32(int32_t idx, float* h, int64_t n) { download_impl(*this, idx, h, n); }
+void Runtime::download_f64(int32_t idx, double* h, int64_t n) { download_impl(*this, idx, h, n); }
+
+}  // namespace fmc

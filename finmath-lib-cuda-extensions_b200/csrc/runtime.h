@@ -1,0 +1,186 @@
+// runtime.h — internal structures of libfmcuda.so: device runtime (pool, stream, staging), the pending-op
+// graph (op-tape) and its code generator. Replaces RandomVariableCuda.DeviceMemoryPool
+// (/root/reference/src/main/java/net/finmath/cuda/montecarlo/RandomVariableCuda.java:119-558).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/fmcuda.h"
+#include "kernels.h"
+#include "tape_isa.h"
+
+namespace fmc {
+
+// ---------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+struct Fail { int code; };   // thrown internally, converted to a status code at the C boundary
+[[noreturn]] void fail(int code, const char* fmt, ...);
+#define FMC_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    ::fmc::fail(e_ == cudaErrorMemoryAllocation ? FMC_ERR_OOM : FMC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// device memory pool: slabs obtained from the driver, carved into blocks; freed blocks are recycled by exact
+// rounded size (Monte-Carlo vectors of one simulation all have the same size, like RVC:295-306) and are safe to
+// reuse immediately because every kernel and copy runs in order on the one compute stream (stream-ordered
+// reuse, the property RVC relies on implicitly). No cudaMemGetInfo per allocation (RVC:308), no GC coupling.
+// ---------------------------------------------------------------------------------------------------------
+class DevicePool {
+public:
+    void* alloc(size_t bytes);          // throws Fail{FMC_ERR_OOM}
+    void  free(void* p);
+    void  trim();                       // return slabs without live blocks to the driver
+    void  purge();                      // trim, must be called with no live blocks to release everything
+    uint64_t bytes_in_use = 0, bytes_cached = 0, bytes_reserved = 0, high_water = 0, n_alloc = 0, n_reused = 0;
+private:
+    struct Slab { char* base; size_t size, used; int live; bool dedicated; };
+    struct Block { size_t size; int slab; };
+    std::vector<Slab> slabs_;
+    std::unordered_map<void*, Block> blocks_;                  // live + cached blocks by address
+    std::unordered_map<size_t, std::vector<void*>> free_;      // rounded size -> cached blocks
+    static size_t round_size(size_t b);
+    void* carve(size_t rounded);
+};
+
+// pinned staging buffer for H2D / D2H (replaces the pageable cuMemcpy of RVC:457-481)
+struct Staging {
+    void* host = nullptr;
+    size_t bytes = 0;
+    void ensure(size_t need);
+    void release();
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// pending-op graph
+// ---------------------------------------------------------------------------------------------------------
+enum NodeOp : uint8_t {
+    N_LEAF = 0,
+    // binary: in[0], in[1] (node index or -1 => scalar imm[k])
+    N_ADD, N_SUB, N_MUL, N_DIV, N_MIN, N_MAX,
+    // unary on in[0]
+    N_SQRT, N_EXP, N_LOG, N_SIN, N_COS, N_ABS, N_INV, N_ISNAN,
+    N_POW,       // in[0] ^ imm[1]
+    N_CHOOSE,    // in[0] >= 0 ? in[1] : in[2]   (in[1], in[2] may be scalars)
+    N_CONST      // every element = imm[0]
+};
+enum NodeState : uint8_t { NS_FREE = 0, NS_LAZY = 1, NS_MAT = 2 };
+
+struct Node {
+    uint8_t op = N_LEAF, state = NS_FREE;
+    int32_t in[3] = {-1, -1, -1};
+    float imm[3] = {0.f, 0.f, 0.f};
+    int64_t n = 0;
+    uint32_t ext_refs = 0;      // handles held by the caller
+    uint32_t int_refs = 0;      // operand slots of pending (lazy) nodes that reference this node
+    uint32_t gen = 1;
+    uint64_t seq = 0;           // creation order == a topological order
+    float* buf = nullptr;       // device vector when NS_MAT
+    // scratch used during one flush
+    uint32_t epoch = 0;
+    int32_t local = -1;
+};
+
+struct Options {
+    int64_t flush_threshold = 4096;
+    bool fuse = true;
+};
+
+struct Stats {
+    uint64_t n_ops = 0, n_kernels = 0, n_tape_kernels = 0, n_tape_instr = 0, n_stored = 0, n_fused = 0, n_flushes = 0;
+    uint64_t h2d = 0, d2h = 0;
+};
+
+struct Operand { int32_t node; float imm; };   // node < 0 => scalar
+
+struct ReduceSpec {
+    int mode = RM_NONE;          // tape reduce mode
+    double param = 0.0;
+    int32_t weight = -1;         // node index of the weight vector (RM_DOT / RM_WSQ)
+};
+
+class Runtime {
+public:
+    static Runtime& get();
+    std::mutex mu;
+
+    // lifecycle
+    bool initialized = false;
+    int device = -1, sm_count = 0;
+    cudaDeviceProp prop{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_copy[2] = {nullptr, nullptr};
+    void init(int device_index);
+    void shutdown();
+    void require_init() const;
+
+    // memory
+    DevicePool pool;
+    Staging staging;
+    double* d_partials = nullptr;       // reduction scratch
+    unsigned int* d_counter = nullptr;
+    double* d_result = nullptr;         // [256] doubles
+    double* h_result = nullptr;         // pinned mirror
+    int max_grid = 0;
+
+    // graph
+    std::vector<Node> nodes;
+    std::vector<int32_t> free_nodes;
+    std::vector<int32_t> pending;       // lazy nodes in creation order (may contain stale entries)
+    uint64_t next_seq = 1;
+    uint32_t epoch = 0;
+    int64_t n_lazy = 0, n_live_handles = 0;
+    Options opt;
+    Stats stats;
+
+    // handles
+    fmc_vec handle_of(int32_t idx) const { return ((uint64_t)nodes[idx].gen << 32) | (uint32_t)(idx + 1); }
+    int32_t resolve(fmc_vec h) const;   // throws on invalid
+
+    int32_t new_node();
+    int32_t new_leaf(int64_t n);                          // allocates the device buffer, ext_refs = 1
+    int32_t record(NodeOp op, int64_t n, Operand a, Operand b = {-1, 0.f}, Operand c = {-1, 0.f});
+    void retain(int32_t idx);
+    void release_ext(int32_t idx);
+    void release_int(int32_t idx);
+    void maybe_free(int32_t idx);
+
+    // execution
+    void flush_all();                                     // materialise every referenced pending node
+    void materialize(int32_t idx);                        // make node idx NS_MAT
+    void run_cone(const std::vector<int32_t>& targets, const ReduceSpec* red);   // core scheduler
+    void reduce(int32_t idx, const ReduceSpec& spec, double out[3]);            // {count, value, M2} of the LOCAL slice
+    void auto_flush();
+
+    // host copies
+    int32_t upload_f64(const double* h, int64_t n);
+    int32_t upload_f32(const float* h, int64_t n);
+    void download_f32(int32_t idx, float* h, int64_t n);
+    void download_f64(int32_t idx, double* h, int64_t n);
+
+    // comm (NCCL, loaded with dlopen; see comm.cpp)
+    int comm_rank = 0, comm_size = 1;
+    void* nccl_comm = nullptr;
+    void allreduce_sum(double* dev, int count);           // in place on the compute stream
+    void allreduce_minmax(double* dev, int count, bool is_max);
+};
+
+// comm.cpp
+void comm_get_unique_id(char* id);
+void comm_init(Runtime& rt, int rank, int nranks, const char* id);
+void comm_destroy(Runtime& rt);
+
+// brownian.cpp
+void brownian_generate(Runtime& rt, int seed_mode, int64_t seed, int T, int F, int64_t p0, int64_t p1,
+                       const double* sqrt_dt, int32_t* out_nodes);
+void mt19937_raw(Runtime& rt, int seed_mode, int64_t seed, uint64_t skip, int64_t count, uint32_t* host_out);
+void brownian_release_caches(Runtime& rt);
+
+}  // namespace fmc

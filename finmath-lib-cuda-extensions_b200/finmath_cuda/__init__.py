@@ -1,0 +1,18 @@
+"""finmath_cuda — B200-native backend for finmath-lib's RandomVariable / BrownianMotion vector layer.
+
+Host-side mirror (Python) of the reference's plug-in surface over the C ABI of include/fmcuda.h:
+RandomVariableCudaFactory, RandomVariableCuda (type priority 20), BrownianMotionCuda,
+MonteCarloConditionalExpectationRegression. No CPU fallback: importing works without a GPU (so that the symbol
+table can be checked), creating a stochastic vector without one raises.
+"""
+from . import _capi
+from ._capi import CudaError, ensure_init, set_option, shutdown, stats
+from .random_variable import RandomVariable, RandomVariableCuda, RandomVariableCudaFactory
+from .brownian_motion import BrownianMotionCuda, TimeDiscretization
+from .conditional_expectation import MonteCarloConditionalExpectationRegression
+from . import distributed
+
+__all__ = [
+    "RandomVariable", "RandomVariableCuda", "RandomVariableCudaFactory", "BrownianMotionCuda", "TimeDiscretization",
+    "MonteCarloConditionalExpectationRegression", "CudaError", "ensure_init", "shutdown", "stats", "set_option", "distributed",
+]

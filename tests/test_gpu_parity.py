@@ -1,0 +1,348 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI / host mirror) against the CPU oracle on the same
+seeded inputs. Bit-exact for + - * / min max abs choose and the uint32 random stream; <= 1 float ulp for the
+double-then-round transcendentals; 1e-5 relative for reductions and regression (north-star tolerances)."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N = 100_000          # RandomVariableGPUTest.java:196
+
+
+def ulp_diff(a: np.ndarray, b: np.ndarray) -> int:
+    a = np.asarray(a, dtype=np.float32); b = np.asarray(b, dtype=np.float32)
+    nan_a, nan_b = np.isnan(a), np.isnan(b)
+    assert np.array_equal(nan_a, nan_b), "NaN pattern differs"
+    ia = a.view(np.int32).astype(np.int64); ib = b.view(np.int32).astype(np.int64)
+    ia = np.where(ia < 0, -(ia & 0x7fffffff), ia); ib = np.where(ib < 0, -(ib & 0x7fffffff), ib)
+    d = np.abs(ia - ib)
+    d[nan_a] = 0
+    return int(d.max()) if d.size else 0
+
+
+def bits_equal(a, b) -> bool:
+    a = np.asarray(a, dtype=np.float32); b = np.asarray(b, dtype=np.float32)
+    nan = np.isnan(a) & np.isnan(b)
+    return bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | nan))
+
+
+@pytest.fixture(scope="module")
+def data(O):
+    # inputs: commons-math3 style uniforms from the MT stream the generator under test also produces
+    x = O.mt_doubles_from_u32(O.mt_u32(31415, 2 * N, O.SEED_INT))
+    y = O.mt_doubles_from_u32(O.mt_u32(314151, 2 * N, O.SEED_INT))
+    z = O.mt_doubles_from_u32(O.mt_u32(1234, 2 * N, O.SEED_INT)) - 0.5
+    return x, y, z
+
+
+def test_upload_download_roundtrip(fc, O, data):
+    x, _, _ = data
+    rv = fc.RandomVariableCuda(0.0, x)
+    assert rv.size() == N and not rv.isDeterministic() and rv.getTypePriority() == 20
+    assert bits_equal(rv.getRealizationsFloat(), O.from_f64(x))
+    assert np.array_equal(rv.getRealizations(), O.from_f64(x).astype(np.float64))
+    assert rv.get(17) == float(np.float32(x[17]))
+
+
+SCALARS = [1.0 / 3.0, 3.1415, 2.0, -0.25, 0.0]
+
+
+@pytest.mark.parametrize("name", ["cap", "floor", "add", "sub", "bus", "mult", "div", "vid"])
+def test_scalar_ops_bit_exact(fc, O, data, name):
+    x, _, z = data
+    for src in (x, z):
+        rv = fc.RandomVariableCuda(0.0, src)
+        xf = O.from_f64(src)
+        for s in SCALARS:
+            got = getattr(rv, name)(s).getRealizationsFloat()
+            want = O.op_vs(getattr(O, name.upper()), xf, s)
+            assert bits_equal(got, want), (name, s)
+
+
+@pytest.mark.parametrize("name", ["add", "sub", "bus", "mult", "div", "vid", "cap", "floor"])
+def test_vector_ops_bit_exact(fc, O, data, name):
+    x, y, z = data
+    a, b = fc.RandomVariableCuda(0.0, x), fc.RandomVariableCuda(0.0, z)
+    got = getattr(a, name)(b).getRealizationsFloat()
+    want = O.op_vv(getattr(O, name.upper()), O.from_f64(x), O.from_f64(z))
+    assert bits_equal(got, want)
+    # x op x (same operand twice)
+    got = getattr(a, name)(a).getRealizationsFloat()
+    want = O.op_vv(getattr(O, name.upper()), O.from_f64(x), O.from_f64(x))
+    assert bits_equal(got, want)
+
+
+@pytest.mark.parametrize("name,exact", [("squared", True), ("sqrt", True), ("invert", True), ("abs", True), ("isNaN", True),
+                                        ("exp", False), ("log", False), ("sin", False), ("cos", False)])
+def test_unary_ops(fc, O, data, name, exact):
+    x, _, z = data
+    for src in (x, z * 20.0):
+        rv = fc.RandomVariableCuda(0.0, src)
+        got = getattr(rv, name)().getRealizationsFloat()
+        want = O.op_v(getattr(O, name.upper()), O.from_f64(src))
+        if exact:
+            assert bits_equal(got, want), name
+        else:
+            assert ulp_diff(got, want) <= 1, (name, ulp_diff(got, want))
+
+
+@pytest.mark.parametrize("e", [2.0, 0.5, 3.0, -1.5, 1.0 / 3.0, 0.0, 1.0])
+def test_pow(fc, O, data, e):
+    x, _, _ = data
+    rv = fc.RandomVariableCuda(0.0, x * 4.0)
+    got = rv.pow(e).getRealizationsFloat()
+    want = O.op_vs(O.POW, O.from_f64(x * 4.0), e)
+    assert ulp_diff(got, want) <= 1, ulp_diff(got, want)
+
+
+def test_compound_ops_bit_exact(fc, O, data):
+    x, y, z = data
+    X, Y, Z = (fc.RandomVariableCuda(0.0, v) for v in (x, y, z))
+    xf, yf, zf = O.from_f64(x), O.from_f64(y), O.from_f64(z)
+    for p in (2.0, 1.0 / 3.0):
+        assert bits_equal(X.accrue(Y, p).getRealizationsFloat(), O.op_vvs(O.ACCRUE, xf, yf, p))
+        assert bits_equal(X.discount(Y, p).getRealizationsFloat(), O.op_vvs(O.DISCOUNT, xf, yf, p))
+        assert bits_equal(X.addProduct(Y, p).getRealizationsFloat(), O.op_vvs(O.ADDPRODUCT, xf, yf, p))
+    assert bits_equal(X.addProduct(Y, Z).getRealizationsFloat(), O.op_vvv(O.ADDPRODUCT, xf, yf, zf))
+    assert bits_equal(X.addRatio(Z, Y).getRealizationsFloat(), O.op_vvv(O.ADDRATIO, xf, zf, yf))
+    assert bits_equal(X.subRatio(Z, Y).getRealizationsFloat(), O.op_vvv(O.SUBRATIO, xf, zf, yf))
+    assert bits_equal(Z.choose(X, Y).getRealizationsFloat(), O.op_vvv(O.CHOOSE, zf, xf, yf))
+    # choose with deterministic branches
+    got = Z.choose(fc.RandomVariableCuda(1.5), Y).getRealizationsFloat()
+    assert bits_equal(got, O.op_vvv(O.CHOOSE, zf, np.full(N, 1.5, dtype=np.float32), yf))
+    got = Z.choose(X, fc.RandomVariableCuda(-2.0)).getRealizationsFloat()
+    assert bits_equal(got, O.op_vvv(O.CHOOSE, zf, xf, np.full(N, -2.0, dtype=np.float32)))
+    # addSumProduct = fold of addProduct (RVF:1385-1392)
+    got = X.addSumProduct([X, Y], [Y, Z]).getRealizationsFloat()
+    want = O.op_vvv(O.ADDPRODUCT, O.op_vvv(O.ADDPRODUCT, xf, xf, yf), yf, zf)
+    assert bits_equal(got, want)
+
+
+def test_edge_values_min_max_nan_zero(fc, O):
+    nan, inf = float("nan"), float("inf")
+    a = np.array([0.0, -0.0, 0.0, -0.0, nan, 1.0, nan, inf, -inf, 1e-45, 3.0, -1.0], dtype=np.float32)
+    b = np.array([-0.0, 0.0, 0.0, -0.0, 1.0, nan, nan, -inf, inf, -1e-45, 3.0, 2.0], dtype=np.float32)
+    A, B = fc.RandomVariableCuda(0.0, a), fc.RandomVariableCuda(0.0, b)
+    for name in ("cap", "floor", "add", "sub", "mult", "div", "vid"):
+        got = getattr(A, name)(B).getRealizationsFloat()
+        want = O.op_vv(getattr(O, name.upper()), a, b)
+        assert bits_equal(got, want), (name, got, want)
+    for s in (0.0, -0.0, nan, 1.0):
+        assert bits_equal(A.cap(s).getRealizationsFloat(), O.op_vs(O.CAP, a, s)), s
+        assert bits_equal(A.floor(s).getRealizationsFloat(), O.op_vs(O.FLOOR, a, s)), s
+    assert bits_equal(A.isNaN().getRealizationsFloat(), O.op_v(O.ISNAN, a))
+    assert bits_equal(A.abs().getRealizationsFloat(), O.op_v(O.ABS, a))
+    assert bits_equal(A.choose(B, A).getRealizationsFloat(), O.op_vvv(O.CHOOSE, a, b, a))
+    for e in (nan, 0.0, inf, 2.0, 0.5):
+        assert ulp_diff(A.pow(e).getRealizationsFloat(), O.op_vs(O.POW, a, e)) <= 1, e
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5, 7, 2047, 2048, 2049, 4097, 65536 + 3])
+def test_ragged_sizes(fc, O, n):
+    rng = np.random.RandomState(n + 1)
+    x = rng.standard_normal(n); y = rng.standard_normal(n)
+    X, Y = fc.RandomVariableCuda(0.0, x), fc.RandomVariableCuda(0.0, y)
+    xf, yf = O.from_f64(x), O.from_f64(y)
+    got = X.mult(Y).add(1.0).sub(X).getRealizationsFloat()
+    want = O.op_vv(O.SUB, O.op_vs(O.ADD, O.op_vv(O.MULT, xf, yf), 1.0), xf)
+    assert bits_equal(got, want)
+    if n > 0:
+        assert abs(X.mult(Y).getAverage() - O.average(O.op_vv(O.MULT, xf, yf))) <= 1e-12 + 1e-9 * abs(O.average(O.op_vv(O.MULT, xf, yf)))
+    else:
+        assert math.isnan(X.getAverage())
+
+
+def test_reductions(fc, O, data):
+    x, y, z = data
+    for src in (x, z, x * 1000.0 + 5000.0):
+        rv = fc.RandomVariableCuda(0.0, src)
+        f = O.from_f64(src)
+        for got, want in ((rv.getAverage(), O.average(f)), (rv.getVariance(), O.variance(f)),
+                          (rv.getSampleVariance(), O.sample_variance(f)),
+                          (rv.getStandardDeviation(), math.sqrt(O.variance(f))),
+                          (rv.getStandardError(), math.sqrt(O.variance(f)) / math.sqrt(N))):
+            assert abs(got - want) <= 1e-5 * abs(want), (got, want)
+            assert abs(got - want) <= 1e-10 * abs(want) + 1e-300, ("tighter than required", got, want)
+        assert rv.getMin() == O.minimum(f) and rv.getMax() == O.maximum(f)
+    X, P = fc.RandomVariableCuda(0.0, x), fc.RandomVariableCuda(0.0, y / N)
+    want = O.average(O.from_f64(x), O.from_f64(y / N))
+    assert abs(X.getAverage(P) - want) <= 1e-10 * abs(want)
+    want = O.variance(O.from_f64(x), O.from_f64(y / N))
+    assert abs(X.getVariance(P) - want) <= 1e-9 * abs(want)
+    # quantiles / histogram (RVF:472-602)
+    for q in (0.0, 0.05, 0.5, 0.95, 1.0):
+        assert X.getQuantile(q) == O.quantile(O.from_f64(x), q)
+    assert abs(X.getQuantileExpectation(0.1, 0.9) - O.quantile_expectation(O.from_f64(x), 0.1, 0.9)) < 1e-12
+    pts = np.linspace(0.1, 0.9, 9)
+    assert np.allclose(X.getHistogram(pts), O.histogram(O.from_f64(x), pts), atol=0, rtol=0)
+
+
+def test_fused_chain_and_lazy_semantics(fc, O, data):
+    x, y, z = data
+    X, Y, Z = (fc.RandomVariableCuda(0.0, v) for v in (x, y, z))
+    xf, yf, zf = O.from_f64(x), O.from_f64(y), O.from_f64(z)
+    before = fc.stats()
+    # Black-Scholes Euler step + payoff chain (MonteCarloBlackScholesModelTest.java:139-144), 7 ops, one getAverage
+    s = X.add(0.005).addProduct(Z, 0.3).exp()
+    payoff = s.sub(1.05).floor(0.0).div(1.1).mult(1.0)
+    got = payoff.getAverage()
+    after = fc.stats()
+    so = O.op_v(O.EXP, O.op_vvs(O.ADDPRODUCT, O.op_vs(O.ADD, xf, 0.005), zf, 0.3))
+    po = O.op_vs(O.MULT, O.op_vs(O.DIV, O.op_vs(O.FLOOR, O.op_vs(O.SUB, so, 1.05), 0.0), 1.1), 1.0)
+    want = O.average(po)
+    assert abs(got - want) <= 1e-6 * abs(want)
+    assert after["n_tape_kernels"] - before["n_tape_kernels"] == 1, "the whole chain + reduction must be ONE kernel"
+    # s is still referenced -> it was stored; payoff (the reduction target) stays pending and is recomputed on demand
+    assert ulp_diff(s.getRealizationsFloat(), so) <= 1
+    assert ulp_diff(payoff.getRealizationsFloat(), po) <= 1
+    # dropping handles of pending nodes frees them without running anything
+    k0 = fc.stats()["n_kernels"]
+    t = X.mult(Y).add(Z).squared()
+    del t
+    assert fc.stats()["n_kernels"] == k0
+    assert fc.stats()["pending_nodes"] == 0
+
+
+def test_long_tape_register_pressure_and_cuts(fc, O, data):
+    """A DAG with many live values (forces the shared-memory register file and HBM spills) and a chain long enough
+    to be cut into several kernels must still be bit-exact."""
+    x, y, z = data
+    n = 20000
+    xs = [np.float32(x[:n] + 0.01 * k) for k in range(24)]
+    X = [fc.RandomVariableCuda(0.0, v) for v in xs]
+    # 24 live intermediates, all consumed at the end
+    inter = [X[k].mult(X[(k + 1) % 24]).add(float(k)) for k in range(24)]
+    inter_o = [O.op_vs(O.ADD, O.op_vv(O.MULT, xs[k], xs[(k + 1) % 24]), float(k)) for k in range(24)]
+    acc = inter[0]; acc_o = inter_o[0]
+    for k in range(1, 24):
+        acc = acc.addProduct(inter[k], inter[(k * 7) % 24]); acc_o = O.op_vvv(O.ADDPRODUCT, acc_o, inter_o[k], inter_o[(k * 7) % 24])
+    del inter
+    assert bits_equal(acc.getRealizationsFloat(), acc_o)
+    # long chain: 3000 ops -> several tapes
+    c = X[0]; co = xs[0]
+    for k in range(1000):
+        c = c.mult(1.0001).add(X[k % 24]).sub(0.5); co = O.op_vs(O.SUB, O.op_vv(O.ADD, O.op_vs(O.MULT, co, 1.0001), xs[k % 24]), 0.5)
+    assert bits_equal(c.getRealizationsFloat(), co)
+
+
+def test_unfused_mode_matches(fc, O, data):
+    x, y, _ = data
+    xf, yf = O.from_f64(x), O.from_f64(y)
+    fc.set_option("fuse", 0)
+    try:
+        k0 = fc.stats()["n_tape_kernels"]
+        X, Y = fc.RandomVariableCuda(0.0, x), fc.RandomVariableCuda(0.0, y)
+        r = X.mult(Y).add(1.0).div(Y)
+        assert fc.stats()["n_tape_kernels"] - k0 == 3        # the reference's execution model: one kernel per op
+        assert bits_equal(r.getRealizationsFloat(), O.op_vv(O.DIV, O.op_vs(O.ADD, O.op_vv(O.MULT, xf, yf), 1.0), yf))
+    finally:
+        fc.set_option("fuse", 1)
+
+
+def test_mt19937_stream_bit_exact(fc, O):
+    from finmath_cuda.brownian_motion import mt19937_raw
+    for mode in (O.SEED_LONG, O.SEED_INT):
+        for seed in (31415, 5489, 1234):
+            got = mt19937_raw(seed, 200_000, mode)
+            assert np.array_equal(got, O.mt_u32(seed, 200_000, mode)), (mode, seed)
+    # deep offsets exercise the jump-ahead polynomials (several chunk bits set)
+    for skip in (1, 623, 624, 32768, 32768 * 5 + 17, 10_000_019):
+        got = mt19937_raw(31415, 5000, O.SEED_LONG, skip)
+        assert np.array_equal(got, O.mt_u32(31415, 5000, O.SEED_LONG, skip)), skip
+    # mt19937ar known answers
+    assert list(mt19937_raw(5489, 3, O.SEED_INT)) == [3499211612, 581869302, 3890346734]
+
+
+@pytest.mark.parametrize("T,F,n,dt", [(100, 1, 5000, 1.0), (80, 1, 10000, 0.5), (40, 6, 4099, 0.5), (3, 2, 7, 0.1), (500, 1, 300, 0.01)])
+def test_brownian_increments_bit_exact(fc, O, T, F, n, dt):
+    td = fc.TimeDiscretization(0.0, T, dt)
+    sqrt_dt = np.array([math.sqrt(td.getTimeStep(t)) for t in range(T)])
+    for seed, mode in ((31415, O.SEED_LONG), (314151, O.SEED_INT)):
+        bm = fc.BrownianMotionCuda(td, F, n, seed, seedMode=mode)
+        want = O.brownian(seed, T, F, n, sqrt_dt, mode)
+        for t in (0, T // 2, T - 1):
+            for f in range(F):
+                inc = bm.getBrownianIncrement(t, f)
+                assert inc.getFiltrationTime() == td.getTime(t + 1)
+                assert bits_equal(inc.getRealizationsFloat(), want[t * F + f]), (T, F, n, t, f)
+
+
+def test_brownian_path_slices_concatenate(fc, O):
+    """Multi-GPU sharding: a rank that owns paths [p0,p1) generates exactly the increments of those paths."""
+    T, F, n = 20, 2, 10007
+    td = fc.TimeDiscretization(0.0, T, 0.25)
+    full = fc.BrownianMotionCuda(td, F, n, 53252)
+    parts = [fc.BrownianMotionCuda(td, F, n, 53252, pathRange=fc.distributed.path_slice(n, r, 4)) for r in range(4)]
+    for t in (0, 7, 19):
+        for f in range(F):
+            whole = full.getBrownianIncrement(t, f).getRealizationsFloat()
+            cat = np.concatenate([p.getBrownianIncrement(t, f).getRealizationsFloat() for p in parts])
+            assert bits_equal(whole, cat)
+
+
+def test_brownian_moments(fc):
+    """BrownianMotionTest.java:66-122: mean within 3*sqrt(dt)/sqrt(n), variance within 3*dt/sqrt(n) (1e6 paths, dt 0.1)."""
+    n, dt = 1_000_000, 0.1
+    bm = fc.BrownianMotionCuda(fc.TimeDiscretization(0.0, 10, dt), 1, n, 1234)
+    inc = bm.getBrownianIncrement(0, 0)
+    assert abs(inc.getAverage()) < 3.0 * math.sqrt(dt) / math.sqrt(n)
+    assert abs(inc.getVariance() - dt) < 3.0 * dt / math.sqrt(n)
+
+
+@pytest.mark.parametrize("k", [3, 6, 8])
+def test_regression_normal_equations(fc, O, data, k):
+    x, y, z = data
+    xf, yf, zf = O.from_f64(x), O.from_f64(y), O.from_f64(z)
+    X, Y, Z = (fc.RandomVariableCuda(0.0, v) for v in (x, y, z))
+    one = fc.RandomVariableCuda(1.0)
+    basis = [one, X, X.squared(), Y, Y.squared(), X.mult(Y), X.pow(3.0), Y.exp()][:k]
+    basis_o = [1.0, xf, O.op_v(O.SQUARED, xf), yf, O.op_v(O.SQUARED, yf), O.op_vv(O.MULT, xf, yf), O.op_vs(O.POW, xf, 3.0), O.op_v(O.EXP, yf)][:k]
+    from finmath_cuda.conditional_expectation import normal_equations
+    XtX, XtY = normal_equations(basis, Z)
+    XtX_o, XtY_o = O.regression_normal_eq(basis_o, zf)
+    assert np.allclose(XtX, XtX_o, rtol=1e-9, atol=1e-14)
+    assert np.allclose(XtY, XtY_o, rtol=1e-9, atol=1e-14)
+    est = fc.MonteCarloConditionalExpectationRegression(basis)
+    c = est.getLinearRegressionParameters(Z)
+    c_o = np.linalg.lstsq(XtX_o, XtY_o, rcond=None)[0]
+    assert np.allclose(c, c_o, rtol=1e-5, atol=1e-8)
+    ce = Z.getConditionalExpectation(est)
+    want = O.op_vs(O.MULT, np.full(N, 1.0, dtype=np.float32), c_o[0]) if False else None
+    # estimate = basis[0]*c0 + sum c_i*basis[i] (float arithmetic); compare against the oracle evaluation of the same chain
+    acc = np.full(N, np.float32(c_o[0]), dtype=np.float32) if np.isscalar(basis_o[0]) else O.op_vs(O.MULT, basis_o[0], c_o[0])
+    for i in range(1, k):
+        acc = O.op_vvs(O.ADDPRODUCT, acc, basis_o[i], c_o[i])
+    got = ce.getRealizationsFloat()
+    assert np.allclose(got, acc, rtol=1e-4, atol=1e-5)
+
+
+def test_size_mismatch_and_bad_handles(fc):
+    a = fc.RandomVariableCuda(0.0, np.arange(10.0))
+    b = fc.RandomVariableCuda(0.0, np.arange(11.0))
+    with pytest.raises(IndexError):
+        a.add(b)
+    with pytest.raises(IndexError):
+        a.get(10)
+
+
+def test_pool_recycles_and_purges(fc):
+    """BrownianMotionMemoryTest.java:40-80 in spirit: many motions of growing size do not exhaust memory, buffers are recycled."""
+    fc.RandomVariableCuda.purge()
+    s0 = fc.stats()
+    for i in range(20):
+        bm = fc.BrownianMotionCuda(fc.TimeDiscretization(0.0, 10, 0.1), 1, 100_000 + 10_000 * i, 53252)
+        inc = bm.getBrownianIncrement(3, 0)
+        assert abs(inc.getVariance() - 0.1) < 5.0 * 0.1 / math.sqrt(100_000)
+        del bm, inc
+    s1 = fc.stats()
+    assert s1["bytes_in_use"] <= s0["bytes_in_use"] + (1 << 20)
+    x = [fc.RandomVariableCuda(0.0, np.zeros(50_000)) for _ in range(8)]
+    del x
+    y = [fc.RandomVariableCuda(0.0, np.zeros(50_000)) for _ in range(8)]
+    s2 = fc.stats()
+    assert s2["n_alloc_reused"] > s1["n_alloc_reused"]
+    del y
+    fc.RandomVariableCuda.purge()
+    assert fc.stats()["bytes_cached"] <= s2["bytes_cached"]
