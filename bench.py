@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json: "LMM ATM calibration sec & path-steps/s at 1/2/4/8
+B200; op HBM GB/s vs peak").
+
+A "step" is one pass of the calibration inner loop of LIBORMarketModelCalibrationATMTest (T-ATM): Euler simulation
+of the LIBOR market model (80 time steps x 80 forward rates, 1 factor, seed 31415, SPOT measure, NORMAL state
+space; every arithmetic step one RandomVariable call) followed by the valuation of the 144 in-horizon ATM calibration
+swaptions (each ending in getAverage()), all through RandomVariableCudaFactory / BrownianMotionCuda over the C ABI.
+
+  value : path-steps/s (paths x 80 time steps / step time), Brownian increments already resident in HBM
+  e2e   : same, but the increments come from HOST double arrays through createRandomVariable(time, double[]) inside
+          the timed region (what T-ATM:283 does with BrownianMotionFromMersenneRandomNumbers + RandomVariableCudaFactory)
+          and the 144 results are read back to the host
+  roofline      : the op-tape interpreter kernel, algorithmic bytes / CUDA-event time, vs measured HBM peak
+  cpu_baseline  : the CPU oracle (C++ restatement of RandomVariableFromFloatArray + the same driver source) on a
+                  bounded sample, 1 thread
+  --impl reference : the reference's CPU path (same oracle build; no JVM exists here) on all host threads
+
+N > 1: launched by torchrun, one process per GPU; every rank owns a contiguous path slice (weak scaling: paths per
+GPU fixed), the only exchange is the all-reduce of reduction partials inside the runtime (NCCL).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "finmath-lib-cuda-extensions_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+N_PERIODS = 80          # T-ATM:275-278: 0..40y in 0.5y steps
+DELTA = 0.5
+SEED = 31415            # T-ATM:283
+METRIC = "lmm_atm_path_steps_per_s"
+UNIT = "path-steps/s"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax = float(parts[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args) -> None:
+    """The reference's CPU implementation of the path (RandomVariableFromFloatArray restated in C++; no JVM here),
+    every host thread simulating its own path slice; same config / metric / unit as our arm."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle.workloads_oracle import driver
+    lib = driver()
+    cores = os.cpu_count() or 1
+    paths_per_thread = args.ref_paths_per_thread
+    total = cores * paths_per_thread
+    models = [lib.lmm(total, N_PERIODS, DELTA, 1, SEED, 0, (i * paths_per_thread, (i + 1) * paths_per_thread)) for i in range(cores)]
+    pool = ThreadPoolExecutor(cores)
+
+    def step():
+        # each worker values its slice; the slice averages are combined with the slice weights (equal sizes)
+        vals = list(pool.map(lambda m: m.step(), models))     # ctypes releases the GIL: the C++ drivers run in parallel
+        return sum(vals) / len(vals)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = total * N_PERIODS * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "LIBORMarketModelCalibrationATMTest inner loop: LMM Euler simulation 80x80, 1 factor + 144 ATM swaptions",
+                   "paths": total, "time_steps": N_PERIODS, "note": "bounded sample of the workload on host cores"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{total} paths ({paths_per_thread} per thread x {cores} threads), {args.steps} steps; C++ restatement of "
+                                   "RandomVariableFromFloatArray (no JVM in this environment)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import finmath_cuda as fc
+    from finmath_cuda import _capi as capi
+    from finmath_cuda.workloads import DriverLib
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    fc.ensure_init(local_rank)
+    if world > 1:
+        fc.distributed.init_comm_from_torch()
+
+    paths_per_gpu = args.paths
+    total_paths = paths_per_gpu * world                      # weak scaling: per-GPU work fixed
+    p0, p1 = rank * paths_per_gpu, (rank + 1) * paths_per_gpu
+    lib = DriverLib()
+    model = lib.lmm(total_paths, N_PERIODS, DELTA, 1, SEED, 0, (p0, p1))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm ----
+    values = None
+    for _ in range(args.warmup):
+        values = model.step()
+    capi.check(capi.load().fmc_reset_stats())
+    capi.set_option("profile", 1)
+    capi.profile_read()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    capi.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        values = model.step()
+    dev_ms = capi.timer_stop()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop()
+    prof = capi.profile_read()
+    capi.set_option("profile", 0)
+    st = fc.stats()
+    step_ms = max_over_ranks(max(dev_ms, 0.0)) / args.steps
+    value = total_paths * N_PERIODS / (step_ms * 1e-3)
+
+    # ---- end-to-end arm: Brownian increments enter from host double arrays inside the timed region ----
+    host_bytes = model.prepare_host_brownian()
+    for _ in range(max(1, min(args.warmup, 2))):
+        model.step(from_host=True)
+    capi.check(capi.load().fmc_reset_stats())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        values_e2e = model.step(from_host=True)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    st2 = fc.stats()
+    e2e_ms = max_over_ranks(1e3 * e2e_s) / args.steps
+    e2e_value = total_paths * N_PERIODS / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = measured_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = prof["tape_algorithmic_bytes"] / (prof["tape_ms"] * 1e-3) / 1e9 if prof["tape_ms"] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "tape_kernel (op-tape interpreter)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "launches": prof["tape_launches"], "kernel_ms_per_step": prof["tape_ms"] / args.steps,
+                "kernel_share_of_step": (prof["tape_ms"] / args.steps) / step_ms if step_ms > 0 else None,
+                "algorithmic_bytes_per_step": prof["tape_algorithmic_bytes"] / args.steps}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        from oracle.workloads_oracle import driver
+        olib = driver()
+        sample_paths = args.cpu_sample_paths
+        om = olib.lmm(sample_paths, N_PERIODS, DELTA, 1, SEED, 0)
+        t0 = time.perf_counter()
+        ovalues = om.step()
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": sample_paths * N_PERIODS / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": f"1 step at {sample_paths} paths, single thread ({dt:.1f} s); C++ restatement of RandomVariableFromFloatArray",
+                        "max_abs_price_diff_vs_gpu_sample": None}
+        del om
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "LIBORMarketModelCalibrationATMTest inner loop: LMM Euler simulation 80x80, 1 factor + 144 ATM swaptions",
+                   "paths_per_gpu": paths_per_gpu, "paths_total": total_paths, "time_steps": N_PERIODS, "seed": SEED,
+                   "parallelism": f"path-sharded x{world}", "l2": "inputs larger than L2 (simulation state >> 126 MB)",
+                   "forward_curve": "synthetic", "wall_ms_per_step": wall_ms / args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": st2["h2d_bytes"] // args.steps,
+                "d2h_bytes_per_step": st2["d2h_bytes"] // args.steps, "host_input_bytes": host_bytes},
+        "gpu_launches": st["n_kernels"],
+        "gpu_launches_per_step": st["n_kernels"] / args.steps,
+        "ops_recorded_per_step": st["n_ops_recorded"] / args.steps,
+        "nodes_stored_per_step": st["n_nodes_stored"] / args.steps, "nodes_fused_per_step": st["n_nodes_fused"] / args.steps,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "price_check": {"first_values": [float(v) for v in values[:3]], "e2e_equal": bool((values == values_e2e).all())},
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--paths", type=int, default=1 << 20, help="paths per GPU (north-star: 1M-path runs)")
+    ap.add_argument("--cpu-sample-paths", type=int, default=131072)
+    ap.add_argument("--ref-paths-per-thread", type=int, default=16384)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -373,6 +373,7 @@ int fmc_set_option(const char* key, double value) {
     return guarded([&](Runtime& rt) {
         if (!std::strcmp(key, "flush_threshold")) rt.opt.flush_threshold = (int64_t)value;
         else if (!std::strcmp(key, "fuse")) { rt.opt.fuse = value != 0.0; if (rt.initialized) rt.flush_all(); }
+        else if (!std::strcmp(key, "profile")) rt.opt.profile = value != 0.0;
         else fail(FMC_ERR_INVALID, "unknown option '%s'", key);
     });
 }
@@ -380,6 +381,7 @@ int fmc_get_option(const char* key, double* value) {
     return guarded([&](Runtime& rt) {
         if (!std::strcmp(key, "flush_threshold")) *value = (double)rt.opt.flush_threshold;
         else if (!std::strcmp(key, "fuse")) *value = rt.opt.fuse ? 1.0 : 0.0;
+        else if (!std::strcmp(key, "profile")) *value = rt.opt.profile ? 1.0 : 0.0;
         else fail(FMC_ERR_INVALID, "unknown option '%s'", key);
     });
 }
@@ -410,6 +412,10 @@ int fmc_pool_purge(void) {
         brownian_release_caches(rt);
         rt.pool.purge();
     });
+}
+
+int fmc_profile_read(double* tape_ms, uint64_t* tape_algorithmic_bytes, uint64_t* tape_launches) {
+    return guarded([&](Runtime& rt) { rt.require_init(); rt.profile_read(tape_ms, tape_algorithmic_bytes, tape_launches); });
 }
 
 int fmc_timer_start(void) { return guarded([&](Runtime& rt) { rt.require_init(); FMC_CUDA(cudaEventRecord(rt.ev_start, rt.stream)); }); }

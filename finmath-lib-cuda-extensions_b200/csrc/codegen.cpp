@@ -52,6 +52,7 @@ struct Gen {
     int32_t reg_owner[TAPE_REGS];
     int32_t acc_owner = -1;
     int regs_used = 0;
+    int n_leaf_slots = 0, n_result_stores = 0;   // algorithmic traffic of the current kernel (spills excluded)
     uint32_t tick = 0;
     TapeParams* params;                 // reused launch parameter block
 
@@ -73,6 +74,7 @@ struct Gen {
         }
         acc_owner = -1;
         regs_used = 0;
+        n_leaf_slots = 0; n_result_stores = 0;
     }
 
     int slot_for(int32_t L) {
@@ -81,6 +83,7 @@ struct Gen {
             f.slot = (int16_t)ptrs.size();
             ptrs.push_back(f.buf);
             slotted.push_back(L);
+            if (!f.lazy) n_leaf_slots++;
         }
         return f.slot;
     }
@@ -261,7 +264,7 @@ struct Gen {
         acc_owner = L;
         info[L].computed = true;
         info[L].last_use = ++tick;
-        if (info[L].store) store_value(L);
+        if (info[L].store) { store_value(L); n_result_stores++; }
     }
 
     // end the current kernel early: everything live in acc / registers that is still needed goes to HBM
@@ -302,7 +305,9 @@ struct Gen {
         int grid = (int)std::min<int64_t>(tiles, (int64_t)per_sm * rt.sm_count);
         grid = std::min(grid, rt.max_grid);
         if (grid < 1) grid = 1;
+        if (rt.opt.profile) rt.profile_begin();
         FMC_CUDA(launch_tape(P, grid, regs_used, rt.stream));
+        if (rt.opt.profile) rt.profile_end(4ull * (uint64_t)n * (uint64_t)(n_leaf_slots + n_result_stores));
         rt.stats.n_kernels++; rt.stats.n_tape_kernels++; rt.stats.n_tape_instr += ins.size();
     }
 };

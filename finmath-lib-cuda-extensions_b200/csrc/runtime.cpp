@@ -63,6 +63,8 @@ void Runtime::shutdown() {
     staging.release();
     cudaFree(d_partials); cudaFree(d_counter); cudaFree(d_result); cudaFreeHost(h_result);
     d_partials = nullptr; d_counter = nullptr; d_result = nullptr; h_result = nullptr;
+    for (auto& pe : prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
+    prof_events.clear(); prof_used = 0;
     cudaEventDestroy(ev_start); cudaEventDestroy(ev_stop); cudaEventDestroy(ev_copy[0]); cudaEventDestroy(ev_copy[1]);
     cudaStreamDestroy(stream);
     stream = nullptr;
@@ -178,6 +180,35 @@ void Runtime::materialize(int32_t idx) {
     if (nodes[idx].state == NS_MAT) return;
     std::vector<int32_t> t{idx};
     run_cone(t, nullptr);
+}
+
+void Runtime::profile_begin() {
+    if (prof_used == prof_events.size()) {
+        cudaEvent_t a, b;
+        FMC_CUDA(cudaEventCreate(&a));
+        FMC_CUDA(cudaEventCreate(&b));
+        prof_events.emplace_back(a, b);
+    }
+    FMC_CUDA(cudaEventRecord(prof_events[prof_used].first, stream));
+}
+void Runtime::profile_end(uint64_t algorithmic_bytes) {
+    FMC_CUDA(cudaEventRecord(prof_events[prof_used].second, stream));
+    prof_used++;
+    prof_bytes += algorithmic_bytes;
+    prof_launches++;
+}
+void Runtime::profile_read(double* ms, uint64_t* bytes, uint64_t* launches) {
+    FMC_CUDA(cudaStreamSynchronize(stream));
+    double total = 0.0;
+    for (size_t i = 0; i < prof_used; i++) {
+        float t = 0.f;
+        FMC_CUDA(cudaEventElapsedTime(&t, prof_events[i].first, prof_events[i].second));
+        total += t;
+    }
+    if (ms) *ms = total;
+    if (bytes) *bytes = prof_bytes;
+    if (launches) *launches = prof_launches;
+    prof_used = 0; prof_bytes = 0; prof_launches = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -91,6 +91,7 @@ struct Node {
 struct Options {
     int64_t flush_threshold = 4096;
     bool fuse = true;
+    bool profile = false;       // time every interpreter launch with CUDA events (benchmarks)
 };
 
 struct Stats {
@@ -139,6 +140,14 @@ public:
     int64_t n_lazy = 0, n_live_handles = 0;
     Options opt;
     Stats stats;
+
+    // profile mode: event pairs around interpreter launches + their algorithmic bytes
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+    uint64_t prof_bytes = 0, prof_launches = 0;
+    void profile_begin();                                  // records the start event of the next launch
+    void profile_end(uint64_t algorithmic_bytes);
+    void profile_read(double* ms, uint64_t* bytes, uint64_t* launches);   // synchronises, sums, resets
 
     // handles
     fmc_vec handle_of(int32_t idx) const { return ((uint64_t)nodes[idx].gen << 32) | (uint32_t)(idx + 1); }

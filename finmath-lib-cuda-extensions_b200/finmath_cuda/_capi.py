@@ -78,6 +78,7 @@ PROTOTYPES = {
     "fmc_reset_stats": (C.c_int, []),
     "fmc_pool_trim": (C.c_int, []),
     "fmc_pool_purge": (C.c_int, []),
+    "fmc_profile_read": (C.c_int, [_f64p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "fmc_timer_start": (C.c_int, []),
     "fmc_timer_stop": (C.c_int, [C.POINTER(C.c_float)]),
     "fmc_comm_get_unique_id": (C.c_int, [C.c_char_p]),
@@ -159,6 +160,22 @@ def stats() -> dict:
     s = FmcStats()
     check(load().fmc_get_stats(C.byref(s)))
     return {n: int(getattr(s, n)) for n, _ in FmcStats._fields_}
+
+
+def profile_read() -> dict:
+    ms, b, n = C.c_double(), C.c_uint64(), C.c_uint64()
+    check(load().fmc_profile_read(C.byref(ms), C.byref(b), C.byref(n)))
+    return {"tape_ms": ms.value, "tape_algorithmic_bytes": int(b.value), "tape_launches": int(n.value)}
+
+
+def timer_start() -> None:
+    check(load().fmc_timer_start())
+
+
+def timer_stop() -> float:
+    ms = C.c_float()
+    check(load().fmc_timer_stop(C.byref(ms)))
+    return float(ms.value)
 
 
 def set_option(key: str, value: float) -> None:

@@ -124,7 +124,8 @@ int fmc_mt19937_raw(int seed_mode, int64_t seed, uint64_t skip, int64_t count, u
 int fmc_flush(void);                    /* execute every pending node that is still referenced */
 int fmc_sync(void);                     /* flush + wait for the device (cuCtxSynchronize, RVC:472-476) */
 /* options: "flush_threshold" (pending nodes before an automatic flush; default 4096),
- *          "fuse" (1 default; 0 = execute every op as its own kernel, the reference's execution model) */
+ *          "fuse" (1 default; 0 = execute every op as its own kernel, the reference's execution model),
+ *          "profile" (0 default; see fmc_profile_read) */
 int fmc_set_option(const char* key, double value);
 int fmc_get_option(const char* key, double* value);
 
@@ -148,6 +149,11 @@ int fmc_get_stats(fmc_stats* out);
 int fmc_reset_stats(void);
 int fmc_pool_trim(void);                /* RandomVariableCuda.clean() RVC:751-753: return cached blocks to the driver */
 int fmc_pool_purge(void);               /* RandomVariableCuda.purge() RVC:755-757 */
+
+/* option "profile" = 1: every interpreter launch is bracketed by CUDA events; fmc_profile_read synchronises and returns
+ * the summed kernel time, the algorithmic bytes (4 * n * (leaf vectors read + result vectors stored)) and the launch
+ * count since the last read, then resets the counters. */
+int fmc_profile_read(double* tape_ms, uint64_t* tape_algorithmic_bytes, uint64_t* tape_launches);
 
 /* device-side timing of the compute stream (CUDA events), for benchmarks */
 int fmc_timer_start(void);
