@@ -410,7 +410,8 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
     // ---- 3. emit ----
     g.begin_kernel();
     for (int32_t L = 0; L < n_cone; L++) {
-        if ((int)g.ins.size() + 24 > TAPE_MAX_INSTR || (int)g.ptrs.size() + 8 > TAPE_MAX_PTRS) g.cut();
+        // margins: one node emits < 16 instructions / < 8 new pointers; a cut spills at most TAPE_REGS + 1 live values
+        if ((int)g.ins.size() + 48 > TAPE_MAX_INSTR || (int)g.ptrs.size() + 28 > TAPE_MAX_PTRS) g.cut();
         g.emit_node(L);
     }
     if (red) {
