@@ -374,6 +374,11 @@ int fmc_set_option(const char* key, double value) {
         if (!std::strcmp(key, "flush_threshold")) rt.opt.flush_threshold = (int64_t)value;
         else if (!std::strcmp(key, "fuse")) { rt.opt.fuse = value != 0.0; if (rt.initialized) rt.flush_all(); }
         else if (!std::strcmp(key, "profile")) rt.opt.profile = value != 0.0;
+        else if (!std::strcmp(key, "ring_max")) rt.opt.ring_max = std::max(1, std::min((int)value, (int)TAPE_MAX_RING));
+        else if (!std::strcmp(key, "ring_min")) rt.opt.ring_min = std::max(1, std::min((int)value, (int)TAPE_MAX_RING));
+        else if (!std::strcmp(key, "target_ctas")) rt.opt.target_ctas = std::max(1, (int)value);
+        else if (!std::strcmp(key, "horizon")) rt.opt.horizon = std::max(0, (int)value);
+        else if (!std::strcmp(key, "pipeline")) rt.opt.pipeline = value != 0.0;
         else fail(FMC_ERR_INVALID, "unknown option '%s'", key);
     });
 }
@@ -382,6 +387,11 @@ int fmc_get_option(const char* key, double* value) {
         if (!std::strcmp(key, "flush_threshold")) *value = (double)rt.opt.flush_threshold;
         else if (!std::strcmp(key, "fuse")) *value = rt.opt.fuse ? 1.0 : 0.0;
         else if (!std::strcmp(key, "profile")) *value = rt.opt.profile ? 1.0 : 0.0;
+        else if (!std::strcmp(key, "ring_max")) *value = rt.opt.ring_max;
+        else if (!std::strcmp(key, "ring_min")) *value = rt.opt.ring_min;
+        else if (!std::strcmp(key, "target_ctas")) *value = rt.opt.target_ctas;
+        else if (!std::strcmp(key, "horizon")) *value = rt.opt.horizon;
+        else if (!std::strcmp(key, "pipeline")) *value = rt.opt.pipeline ? 1.0 : 0.0;
         else fail(FMC_ERR_INVALID, "unknown option '%s'", key);
     });
 }

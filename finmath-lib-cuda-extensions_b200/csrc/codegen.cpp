@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 
 #include "runtime.h"
 
@@ -19,41 +20,60 @@ namespace fmc {
 
 namespace {
 
+constexpr int32_t NO_USE = 0x7fffffff;
+
 struct Info {
     int32_t node;
-    int32_t rem = 0;        // remaining uses (operand slots) inside this flush
-    int32_t uses = 0;       // total uses inside the cone
+    int32_t uses = 0;       // operand slots that read this value inside the flush (+1 for the reduction epilogue)
     int32_t eph_uses = 0;
+    int32_t ubeg = 0, ucur = 0, uend = 0;   // window into Gen::use_list (positions of the consuming nodes, ascending)
     int16_t slot = -1;      // pointer-table slot in the current kernel
     int8_t reg = -1;
     bool lazy = false;      // cone node (to be computed) vs. materialised leaf
     bool store = false, eph = false, computed = false;
+    bool written_here = false;   // its HBM buffer is written by the kernel being built: no TMA read-back before the next kernel
     float* buf = nullptr;   // device buffer (existing for leaves, new for stored / spilled nodes)
-    uint32_t last_use = 0;
 };
 
-uint32_t rev_op(uint32_t op) {
+// ---- abstract accumulator-machine code (before ring scheduling) ----
+enum AKind : uint8_t { K_NONE = 0, K_IMM, K_REG, K_LEAF };
+enum BinOp : uint16_t { B_MOV = 0, B_ADD, B_SUB, B_BUS, B_MUL, B_DIV, B_VID, B_MIN, B_MAX, B_SEL, B_ADDPROD, B_ACCRUE, B_DISCOUNT };
+constexpr uint16_t A_BIN = 0x100;   // AIns::op = A_BIN | BinOp for binary instructions, a plain TapeOp otherwise
+struct AIns {
+    uint16_t op;
+    uint8_t kind;
+    int32_t arg;      // K_REG: register-file slot; K_LEAF: local id of the leaf
+    uint32_t y;       // immediate bits / pointer-table slot
+};
+
+uint32_t f2u(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+
+uint16_t rev_op(uint16_t op) {
     switch (op) {
-    case T_SUB: return T_BUS;
-    case T_BUS: return T_SUB;
-    case T_DIV: return T_VID;
-    case T_VID: return T_DIV;
+    case B_SUB: return B_BUS;
+    case B_BUS: return B_SUB;
+    case B_DIV: return B_VID;
+    case B_VID: return B_DIV;
     default: return op;   // ADD MUL MIN MAX commute
     }
 }
+
+struct OccCache { std::map<std::pair<size_t, bool>, int> blocks; };
 
 struct Gen {
     Runtime& rt;
     int64_t n;
     std::vector<Info> info;
-    std::vector<TapeInstr> ins;
+    std::vector<int32_t> use_list;
+    std::vector<AIns> A;                // abstract code of the kernel being built
     std::vector<float*> ptrs;
-    std::vector<int32_t> slotted;       // locals that own a slot in the current kernel
+    std::vector<int32_t> slotted;       // locals that own a pointer-table slot in the current kernel
+    std::vector<int32_t> written;       // locals whose buffer the current kernel writes
     int32_t reg_owner[TAPE_REGS];
     int32_t acc_owner = -1;
-    int regs_used = 0;
-    int n_leaf_slots = 0, n_result_stores = 0;   // algorithmic traffic of the current kernel (spills excluded)
-    uint32_t tick = 0;
+    int32_t pos = 0;                    // cone position of the node being emitted
+    int regs_used = 0, n_leaf_refs = 0;
+    int n_leaf_slots = 0, n_result_stores = 0;   // algorithmic traffic of the current kernel (spills / re-reads excluded)
     TapeParams* params;                 // reused launch parameter block
 
     Gen(Runtime& r, int64_t n_) : rt(r), n(n_) {
@@ -63,17 +83,25 @@ struct Gen {
     }
 
     bool has_buf(int32_t L) const { return info[L].buf != nullptr; }
+    bool reloadable(int32_t L) const { return info[L].buf != nullptr && !info[L].written_here; }
+    int32_t rem(int32_t L) const { return info[L].uend - info[L].ucur; }
+    int32_t next_use(int32_t L) const { const Info& f = info[L]; return f.ucur < f.uend ? use_list[f.ucur] : NO_USE; }
+    // next use that is not the instruction being built (which consumes `now` operand slots)
+    int32_t next_use_after(int32_t L, int now) const { const Info& f = info[L]; return f.ucur + now < f.uend ? use_list[f.ucur + now] : NO_USE; }
+    bool available(int32_t L) const { return acc_owner == L || info[L].reg >= 0 || reloadable(L); }
 
     void begin_kernel() {
-        ins.clear(); ptrs.clear();
+        A.clear(); ptrs.clear();
         for (int32_t L : slotted) info[L].slot = -1;
         slotted.clear();
+        for (int32_t L : written) info[L].written_here = false;
+        written.clear();
         for (int j = 0; j < TAPE_REGS; j++) {
             if (reg_owner[j] >= 0) info[reg_owner[j]].reg = -1;
             reg_owner[j] = -1;
         }
         acc_owner = -1;
-        regs_used = 0;
+        regs_used = 0; n_leaf_refs = 0;
         n_leaf_slots = 0; n_result_stores = 0;
     }
 
@@ -93,16 +121,21 @@ struct Gen {
         if (!f.buf) f.buf = (float*)rt.pool.alloc(sizeof(float) * (size_t)std::max<int64_t>(n, 1));
     }
 
-    void emit(uint32_t op, uint32_t src, uint32_t idx, float imm = 0.f) { ins.push_back(enc(op, src, idx, imm)); }
+    void emit(uint16_t op, uint8_t kind = K_NONE, int32_t arg = 0, uint32_t y = 0) { A.push_back(AIns{op, kind, arg, y}); }
+    void emit_src(uint16_t binop, int32_t L) {      // binary instruction whose operand is the value L (register file or leaf)
+        const Info& f = info[L];
+        if (f.reg >= 0) emit(A_BIN | binop, K_REG, f.reg);
+        else if (reloadable(L)) { slot_for(L); emit(A_BIN | binop, K_LEAF, L); n_leaf_refs++; }
+        else fail(FMC_ERR_UNSUPPORTED, "internal: operand has no location");
+    }
 
     // write local L (currently in acc or in a register) to its HBM buffer
     void store_value(int32_t L) {
         ensure_buffer(L);
         const int slot = slot_for(L);
-        uint32_t src;
-        if (acc_owner == L) src = S_ACC;
-        else src = S_REG0 + (uint32_t)info[L].reg;
-        ins.push_back(enc_stg((uint32_t)slot, src));
+        if (acc_owner == L) emit(T_STG, K_NONE, 0, (uint32_t)slot);
+        else emit(T_STGS, K_REG, info[L].reg, (uint32_t)slot);
+        if (!info[L].written_here) { info[L].written_here = true; written.push_back(L); }
     }
 
     void free_reg_of(int32_t L) {
@@ -110,23 +143,24 @@ struct Gen {
         if (f.reg >= 0) { reg_owner[f.reg] = -1; f.reg = -1; }
     }
 
-    // find a register; may evict (and, if needed, spill to HBM) a value that is not pinned
     int32_t pins[3] = {-1, -1, -1};      // operands of the instruction being built: never evicted
     void set_pins(int32_t a, int32_t b = -1, int32_t c = -1) { pins[0] = a; pins[1] = b; pins[2] = c; }
 
+    // Find a register-file slot. When all are taken, the value whose next use is farthest away leaves: one that already
+    // has an HBM copy is simply dropped, any other is stored first. Either way it cannot be read back through the TMA
+    // ring inside this kernel (its buffer is written here), so its next use ends the kernel (see emit loop).
     int alloc_reg() {
         for (int j = 0; j < TAPE_REGS; j++) if (reg_owner[j] < 0) { regs_used = std::max(regs_used, j + 1); return j; }
-        int victim = -1;
-        // prefer a value that already has an HBM copy, then the least recently used
-        for (int pass = 0; pass < 2 && victim < 0; pass++) {
-            uint32_t best = 0xffffffffu;
-            for (int j = 0; j < TAPE_REGS; j++) {
-                const int32_t L = reg_owner[j];
-                if (L == pins[0] || L == pins[1] || L == pins[2]) continue;
-                if (pass == 0 && !has_buf(L)) continue;
-                if (info[L].last_use < best) { best = info[L].last_use; victim = j; }
-            }
+        int victim = -1, victim_buf = -1;
+        int32_t far = -1, far_buf = -1;
+        for (int j = 0; j < TAPE_REGS; j++) {
+            const int32_t L = reg_owner[j];
+            if (L == pins[0] || L == pins[1] || L == pins[2]) continue;
+            const int32_t nu = next_use(L);
+            if (nu > far) { far = nu; victim = j; }
+            if (has_buf(L) && nu > far_buf) { far_buf = nu; victim_buf = j; }
         }
+        if (victim_buf >= 0 && far_buf - pos > 32) victim = victim_buf;
         if (victim < 0) fail(FMC_ERR_UNSUPPORTED, "internal: register allocation failed");
         const int32_t L = reg_owner[victim];
         if (!has_buf(L)) store_value(L);        // spill
@@ -137,178 +171,314 @@ struct Gen {
     void put_acc_in_reg() {
         const int32_t L = acc_owner;
         const int j = alloc_reg();
-        emit(T_STR, 0, (uint32_t)j);
+        emit(T_STR, K_REG, j);
         reg_owner[j] = L; info[L].reg = (int8_t)j;
     }
+    bool free_reg_exists() const { for (int j = 0; j < TAPE_REGS; j++) if (reg_owner[j] < 0) return true; return false; }
 
     // the accumulator is about to be overwritten: keep its value if somebody still needs it
     void save_acc() {
         const int32_t L = acc_owner;
         if (L < 0) return;
-        const Info& f = info[L];
-        if (f.rem > 0 && f.reg < 0) {
+        if (rem(L) > 0 && info[L].reg < 0) {
             if (!has_buf(L)) put_acc_in_reg();
-            else {
-                // value is already in HBM: keep a register copy only if one is free
-                for (int j = 0; j < TAPE_REGS; j++) if (reg_owner[j] < 0) { put_acc_in_reg(); break; }
-            }
+            // the value is already in HBM: a register copy pays only for a use that is near
+            else if (next_use(L) - pos < 192 && free_reg_exists()) put_acc_in_reg();
         }
-    }
-
-    void src_of(int32_t L, uint32_t& src, uint32_t& idx) {
-        const Info& f = info[L];
-        idx = 0;
-        if (acc_owner == L) { src = S_ACC; return; }
-        if (f.reg >= 0) { src = S_REG0 + (uint32_t)f.reg; return; }
-        if (!f.buf) fail(FMC_ERR_UNSUPPORTED, "internal: operand has no location");
-        src = S_LEAF; idx = (uint32_t)slot_for(L);
     }
 
     // make acc hold L; `uses_now` operand slots of L are consumed by the instruction being built
     void take_acc(int32_t L, int uses_now) {
         if (acc_owner != L) {
             save_acc();
-            uint32_t src, idx;
-            src_of(L, src, idx);
-            emit(T_MOV, src, idx);
+            emit_src(B_MOV, L);
             acc_owner = L;
         }
-        Info& f = info[L];
-        if (f.rem > uses_now && f.reg < 0 && !has_buf(L)) put_acc_in_reg();
+        const Info& f = info[L];
+        if (rem(L) > uses_now && f.reg < 0) {
+            if (!has_buf(L)) put_acc_in_reg();
+            else if (!reloadable(L) && next_use_after(L, uses_now) - pos < 192 && free_reg_exists()) put_acc_in_reg();
+        }
     }
 
     void consume(int32_t L) {
         Info& f = info[L];
-        f.rem--;
-        f.last_use = ++tick;
-        if (f.rem <= 0) free_reg_of(L);
+        f.ucur++;
+        if (f.ucur >= f.uend) free_reg_of(L);
     }
 
-    void emit_binary(uint32_t op, int32_t A, float immA, int32_t B, float immB) {
+    void emit_binary(uint16_t op, int32_t A_, float immA, int32_t B_, float immB) {
         // choose the operand that sits in (or goes to) the accumulator
-        int32_t X, O; float immO; uint32_t xop;
-        if (A >= 0 && acc_owner == A) { X = A; O = B; immO = immB; xop = op; }
-        else if (B >= 0 && acc_owner == B) { X = B; O = A; immO = immA; xop = rev_op(op); }
-        else if (A >= 0) { X = A; O = B; immO = immB; xop = op; }
-        else { X = B; O = A; immO = immA; xop = rev_op(op); }
-        const int uses_now = (O == X) ? 2 : 1;
+        int32_t X, O; float immO; uint16_t xop;
+        if (A_ >= 0 && acc_owner == A_) { X = A_; O = B_; immO = immB; xop = op; }
+        else if (B_ >= 0 && acc_owner == B_) { X = B_; O = A_; immO = immA; xop = rev_op(op); }
+        else if (A_ >= 0) { X = A_; O = B_; immO = immB; xop = op; }
+        else { X = B_; O = A_; immO = immA; xop = rev_op(op); }
         set_pins(X, O);
-        take_acc(X, uses_now);
-        if (O >= 0) {
-            uint32_t src, idx;
-            src_of(O, src, idx);
-            emit(xop, src, idx);
-        } else {
-            emit(xop, S_IMM, 0, immO);
+        if (O == X) {
+            // both operands are the same value
+            take_acc(X, 2);
+            if (op == B_MUL) emit(T_SQR);
+            else {
+                if (info[X].reg < 0) put_acc_in_reg();
+                emit(A_BIN | xop, K_REG, info[X].reg);
+            }
+            consume(X); consume(X);
+            return;
         }
+        take_acc(X, 1);
+        if (O >= 0) emit_src(xop, O);
+        else emit(A_BIN | xop, K_IMM, 0, f2u(immO));
         consume(X);
         if (O >= 0) consume(O);
     }
 
     void emit_node(int32_t L) {
+        pos = L;
         const Node& nd = rt.nodes[info[L].node];
         auto loc = [&](int k) -> int32_t { return nd.in[k] >= 0 ? rt.nodes[nd.in[k]].local : -1; };
         switch (nd.op) {
-        case N_ADD: emit_binary(T_ADD, loc(0), nd.imm[0], loc(1), nd.imm[1]); break;
-        case N_SUB: emit_binary(T_SUB, loc(0), nd.imm[0], loc(1), nd.imm[1]); break;
-        case N_MUL: emit_binary(T_MUL, loc(0), nd.imm[0], loc(1), nd.imm[1]); break;
-        case N_DIV: emit_binary(T_DIV, loc(0), nd.imm[0], loc(1), nd.imm[1]); break;
-        case N_MIN: emit_binary(T_MIN, loc(0), nd.imm[0], loc(1), nd.imm[1]); break;
-        case N_MAX: emit_binary(T_MAX, loc(0), nd.imm[0], loc(1), nd.imm[1]); break;
+        case N_ADD: emit_binary(B_ADD, loc(0), nd.imm[0], loc(1), nd.imm[1]); break;
+        case N_SUB: emit_binary(B_SUB, loc(0), nd.imm[0], loc(1), nd.imm[1]); break;
+        case N_MUL: emit_binary(B_MUL, loc(0), nd.imm[0], loc(1), nd.imm[1]); break;
+        case N_DIV: emit_binary(B_DIV, loc(0), nd.imm[0], loc(1), nd.imm[1]); break;
+        case N_MIN: emit_binary(B_MIN, loc(0), nd.imm[0], loc(1), nd.imm[1]); break;
+        case N_MAX: emit_binary(B_MAX, loc(0), nd.imm[0], loc(1), nd.imm[1]); break;
         case N_SQRT: case N_EXP: case N_LOG: case N_SIN: case N_COS: case N_ABS: case N_INV: case N_ISNAN: case N_POW: {
-            static const uint32_t map[] = {0, 0, 0, 0, 0, 0, 0, T_SQRT, T_EXP, T_LOG, T_SIN, T_COS, T_ABS, T_INV, T_ISNAN, T_POW};
-            const int32_t A = loc(0);
-            set_pins(A);
-            take_acc(A, 1);
-            emit(map[nd.op], 0, 0, nd.imm[1]);
-            consume(A);
+            static const uint16_t map[] = {0, 0, 0, 0, 0, 0, 0, T_SQRT, T_EXP, T_LOG, T_SIN, T_COS, T_ABS, T_INV, T_ISNAN, T_POW};
+            const int32_t A_ = loc(0);
+            set_pins(A_);
+            take_acc(A_, 1);
+            emit(map[nd.op], K_NONE, 0, f2u(nd.imm[1]));
+            consume(A_);
             break;
         }
         case N_CHOOSE: {
-            const int32_t X = loc(0), A = loc(1), B = loc(2);
-            set_pins(X, A, B);
+            const int32_t X = loc(0), A_ = loc(1), B_ = loc(2);
+            set_pins(X, A_, B_);
             take_acc(X, 1);
-            emit(T_SETP, 0, 0);
+            emit(T_SETP);
             consume(X);
             // acc := A
-            if (A >= 0) {
-                if (acc_owner != A) {
+            if (A_ >= 0) {
+                if (acc_owner != A_) {
                     save_acc();
-                    uint32_t src, idx; src_of(A, src, idx);
-                    emit(T_MOV, src, idx);
-                    acc_owner = A;
+                    emit_src(B_MOV, A_);
+                    acc_owner = A_;
                 }
-                if (info[A].rem > 1 && info[A].reg < 0 && !has_buf(A)) put_acc_in_reg();
+                const int now = (B_ == A_) ? 2 : 1;
+                if (rem(A_) > now && info[A_].reg < 0 && !reloadable(A_)) put_acc_in_reg();
+                else if (B_ == A_ && info[A_].reg < 0 && !reloadable(A_)) put_acc_in_reg();
             } else {
                 save_acc();
-                emit(T_MOV, S_IMM, 0, nd.imm[1]);
+                emit(A_BIN | B_MOV, K_IMM, 0, f2u(nd.imm[1]));
                 acc_owner = -1;
             }
-            if (B >= 0) {
-                uint32_t src, idx; src_of(B, src, idx);
-                emit(T_SEL, src, idx);
+            if (B_ >= 0) {
+                if (B_ == A_) { /* choose(x, a, a) == a */ }
+                else emit_src(B_SEL, B_);
             } else {
-                emit(T_SEL, S_IMM, 0, nd.imm[2]);
+                emit(A_BIN | B_SEL, K_IMM, 0, f2u(nd.imm[2]));
             }
-            if (A >= 0) consume(A);
-            if (B >= 0) consume(B);
+            if (A_ >= 0) consume(A_);
+            if (B_ >= 0) consume(B_);
             break;
         }
         case N_CONST:
             set_pins(-1);
             save_acc();
-            emit(T_MOV, S_IMM, 0, nd.imm[0]);
+            emit(A_BIN | B_MOV, K_IMM, 0, f2u(nd.imm[0]));
             break;
         default: fail(FMC_ERR_UNSUPPORTED, "internal: cannot emit node op %d", (int)nd.op);
         }
         acc_owner = L;
         info[L].computed = true;
-        info[L].last_use = ++tick;
         if (info[L].store) { store_value(L); n_result_stores++; }
+    }
+
+    // every operand of node L can be fetched inside the kernel being built
+    bool operands_available(int32_t L) const {
+        const Node& nd = rt.nodes[info[L].node];
+        for (int k = 0; k < 3; k++) {
+            if (nd.in[k] < 0) continue;
+            if (!available(rt.nodes[nd.in[k]].local)) return false;
+        }
+        return true;
     }
 
     // end the current kernel early: everything live in acc / registers that is still needed goes to HBM
     void cut() {
-        if (acc_owner >= 0 && info[acc_owner].rem > 0 && !has_buf(acc_owner)) store_value(acc_owner);
+        if (acc_owner >= 0 && rem(acc_owner) > 0 && !has_buf(acc_owner)) store_value(acc_owner);
         for (int j = 0; j < TAPE_REGS; j++) {
             const int32_t L = reg_owner[j];
-            if (L >= 0 && info[L].rem > 0 && !has_buf(L)) store_value(L);
+            if (L >= 0 && rem(L) > 0 && !has_buf(L)) store_value(L);
         }
         launch(RM_NONE, 0.0, -1);
         begin_kernel();
     }
 
+    // ---- ring scheduling: abstract code -> tape (see tape_isa.h) ----
+    struct Event { int32_t leaf; std::vector<int32_t> use; size_t k = 0; int slot = -1; bool waited = false; };
+
+    void schedule(int ring_max, bool pipeline, int horizon, std::vector<TapeInstr>& prologue, std::vector<TapeInstr>& body, int& n_ring) {
+        // 1. residency intervals ("events") of every leaf: consecutive uses closer than `horizon` share one TMA copy
+        std::vector<Event> ev;
+        {
+            std::map<int32_t, int> open;    // leaf -> index of its latest event
+            for (int32_t i = 0; i < (int32_t)A.size(); i++) {
+                if (A[i].kind != K_LEAF) continue;
+                const int32_t L = A[i].arg;
+                auto it = open.find(L);
+                if (it != open.end() && i - ev[it->second].use.back() <= horizon) ev[it->second].use.push_back(i);
+                else { Event e; e.leaf = L; e.use.push_back(i); open[L] = (int)ev.size(); ev.push_back(std::move(e)); }
+            }
+        }
+        // events are created in order of their first use; `order` is the queue of events still to be issued
+        std::vector<int> order(ev.size());
+        for (size_t k = 0; k < ev.size(); k++) order[k] = (int)k;
+        size_t q = 0;
+        n_ring = (int)std::min<size_t>((size_t)ring_max, ev.size());
+        const uint32_t R = (uint32_t)n_ring;
+        std::vector<int> slot_ev(R, -1), pro_leaf(R, -1);
+        std::vector<char> loadn_done(R, 0);
+        std::vector<int> ev_at(A.size(), -1);   // instruction -> event it reads
+        auto map_uses = [&](int e) { for (size_t k = ev[e].k; k < ev[e].use.size(); k++) ev_at[ev[e].use[k]] = e; };
+        for (size_t k = 0; k < ev.size(); k++) map_uses((int)k);
+
+        auto issue = [&](std::vector<TapeInstr>& out, int e, int s) {
+            ev[e].slot = s; ev[e].waited = false; slot_ev[s] = e;
+            out.push_back(enc_idx(T_LOAD, (uint32_t)s, (uint32_t)info[ev[e].leaf].slot));
+        };
+        auto refill = [&](int s) {
+            slot_ev[s] = -1;
+            if (q < order.size()) issue(body, order[q++], s);
+            else if (pipeline && pro_leaf[s] >= 0 && !loadn_done[s]) {
+                body.push_back(enc_idx(T_LOADN, (uint32_t)s, (uint32_t)info[pro_leaf[s]].slot));
+                loadn_done[s] = 1;
+            }
+        };
+        // 2. fill the ring: before the first chunk (prologue) when pipelining, else at the top of the body
+        for (uint32_t s = 0; s < R && q < order.size(); s++) {
+            const int e = order[q++];
+            issue(pipeline ? prologue : body, e, (int)s);
+            if (pipeline) pro_leaf[s] = ev[e].leaf;
+        }
+        // 3. walk the code
+        for (int32_t i = 0; i < (int32_t)A.size(); i++) {
+            const AIns& a = A[i];
+            if (a.kind == K_LEAF) {
+                const int e = ev_at[i];
+                if (ev[e].slot < 0) {
+                    // not issued yet and no slot was free in time: take the slot whose occupant is needed last
+                    // (while an event is waiting in the queue every slot is occupied: freed slots are refilled at once)
+                    int vs = -1; int32_t far = -1;
+                    for (uint32_t s = 0; s < R; s++) {
+                        const int o = slot_ev[s];
+                        if (o < 0) continue;
+                        const int32_t nu = ev[o].use[ev[o].k];
+                        if (nu > far) { far = nu; vs = (int)s; }
+                    }
+                    if (vs < 0) fail(FMC_ERR_UNSUPPORTED, "internal: no ring slot to evict");
+                    const int o = slot_ev[vs];
+                    {
+                        if (!ev[o].waited) body.push_back(enc_idx(T_WAIT, (uint32_t)vs, 0));
+                        // the evicted occupant's remaining uses become a new event, queued by its next use
+                        Event rest; rest.leaf = ev[o].leaf;
+                        rest.use.assign(ev[o].use.begin() + (long)ev[o].k, ev[o].use.end());
+                        ev[o].use.resize(ev[o].k);
+                        const int ne = (int)ev.size();
+                        ev.push_back(std::move(rest));
+                        map_uses(ne);
+                        size_t at = q;
+                        while (at < order.size() && ev[order[at]].use[0] < ev[ne].use[0]) at++;
+                        order.insert(order.begin() + (long)at, ne);
+                    }
+                    // e is somewhere in the queue (normally its head): take it out
+                    for (size_t k = q; k < order.size(); k++) if (order[k] == e) { order.erase(order.begin() + (long)k); break; }
+                    issue(body, e, vs);
+                }
+                Event& E = ev[e];
+                const uint32_t fl = E.waited ? 1u : 2u;        // _S / _W
+                E.waited = true;
+                body.push_back(TapeInstr{ (T_BIN0 + 3u * (uint32_t)(a.op & 0xff) + fl) | ((uint32_t)E.slot << TAPE_SLOT_SHIFT), a.y });
+                E.k++;
+                if (E.k >= E.use.size()) refill(E.slot);
+            } else if (a.op & A_BIN) {
+                const uint32_t bop = T_BIN0 + 3u * (uint32_t)(a.op & 0xff);
+                if (a.kind == K_IMM) body.push_back(TapeInstr{ bop, a.y });
+                else body.push_back(TapeInstr{ (bop + 1u) | ((R + (uint32_t)a.arg) << TAPE_SLOT_SHIFT), a.y });
+            } else if (a.op == T_END) {
+                // re-arm whatever prologue slot has not been re-armed yet (only slots that were never freed: none in practice)
+                if (a.kind == K_REG) body.push_back(TapeInstr{ T_END | ((R + (uint32_t)a.arg) << TAPE_SLOT_SHIFT), 1u });
+                else body.push_back(TapeInstr{ T_END, 0u });
+            } else {
+                const uint32_t slot = (a.kind == K_REG) ? R + (uint32_t)a.arg : 0u;
+                body.push_back(TapeInstr{ (uint32_t)a.op | (slot << TAPE_SLOT_SHIFT), a.y });
+            }
+        }
+        if (pipeline) for (uint32_t s = 0; s < R; s++)
+            if (pro_leaf[s] >= 0 && !loadn_done[s]) fail(FMC_ERR_UNSUPPORTED, "internal: ring slot %u not re-armed", s);
+    }
+
     void launch(int reduce_mode, double reduce_param, int32_t weight_local) {
         if (reduce_mode == RM_DOT || reduce_mode == RM_WSQ) {
-            uint32_t src, idx; src_of(weight_local, src, idx);
-            emit(T_END, src, idx);
-        } else emit(T_END, S_IMM, 0);
-        if (ins.size() <= 1 && reduce_mode == RM_NONE) return;   // nothing to do
-        if ((int)ins.size() > TAPE_MAX_INSTR + 1 || (int)ptrs.size() > TAPE_MAX_PTRS)
-            fail(FMC_ERR_UNSUPPORTED, "internal: tape overflow (%zu instr, %zu ptrs)", ins.size(), ptrs.size());
+            // epilogue convention: the VALUE waits in a register-file slot, the WEIGHT sits in acc (so that the ring
+            // slot of the weight leaf is free to be re-armed before T_END)
+            const int32_t V = acc_owner;
+            set_pins(V, weight_local);
+            if (info[V].reg < 0) put_acc_in_reg();
+            const int vreg = info[V].reg;
+            emit_src(B_MOV, weight_local);
+            emit(T_END, K_REG, vreg);
+        } else emit(T_END);
+        if (A.size() <= 1 && reduce_mode == RM_NONE) return;   // nothing to do
+
+        std::vector<TapeInstr> prologue, body;
+        int n_ring = 0;
+        int ring_max = std::max(1, std::min<int>(rt.opt.ring_max, TAPE_MAX_RING));
+        // keep >= target_ctas CTAs resident per SM when the tape needs few slots; long tapes trade occupancy for ring depth
+        {
+            const int budget = (int)(rt.smem_per_sm / 1024) / std::max(1, rt.opt.target_ctas) / TAPE_WARPS - 1;   // slots per warp
+            ring_max = std::min(ring_max, std::max(rt.opt.ring_min, budget - regs_used));
+        }
+        schedule(ring_max, rt.opt.pipeline, rt.opt.horizon, prologue, body, n_ring);
+        const size_t total = prologue.size() + body.size();
+        if (total > (size_t)TAPE_MAX_INSTR + 1 || ptrs.size() > (size_t)TAPE_MAX_PTRS)
+            fail(FMC_ERR_UNSUPPORTED, "internal: tape overflow (%zu instr, %zu ptrs)", total, ptrs.size());
         TapeParams& P = *params;
         P.n = n;
-        P.n_instr = (int)ins.size();
+        P.n_instr = (int)total;
+        P.n_prologue = (int)prologue.size();
+        P.n_ptrs = (int)ptrs.size();
+        P.n_ring = n_ring;
+        P.n_slots = n_ring + regs_used;
         P.reduce_mode = reduce_mode;
         P.reduce_param = reduce_param;
         P.partials = rt.d_partials;
         P.counter = rt.d_counter;
         P.result = rt.d_result;
         std::memcpy(P.ptrs, ptrs.data(), sizeof(float*) * ptrs.size());
-        std::memcpy(P.instr, ins.data(), sizeof(TapeInstr) * ins.size());
-        P.instr[ins.size()] = enc(T_END, S_IMM, 0, 0.f);       // the interpreter prefetches one word ahead
-        const int64_t tiles = (n + TAPE_TILE - 1) / TAPE_TILE;
-        static int blocks_fast = 0, blocks_smem[TAPE_REGS + 1] = {0};
+        if (!prologue.empty()) std::memcpy(P.instr, prologue.data(), sizeof(TapeInstr) * prologue.size());
+        std::memcpy(P.instr + prologue.size(), body.data(), sizeof(TapeInstr) * body.size());
+        P.instr[total] = TapeInstr{ T_END, 0u };                // the interpreter prefetches one word ahead
+        const size_t smem = tape_smem_bytes(P.n_ptrs, P.n_instr, P.n_slots);
+        const bool red = reduce_mode != RM_NONE;
+        static OccCache occ;
         int per_sm;
-        if (regs_used <= TAPE_REGS_FAST) { if (!blocks_fast) blocks_fast = tape_max_blocks_per_sm(regs_used); per_sm = blocks_fast; }
-        else { if (!blocks_smem[regs_used]) blocks_smem[regs_used] = tape_max_blocks_per_sm(regs_used); per_sm = blocks_smem[regs_used]; }
-        int grid = (int)std::min<int64_t>(tiles, (int64_t)per_sm * rt.sm_count);
+        {
+            const auto key = std::make_pair((smem + 1023) / 1024, red);
+            auto it = occ.blocks.find(key);
+            if (it == occ.blocks.end()) it = occ.blocks.emplace(key, tape_max_blocks_per_sm(key.first * 1024, red)).first;
+            per_sm = it->second;
+        }
+        const int64_t chunks = (n + TAPE_CHUNK - 1) / TAPE_CHUNK;
+        int grid = (int)std::min<int64_t>((chunks + TAPE_WARPS - 1) / TAPE_WARPS, (int64_t)per_sm * rt.sm_count);
         grid = std::min(grid, rt.max_grid);
         if (grid < 1) grid = 1;
         if (rt.opt.profile) rt.profile_begin();
-        FMC_CUDA(launch_tape(P, grid, regs_used, rt.stream));
+        FMC_CUDA(launch_tape(P, grid, rt.stream));
         if (rt.opt.profile) rt.profile_end(4ull * (uint64_t)n * (uint64_t)(n_leaf_slots + n_result_stores));
-        rt.stats.n_kernels++; rt.stats.n_tape_kernels++; rt.stats.n_tape_instr += ins.size();
+        rt.stats.n_kernels++; rt.stats.n_tape_kernels++; rt.stats.n_tape_instr += total;
     }
 };
 
@@ -402,19 +572,36 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
             // written to HBM iff somebody can still ask for it after this flush
             f.store = nd.ext_refs > 0 || outside || f.eph_uses > 0;
         }
-        f.rem = f.uses;
     }
     if (!red) for (int32_t t : targets) if (nodes[t].state == NS_LAZY) g.info[nodes[t].local].store = true;
-    for (size_t L = n_cone; L < g.info.size(); L++) g.info[L].rem = g.info[L].uses;
+
+    // use lists: for every value the cone positions of the nodes that read it, one entry per operand slot
+    // (the reduction epilogue counts as position n_cone)
+    {
+        int32_t off = 0;
+        for (Info& f : g.info) { f.ubeg = f.ucur = off; off += f.uses; f.uend = f.ubeg; }
+        g.use_list.assign((size_t)off, 0);
+        auto add_use = [&](int32_t lu, int32_t at) { Info& f = g.info[lu]; g.use_list[(size_t)f.uend++] = at; };
+        for (int32_t L = 0; L < n_cone; L++) {
+            const Node& nd = nodes[cone[L]];
+            for (int k = 0; k < 3; k++) if (nd.in[k] >= 0) add_use(nodes[nd.in[k]].local, L);
+        }
+        if (weight_local >= 0) add_use(weight_local, n_cone);
+        if (target_local >= 0) add_use(target_local, n_cone);
+    }
 
     // ---- 3. emit ----
     g.begin_kernel();
     for (int32_t L = 0; L < n_cone; L++) {
-        // margins: one node emits < 16 instructions / < 8 new pointers; a cut spills at most TAPE_REGS + 1 live values
-        if ((int)g.ins.size() + 48 > TAPE_MAX_INSTR || (int)g.ptrs.size() + 28 > TAPE_MAX_PTRS) g.cut();
+        // margins: one node emits < 16 instructions / < 8 new pointers; a cut stores at most TAPE_REGS + 1 live values;
+        // ring scheduling adds at most two instructions per leaf reference plus two per ring slot
+        if ((int)g.A.size() + 2 * g.n_leaf_refs + 2 * TAPE_MAX_RING + 64 > TAPE_MAX_INSTR || (int)g.ptrs.size() + 28 > TAPE_MAX_PTRS) g.cut();
+        else if (!g.operands_available(L)) g.cut();
         g.emit_node(L);
     }
     if (red) {
+        g.pos = n_cone;
+        if (!g.available(target_local)) g.cut();
         g.set_pins(target_local, weight_local);
         if (g.acc_owner != target_local) g.take_acc(target_local, 1);
         g.launch(red->mode, red->param, weight_local);

@@ -8,9 +8,10 @@
 namespace fmc {
 
 // tape_kernel.cu
-cudaError_t launch_tape(const TapeParams& P, int grid, int regs_used, cudaStream_t stream);
+cudaError_t launch_tape(const TapeParams& P, int grid, cudaStream_t stream);
 cudaError_t tape_kernel_setup();
-int tape_max_blocks_per_sm(int regs_used);
+size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots);   // dynamic shared memory of one CTA
+int tape_max_blocks_per_sm(size_t smem_bytes, bool reduce);
 
 // regression_kernel.cu — fused normal equations: one pass over k basis vectors + y.
 constexpr int REG_MAX_K = 12;

@@ -32,6 +32,7 @@ void Runtime::init(int device_index) {
     FMC_CUDA(cudaGetDeviceProperties(&prop, dev));
     device = dev;
     sm_count = prop.multiProcessorCount;
+    smem_per_sm = prop.sharedMemPerMultiprocessor;
     FMC_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     FMC_CUDA(cudaEventCreate(&ev_start));
     FMC_CUDA(cudaEventCreate(&ev_stop));

@@ -92,6 +92,12 @@ struct Options {
     int64_t flush_threshold = 4096;
     bool fuse = true;
     bool profile = false;       // time every interpreter launch with CUDA events (benchmarks)
+    // interpreter scheduling knobs (see codegen.cpp: Gen::schedule / Gen::launch)
+    int ring_max = TAPE_MAX_RING;   // TMA ring slots per warp, upper bound
+    int ring_min = 4;               // ... lower bound when shared memory is tight
+    int target_ctas = 4;            // CTAs per SM the slot budget aims for
+    int horizon = 96;               // uses of a leaf further apart than this many instructions are separate TMA copies
+    bool pipeline = true;           // cross-chunk prefetch (prologue + T_LOADN)
 };
 
 struct Stats {
@@ -115,6 +121,7 @@ public:
     // lifecycle
     bool initialized = false;
     int device = -1, sm_count = 0;
+    size_t smem_per_sm = 0;
     cudaDeviceProp prop{};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_copy[2] = {nullptr, nullptr};

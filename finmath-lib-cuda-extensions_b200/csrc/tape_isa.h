@@ -1,55 +1,75 @@
 // tape_isa.h — instruction set of the op-tape interpreter (shared by the host code generator and the kernel).
 //
-// Machine model (per path element, E elements per thread):
-//   acc          : accumulator, a real register
-//   r[0..R-1]    : register file, real registers (statically indexed inside every handler)
-//   p            : one predicate (for choose)
-// Instruction word (8 bytes): x = op | src_kind << 8 | idx << 16 ; y = float immediate bits.
-// An instruction first fetches its operand b from `src` (register j, immediate, leaf vector idx, or acc) and
-// then applies op(acc, b). Compound RandomVariable ops (accrue, discount, addProduct, addRatio, subRatio) are
-// expanded at record time into these primitives; every primitive rounds once, exactly like the Java float code.
+// Machine model. One WARP interprets the tape for one chunk of TAPE_CHUNK consecutive paths at a time
+// (lane l owns elements 4l..4l+3 and 128+4l..128+4l+3 of the chunk, i.e. two 128-bit groups), warps are fully
+// independent of each other (no block barrier on the elementwise path):
+//   acc            accumulator, TAPE_E real registers per lane
+//   p              one predicate per element (for choose)
+//   slot[0..S-1]   per-warp shared-memory tiles of TAPE_SLOT_BYTES each.
+//                  slots [0, n_ring)         "ring": destinations of TMA bulk copies (cp.async.bulk) of leaf-vector
+//                                            chunks, each guarded by its own mbarrier; the code generator issues the
+//                                            T_LOAD of a chunk as early as the slot is free, so the copy overlaps the
+//                                            interpretation of earlier instructions (software prefetch, depth n_ring).
+//                                            The prefetch also crosses chunk boundaries: the first instructions of
+//                                            the tape (the "prologue", n_prologue T_LOADs) fill the ring before a
+//                                            warp's first chunk; the body then re-arms each of those slots with
+//                                            T_LOADN (same leaf, the warp's NEXT chunk) as soon as the slot's last
+//                                            occupant has been consumed, so every later chunk starts with its first
+//                                            leaves already in flight or landed.
+//                  slots [n_ring, S)         register file for intermediate values (T_STR writes, *_S reads)
+// Instruction word (8 bytes): x = op | slot_byte_offset (slot * TAPE_SLOT_BYTES, low 10 bits are the opcode);
+//                             y = float immediate bits | pointer-table index | second slot byte offset.
+// Binary opcodes come in three flavours: _I (operand = immediate), _S (operand = slot), _W (operand = ring slot
+// whose TMA copy has not been waited for yet: wait on its mbarrier, then as _S).
+// Every primitive rounds once, exactly like the Java float code; the compound RandomVariable ops (accrue, discount,
+// addProduct) exist as single instructions but still round after every elementary operation (no FMA).
+//
+// The opcode numbering is the index into the interpreter's branch-target table (tape_kernel.cu): keep both in sync.
 #pragma once
 #include <stdint.h>
 
 namespace fmc {
 
-constexpr int TAPE_REGS = 12;         // R: registers the code generator may use (shared-memory register file)
-constexpr int TAPE_REGS_FAST = 4;     // tapes that need <= this many run with the register file in real registers
-constexpr int TAPE_ELEMS = 8;         // E (two float4 per thread)
-constexpr int TAPE_THREADS = 256;
-constexpr int TAPE_TILE = TAPE_THREADS * TAPE_ELEMS;   // 2048 elements per block iteration
-constexpr int TAPE_MAX_INSTR = 1024;
-constexpr int TAPE_MAX_PTRS = 224;
+constexpr int TAPE_E = 8;                              // elements per lane
+constexpr int TAPE_WARPS = 4;                          // warps per CTA
+constexpr int TAPE_THREADS = TAPE_WARPS * 32;
+constexpr int TAPE_CHUNK = 32 * TAPE_E;                // 256 paths per warp iteration
+constexpr int TAPE_SLOT_BYTES = TAPE_CHUNK * 4;        // 1 KB
+constexpr int TAPE_SLOT_SHIFT = 10;
+constexpr int TAPE_MAX_RING = 16;                      // ring slots per warp (mbarriers per warp)
+constexpr int TAPE_REGS = 16;                          // register-file slots the code generator may use
+constexpr int TAPE_MAX_INSTR = 2046;
+constexpr int TAPE_MAX_PTRS = 384;
+
+// binary ops: opcode = T_BIN0 + 3 * k + {0: _I, 1: _S, 2: _W}, k = position in this list
+#define FMC_TAPE_BINOPS(X) X(MOV) X(ADD) X(SUB) X(BUS) X(MUL) X(DIV) X(VID) X(MIN) X(MAX) X(SEL) X(ADDPROD) X(ACCRUE) X(DISCOUNT)
 
 enum TapeOp : uint32_t {
-    T_END = 0,      // src (optional): second operand of a weighted reduction
-    // ops with operand b
-    T_MOV = 1,      // acc = b
-    T_ADD = 2,      // acc = acc + b
-    T_SUB = 3,      // acc = acc - b
-    T_BUS = 4,      // acc = b - acc
-    T_MUL = 5,      // acc = acc * b
-    T_DIV = 6,      // acc = acc / b
-    T_VID = 7,      // acc = b / acc
-    T_MIN = 8,      // acc = Math.min(acc, b)   (NaN propagating, -0 < +0)
-    T_MAX = 9,      // acc = Math.max(acc, b)
-    T_SEL = 10,     // acc = p ? acc : b
-    T_STG = 11,     // out[idx_hi] = b        (idx field = output pointer slot; src in y word, see enc_stg)
-    T_LAST_WITH_SRC = 11,
-    // ops without operand
-    T_STR = 12,     // r[idx] = acc
-    T_SETP = 13,    // p = acc >= 0
-    T_SQRT = 14, T_EXP = 15, T_LOG = 16, T_SIN = 17, T_COS = 18, T_ABS = 19, T_INV = 20, T_ISNAN = 21,
-    T_POW = 22,     // acc = (float) pow((double)acc, (double)imm)
+    T_END = 0,       // slot operand (optional, y != 0): second operand of a weighted reduction
+    T_LOAD = 1,      // ring slot <- ptrs[y][chunk]          (TMA bulk copy, completes on the slot's mbarrier)
+    T_WAIT = 2,      // wait for the ring slot's copy
+    T_STG = 3,       // ptrs[y][chunk] = acc
+    T_STGS = 4,      // ptrs[y][chunk] = slot
+    T_STR = 5,       // slot = acc
+    T_SETP = 6,      // p = acc >= 0
+    T_SQR = 7,       // acc = acc * acc
+    T_SQRT = 8, T_EXP = 9, T_LOG = 10, T_SIN = 11, T_COS = 12, T_ABS = 13, T_INV = 14, T_ISNAN = 15,
+    T_POW = 16,      // acc = (float) pow((double)acc, (double)imm)
+    T_ADDPRODVV = 17,// acc = acc + slot * slot2            (slot2 byte offset in y)
+    T_LOADN = 18,    // ring slot <- ptrs[y][this warp's NEXT chunk]   (cross-chunk prefetch; no-op on the warp's last chunk)
+    T_RESERVED19 = 19,
+#define FMC_X(NAME) T_##NAME##_I, T_##NAME##_S, T_##NAME##_W,
+    FMC_TAPE_BINOPS(FMC_X)
+#undef FMC_X
     T_NUM_OPS
 };
-
-enum TapeSrc : uint32_t {
-    S_IMM = 0,      // b = imm
-    S_LEAF = 1,     // b = ptrs[idx][i]
-    S_ACC = 2,      // b = acc
-    S_REG0 = 3      // b = r[src - S_REG0]
-};
+constexpr uint32_t T_BIN0 = 20;
+// operand semantics of the binary ops (b = operand, s = immediate):
+//   MOV acc = b      ADD acc + b     SUB acc - b     BUS b - acc     MUL acc * b     DIV acc / b     VID b / acc
+//   MIN Math.min(acc, b)   MAX Math.max(acc, b)   (NaN propagating, -0 < +0)      SEL p ? acc : b
+//   ADDPROD  acc + b * s        ACCRUE  acc * (1 + b * s)        DISCOUNT  acc / (1 + b * s)     (_S/_W only)
+static_assert(T_MOV_I == T_BIN0, "binary opcode layout");
+static_assert(T_NUM_OPS == T_BIN0 + 39, "binary opcode layout");
 
 enum ReduceMode : int {
     RM_NONE = 0,
@@ -62,16 +82,19 @@ enum ReduceMode : int {
 
 struct TapeInstr { uint32_t x, y; };
 
-inline TapeInstr enc(uint32_t op, uint32_t src, uint32_t idx, float imm) {
+inline TapeInstr enc_imm(uint32_t op, uint32_t slot, float imm) {
     union { float f; uint32_t u; } c; c.f = imm;
-    return TapeInstr{ op | (src << 8) | (idx << 16), c.u };
+    return TapeInstr{ op | (slot << TAPE_SLOT_SHIFT), c.u };
 }
-// STG needs two indices (output slot and source): slot goes into idx, source kind into src (S_ACC or S_REGj).
-inline TapeInstr enc_stg(uint32_t out_slot, uint32_t src) { return TapeInstr{ T_STG | (src << 8) | (out_slot << 16), 0u }; }
+inline TapeInstr enc_idx(uint32_t op, uint32_t slot, uint32_t idx) { return TapeInstr{ op | (slot << TAPE_SLOT_SHIFT), idx }; }
 
 struct TapeParams {
     long long n;              // elements per vector
-    int n_instr;
+    int n_instr;              // instructions including the final T_END (one more padding word follows)
+    int n_prologue;           // leading T_LOADs executed only before a warp's first chunk; later chunks start behind them
+    int n_ptrs;
+    int n_ring;               // ring slots per warp
+    int n_slots;              // ring + register-file slots per warp
     int reduce_mode;
     double reduce_param;
     double* partials;         // [gridDim.x][4]

@@ -1,0 +1,340 @@
+// fmcuda_emu.cpp — TEST INFRASTRUCTURE, never shipped and never loaded by the product.
+//
+// An instruction-level emulator of the op-tape ISA (finmath-lib-cuda-extensions_b200/csrc/tape_isa.h) plus host
+// stand-ins for the handful of CUDA runtime calls the C++ runtime makes. Linking the product's own host sources
+// (runtime.cpp, pool.cpp, codegen.cpp, capi.cpp, ...) against this file instead of libcudart + the sm_100a kernels
+// yields tests/emu/libfmcuda_emu.so, which exports the same C ABI. It exists for ONE purpose: to check, on a machine
+// without a GPU, that the code generator emits well-formed tapes — every TMA ring slot is armed, waited for and
+// re-armed in a legal order, nothing is read back through the ring that the same launch wrote, cross-chunk
+// prefetches (prologue / T_LOADN) line up with the chunk loop, register-file slots are written before they are
+// read — and that those tapes compute the oracle's values under the documented semantics of each opcode.
+// It is NOT a fallback: the product library has no code path into it, and the GPU tests never load it.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "tape_isa.h"
+
+// ---------------------------------------------------------------------------------------------------------------
+// CUDA runtime stand-ins: "device" memory is host memory, streams are synchronous
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+cudaError_t cudaGetDeviceCount(int* c) { *c = 1; return cudaSuccess; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
+    std::memset(p, 0, sizeof(*p));
+    std::snprintf(p->name, sizeof(p->name), "tape-ISA emulator (no GPU)");
+    p->multiProcessorCount = 148; p->major = 10; p->minor = 0;
+    p->sharedMemPerMultiprocessor = 233472; p->totalGlobalMem = 8ull << 30;
+    return cudaSuccess;
+}
+cudaError_t cudaMalloc(void** p, size_t n) { return posix_memalign(p, 512, n ? n : 1) == 0 ? cudaSuccess : cudaErrorMemoryAllocation; }
+cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
+cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return cudaMalloc(p, n); }
+cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
+cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = 4ull << 30; *t = 8ull << 30; return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)0x1; return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)0x1; return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)0x1; return cudaSuccess; }
+cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulator: tape check failed (see stderr)"; }
+}
+
+namespace fmc {
+
+namespace {
+
+std::string g_emu_error;
+
+struct Check { std::string msg; };
+[[noreturn]] void bad(const char* fmt, int a = 0, int b = 0, int c = 0) {
+    char buf[256]; std::snprintf(buf, sizeof(buf), fmt, a, b, c);
+    throw Check{buf};
+}
+
+float jminf(float a, float b) {      // java.lang.Math.min: NaN propagating, -0 < +0
+    if (a != a) return a;
+    if (b != b) return b;
+    if (a == 0.f && b == 0.f) return (std::signbit(a) || std::signbit(b)) ? -0.f : 0.f;
+    return a < b ? a : b;
+}
+float jmaxf(float a, float b) {
+    if (a != a) return a;
+    if (b != b) return b;
+    if (a == 0.f && b == 0.f) return (std::signbit(a) && std::signbit(b)) ? -0.f : 0.f;
+    return a > b ? a : b;
+}
+float jpow(float x, float e) {       // mirrors f_pow in tape_kernel.cu
+    const double dx = (double)x, de = (double)e;
+    if (de != de) return (float)de;
+    if (de == 0.0) return 1.0f;
+    if (dx != dx) return x;
+    if (std::isinf(de) && std::fabs(dx) == 1.0) return NAN;
+    if (de == 2.0) return x * x;
+    if (de == 1.0) return x;
+    return (float)std::pow(dx, de);
+}
+
+constexpr int C = TAPE_CHUNK;
+
+struct Warp {
+    const TapeParams& P;
+    std::vector<float> slots;                 // [n_slots][C]
+    std::vector<int> issued, waited;          // per ring slot: TMA copies armed / waited for
+    std::vector<char> reg_written;            // per slot: register-file slot holds a value of the current chunk
+    std::vector<long long> slot_chunk;        // chunk the ring slot's (pending or landed) data belongs to
+    std::set<const float*>& stored;           // buffers written by this launch
+    explicit Warp(const TapeParams& p, std::set<const float*>& st)
+        : P(p), slots((size_t)p.n_slots * C, NAN), issued(p.n_ring, 0), waited(p.n_ring, 0), reg_written(p.n_slots, 0),
+          slot_chunk(p.n_ring, -1), stored(st) {}
+
+    void load(uint32_t slot, uint32_t pidx, long long chunk) {
+        if ((int)slot >= P.n_ring) bad("T_LOAD into slot %d outside the ring (n_ring %d)", (int)slot, P.n_ring);
+        if ((int)pidx >= P.n_ptrs) bad("pointer index %d out of range", (int)pidx);
+        if (issued[slot] != waited[slot]) bad("ring slot %d re-armed before its previous copy was waited for", (int)slot);
+        const float* src = P.ptrs[pidx];
+        if (stored.count(src)) bad("TMA read-back of a buffer (ptr %d) written by the same launch", (int)pidx);
+        const long long base = chunk * C;
+        if (base >= P.n) bad("TMA copy of a chunk past the end of the vector");
+        const long long m = std::min<long long>(C, ((P.n - base) + 3) / 4 * 4);
+        std::memcpy(&slots[(size_t)slot * C], src + base, sizeof(float) * (size_t)std::min<long long>(m, P.n - base));
+        issued[slot]++;
+        slot_chunk[slot] = chunk;
+    }
+    void wait(uint32_t slot) {
+        if ((int)slot >= P.n_ring) bad("wait on slot %d outside the ring", (int)slot);
+        if (issued[slot] != waited[slot] + 1) bad("wait on ring slot %d with no copy in flight", (int)slot);
+        waited[slot]++;
+    }
+    const float* read(uint32_t slot, long long chunk) {
+        if ((int)slot >= P.n_slots) bad("slot %d out of range (n_slots %d)", (int)slot, P.n_slots);
+        if ((int)slot < P.n_ring) {
+            if (issued[slot] != waited[slot]) bad("ring slot %d read while its copy is still in flight (missing _W)", (int)slot);
+            if (slot_chunk[slot] != chunk) bad("ring slot %d holds data of another chunk", (int)slot);
+        } else if (!reg_written[slot]) bad("register-file slot %d read before it was written in this chunk", (int)slot);
+        return &slots[(size_t)slot * C];
+    }
+};
+
+struct Partial { double c = 0, s = 0, s2 = 0, mn = 0, mx = 0; };
+
+void run_warp(const TapeParams& P, long long first_chunk, long long stride, std::set<const float*>& stored, Partial& part,
+              std::vector<double>& values /* RM_MOMENTS two-pass */) {
+    const long long n_chunks = (P.n + C - 1) / C;
+    Warp w(P, stored);
+    int ipc0 = 0;
+    for (long long chunk = first_chunk; chunk < n_chunks; chunk += stride) {
+        const long long base = chunk * C;
+        const long long next = chunk + stride;
+        float acc[C]; bool pred[C];
+        for (int e = 0; e < C; e++) { acc[e] = 0.f; pred[e] = false; }
+        std::fill(w.reg_written.begin(), w.reg_written.end(), 0);
+        int pc = ipc0;
+        ipc0 = P.n_prologue;
+        const float* endb = nullptr;
+        for (;; pc++) {
+            if (pc >= P.n_instr) bad("ran off the end of the tape");
+            const TapeInstr in = P.instr[pc];
+            const uint32_t op = in.x & ((1u << TAPE_SLOT_SHIFT) - 1u), slot = in.x >> TAPE_SLOT_SHIFT;
+            float imm; std::memcpy(&imm, &in.y, 4);
+            if (pc < P.n_prologue && op != T_LOAD) bad("prologue instruction %d is not a T_LOAD", pc);
+            if (op == T_END) {
+                if (in.y != 0u) {
+                    if ((int)slot < P.n_ring) bad("T_END reads a ring slot");
+                    endb = w.read(slot, chunk);
+                }
+                break;
+            }
+            if (op >= T_BIN0) {
+                if (op >= T_NUM_OPS) bad("opcode %d out of range", (int)op);
+                const uint32_t k = (op - T_BIN0) / 3u, fl = (op - T_BIN0) % 3u;
+                const float* b = nullptr;
+                if (fl == 2u) { w.wait(slot); b = w.read(slot, chunk); }
+                else if (fl == 1u) b = w.read(slot, chunk);
+                else if (k >= 10u) bad("compound op %d has no immediate-operand form", (int)k);
+                for (int e = 0; e < C; e++) {
+                    const float x = b ? b[e] : imm;
+                    float& a = acc[e];
+                    switch (k) {
+                    case 0: a = x; break;
+                    case 1: a = a + x; break;
+                    case 2: a = a - x; break;
+                    case 3: a = x - a; break;
+                    case 4: a = a * x; break;
+                    case 5: a = a / x; break;
+                    case 6: a = x / a; break;
+                    case 7: a = jminf(a, x); break;
+                    case 8: a = jmaxf(a, x); break;
+                    case 9: a = pred[e] ? a : x; break;
+                    case 10: { const float t = x * imm; a = a + t; break; }
+                    case 11: { float t = x * imm; t = t + 1.0f; a = a * t; break; }
+                    case 12: { float t = x * imm; t = t + 1.0f; a = a / t; break; }
+                    default: bad("binary op %d unknown", (int)k);
+                    }
+                }
+                continue;
+            }
+            switch (op) {
+            case T_LOAD: w.load(slot, in.y, chunk); break;
+            case T_LOADN: if (next < n_chunks) w.load(slot, in.y, next); break;
+            case T_WAIT: w.wait(slot); break;
+            case T_STG: case T_STGS: {
+                if ((int)in.y >= P.n_ptrs) bad("pointer index %d out of range", (int)in.y);
+                const float* v = acc;
+                if (op == T_STGS) { if ((int)slot < P.n_ring) bad("T_STGS from a ring slot"); v = w.read(slot, chunk); }
+                float* dst = P.ptrs[in.y];
+                stored.insert(dst);
+                for (int e = 0; e < C && base + e < P.n; e++) dst[base + e] = v[e];
+                break;
+            }
+            case T_STR:
+                if ((int)slot < P.n_ring || (int)slot >= P.n_slots) bad("T_STR into slot %d outside the register file", (int)slot);
+                std::memcpy(&w.slots[(size_t)slot * C], acc, sizeof(acc));
+                w.reg_written[slot] = 1;
+                break;
+            case T_SETP: for (int e = 0; e < C; e++) pred[e] = acc[e] >= 0.0f; break;
+            case T_SQR: for (int e = 0; e < C; e++) acc[e] = acc[e] * acc[e]; break;
+            case T_SQRT: for (int e = 0; e < C; e++) acc[e] = std::sqrt(acc[e]); break;
+            case T_EXP: for (int e = 0; e < C; e++) acc[e] = (float)std::exp((double)acc[e]); break;
+            case T_LOG: for (int e = 0; e < C; e++) acc[e] = (float)std::log((double)acc[e]); break;
+            case T_SIN: for (int e = 0; e < C; e++) acc[e] = (float)std::sin((double)acc[e]); break;
+            case T_COS: for (int e = 0; e < C; e++) acc[e] = (float)std::cos((double)acc[e]); break;
+            case T_ABS: for (int e = 0; e < C; e++) acc[e] = std::fabs(acc[e]); break;
+            case T_INV: for (int e = 0; e < C; e++) acc[e] = 1.0f / acc[e]; break;
+            case T_ISNAN: for (int e = 0; e < C; e++) acc[e] = (acc[e] != acc[e]) ? 1.0f : 0.0f; break;
+            case T_POW: for (int e = 0; e < C; e++) acc[e] = jpow(acc[e], imm); break;
+            case T_ADDPRODVV: {
+                const float* b = w.read(slot, chunk);
+                const float* c = w.read(in.y >> TAPE_SLOT_SHIFT, chunk);
+                for (int e = 0; e < C; e++) { const float t = b[e] * c[e]; acc[e] = acc[e] + t; }
+                break;
+            }
+            default: bad("opcode %d unknown", (int)op);
+            }
+        }
+        // a T_LOADN'ed slot must be the only kind of copy still in flight, and only if there is a next chunk
+        for (int s = 0; s < P.n_ring; s++) {
+            if (w.issued[s] != w.waited[s]) {
+                if (next >= n_chunks) bad("ring slot %d has a copy in flight when the warp exits", s);
+                if (w.slot_chunk[s] != next) bad("ring slot %d carries a copy of the CURRENT chunk across the chunk boundary", s);
+            }
+        }
+        if (P.reduce_mode != RM_NONE) {
+            for (int e = 0; e < C && base + e < P.n; e++) {
+                const double x = (double)acc[e];
+                switch (P.reduce_mode) {
+                case RM_SUM: part.s += x; break;
+                case RM_MOMENTS: values.push_back(x); break;
+                case RM_MIN: part.mn = part.c == 0 ? x : std::fmin(part.mn, x); if (x != x) part.mn = x; break;
+                case RM_MAX: part.mx = part.c == 0 ? x : std::fmax(part.mx, x); if (x != x) part.mx = x; break;
+                case RM_DOT: if (!endb) bad("RM_DOT without a slot operand on T_END"); part.s += (double)endb[e] * x; break;
+                case RM_WSQ: { if (!endb) bad("RM_WSQ without a slot operand on T_END"); const double d = (double)endb[e] - P.reduce_param; part.s += d * d * x; break; }
+                default: bad("reduce mode %d unknown", P.reduce_mode);
+                }
+                part.c += 1.0;
+            }
+        }
+    }
+}
+
+
+void dump_tape(const TapeParams& P, int grid) {
+    static const char* names[] = {"END", "LOAD", "WAIT", "STG", "STGS", "STR", "SETP", "SQR", "SQRT", "EXP", "LOG", "SIN", "COS", "ABS", "INV",
+                                  "ISNAN", "POW", "ADDPRODVV", "LOADN", "?"};
+    static const char* bins[] = {"MOV", "ADD", "SUB", "BUS", "MUL", "DIV", "VID", "MIN", "MAX", "SEL", "ADDPROD", "ACCRUE", "DISCOUNT"};
+    std::fprintf(stderr, "[tape] n=%lld grid=%d instr=%d prologue=%d ptrs=%d ring=%d slots=%d reduce=%d\n", P.n, grid, P.n_instr, P.n_prologue,
+                 P.n_ptrs, P.n_ring, P.n_slots, P.reduce_mode);
+    for (int i = 0; i < P.n_instr; i++) {
+        const uint32_t op = P.instr[i].x & 1023u, slot = P.instr[i].x >> TAPE_SLOT_SHIFT;
+        float imm; std::memcpy(&imm, &P.instr[i].y, 4);
+        if (op >= T_BIN0) {
+            const uint32_t k = (op - T_BIN0) / 3u, fl = (op - T_BIN0) % 3u;
+            if (fl == 0) std::fprintf(stderr, "  %4d %s_I %g\n", i, bins[k], imm);
+            else std::fprintf(stderr, "  %4d %s_%c s%u%s (imm %g)\n", i, bins[k], fl == 1 ? 'S' : 'W', slot, (int)slot < P.n_ring ? "" : "r", imm);
+        } else std::fprintf(stderr, "  %4d %s s%u y=%u\n", i, names[op < 19 ? op : 19], slot, P.instr[i].y);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_tape(const TapeParams& P, int grid, cudaStream_t) {
+    if (std::getenv("FMC_EMU_DUMP")) dump_tape(P, grid);
+    try {
+        if (P.n_ring < 0 || P.n_ring > TAPE_MAX_RING || P.n_slots < P.n_ring) bad("bad slot counts: ring %d slots %d", P.n_ring, P.n_slots);
+        if (P.n_instr < 1 || P.n_instr > TAPE_MAX_INSTR + 1) bad("bad instruction count %d", P.n_instr);
+        if (P.n_prologue < 0 || P.n_prologue >= P.n_instr) bad("bad prologue length %d", P.n_prologue);
+        if (grid < 1) bad("empty grid");
+        std::set<const float*> stored;
+        Partial part;
+        std::vector<double> values;
+        const long long stride = (long long)grid * TAPE_WARPS;
+        for (long long w = 0; w < stride; w++) run_warp(P, w, stride, stored, part, values);
+        if (P.reduce_mode != RM_NONE) {
+            double v = part.s, m2 = 0.0;
+            if (P.reduce_mode == RM_MIN) v = part.mn;
+            else if (P.reduce_mode == RM_MAX) v = part.mx;
+            else if (P.reduce_mode == RM_MOMENTS) {
+                double s = 0.0; for (double x : values) s += x;
+                const double mean = values.empty() ? 0.0 : s / (double)values.size();
+                for (double x : values) m2 += (x - mean) * (x - mean);
+                v = mean; part.c = (double)values.size();
+            }
+            P.result[0] = part.c; P.result[1] = v; P.result[2] = m2;
+        }
+        return cudaSuccess;
+    } catch (const Check& c) {
+        g_emu_error = c.msg;
+        std::fprintf(stderr, "[tape emulator] ILLEGAL TAPE: %s\n", c.msg.c_str());
+        return cudaErrorLaunchFailure;
+    }
+}
+cudaError_t tape_kernel_setup() { return cudaSuccess; }
+size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots) {
+    size_t s = (size_t)TAPE_WARPS * TAPE_MAX_RING * 8;
+    s += ((size_t)n_ptrs * 8 + 15) & ~(size_t)15;
+    s = (s + ((size_t)n_instr + 1) * 8 + 127) & ~(size_t)127;
+    return s + (size_t)TAPE_WARPS * (size_t)n_slots * TAPE_SLOT_BYTES;
+}
+int tape_max_blocks_per_sm(size_t smem_bytes, bool reduce) {
+    const int by_smem = (int)((233472 - 1024) / (smem_bytes + 1024));
+    return std::max(1, std::min(by_smem, reduce ? 6 : 8));
+}
+
+// the other kernels are not ISA-driven; the emulator gives the regression its plain meaning and declines the rest
+cudaError_t launch_regression(const RegressionParams& P, int, cudaStream_t) {
+    const int k = P.k;
+    std::vector<double> acc((size_t)(k * (k + 1) / 2 + k), 0.0);
+    for (long long p = 0; p < P.n; p++) {
+        float b[REG_MAX_K];
+        for (int i = 0; i < k; i++) b[i] = P.basis[i] ? P.basis[i][p] : P.scalars[i];
+        int t = 0;
+        for (int i = 0; i < k; i++) for (int j = i; j < k; j++, t++) { const float x = b[i] * b[j]; acc[t] += (double)x; }
+        for (int i = 0; i < k; i++, t++) { const float x = P.y[p] * b[i]; acc[t] += (double)x; }
+    }
+    for (size_t t = 0; t < acc.size(); t++) P.result[t] = acc[t];
+    return cudaSuccess;
+}
+int regression_max_blocks_per_sm() { return 1; }
+cudaError_t launch_brownian(const BrownianParams&, cudaStream_t) { return cudaErrorNotSupported; }
+cudaError_t launch_mt_jump(const uint32_t*, const uint32_t*, int, const long long*, uint32_t*, int, cudaStream_t) { return cudaErrorNotSupported; }
+cudaError_t launch_mt_raw(const uint32_t*, const long long*, int, long long, unsigned long long, long long, uint32_t*, cudaStream_t) { return cudaErrorNotSupported; }
+
+}  // namespace fmc
+
+extern "C" const char* fmc_emu_last_tape_error(void) { return fmc::g_emu_error.c_str(); }

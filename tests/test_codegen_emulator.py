@@ -1,0 +1,40 @@
+"""Code-generator check without a GPU: the product's host sources (graph, scheduler, ring/register allocation) are
+linked against the tape-ISA emulator of tests/emu/ and driven through the same C ABI by the GPU parity tests.
+The emulator rejects every tape that arms, waits for, reads or re-arms a TMA ring slot illegally, that reads back a
+buffer the same launch wrote, or that reads a register-file slot before writing it, and it computes each opcode with
+its documented meaning, so value mismatches against the oracle show scheduling errors too.
+(Brownian/MT19937 kernels are not tape-driven and are covered on the GPU only.)"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_LIB = os.path.join(EMU_DIR, "libfmcuda_emu.so")
+
+
+@pytest.fixture(scope="module")
+def emulator():
+    subprocess.check_call(["make", "-s", "-C", EMU_DIR])
+    assert os.path.exists(EMU_LIB)
+    return EMU_LIB
+
+
+def run_parity(emulator, extra_env=None, select="not brownian and not mt19937 and not pool_recycles"):
+    env = dict(os.environ, FMC_TEST_TAPE_EMULATOR=emulator)
+    env.update(extra_env or {})
+    cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider",
+           os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-k", select]
+    r = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+def test_parity_suite_on_the_emulator(emulator):
+    run_parity(emulator)
+
+
+@pytest.mark.parametrize("opts", ["pipeline=0", "ring_max=2,ring_min=1", "ring_max=3,horizon=4", "ring_max=16,target_ctas=1"])
+def test_parity_suite_on_the_emulator_with_scheduler_knobs(emulator, opts):
+    run_parity(emulator, {"FMC_TEST_OPTIONS": opts}, select="compound or ragged or reductions or fused or long_tape or unfused")
