@@ -1,7 +1,9 @@
 // capi.cpp — the extern "C" surface declared in include/fmcuda.h.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 
 #include "runtime.h"
 
@@ -54,7 +56,8 @@ extern "C" {
 
 const char* fmc_last_error(void) { return get_error(); }
 
-int fmc_init(int device_index) { return guarded([&](Runtime& rt) { rt.init(device_index); }); }
+static void fmc_apply_env_options(Runtime& rt);
+int fmc_init(int device_index) { return guarded([&](Runtime& rt) { const bool first = !rt.initialized; rt.init(device_index); if (first) fmc_apply_env_options(rt); }); }
 int fmc_shutdown(void) { return guarded([&](Runtime& rt) { rt.shutdown(); }); }
 int fmc_is_initialized(void) { return Runtime::get().initialized ? 1 : 0; }
 
@@ -369,18 +372,36 @@ int fmc_flush(void) { return guarded([&](Runtime& rt) { rt.require_init(); rt.fl
 int fmc_sync(void) {
     return guarded([&](Runtime& rt) { rt.require_init(); rt.flush_all(); FMC_CUDA(cudaStreamSynchronize(rt.stream)); });
 }
+static void set_option_locked(Runtime& rt, const char* key, double value) {
+    if (!std::strcmp(key, "flush_threshold")) rt.opt.flush_threshold = (int64_t)value;
+    else if (!std::strcmp(key, "fuse")) { rt.opt.fuse = value != 0.0; if (rt.initialized) rt.flush_all(); }
+    else if (!std::strcmp(key, "profile")) rt.opt.profile = value != 0.0;
+    else if (!std::strcmp(key, "ring_max")) rt.opt.ring_max = std::max(1, std::min((int)value, (int)TAPE_MAX_RING));
+    else if (!std::strcmp(key, "ring_min")) rt.opt.ring_min = std::max(1, std::min((int)value, (int)TAPE_MAX_RING));
+    else if (!std::strcmp(key, "target_ctas")) rt.opt.target_ctas = std::max(1, (int)value);
+    else if (!std::strcmp(key, "horizon")) rt.opt.horizon = std::max(0, (int)value);
+    else if (!std::strcmp(key, "pipeline")) rt.opt.pipeline = value != 0.0;
+    else if (!std::strcmp(key, "max_sets")) rt.opt.max_sets = std::max(1, std::min((int)value, 4));
+    else if (!std::strcmp(key, "grid_limit")) rt.opt.grid_limit = std::max(0, (int)value);
+    else fail(FMC_ERR_INVALID, "unknown option '%s'", key);
+}
+// FMC_OPTIONS="key=value,key=value": applied once at fmc_init (tuning experiments without touching the caller)
+static void fmc_apply_env_options(Runtime& rt) {
+    const char* env = std::getenv("FMC_OPTIONS");
+    if (!env) return;
+    std::string s(env);
+    size_t at = 0;
+    while (at < s.size()) {
+        size_t end = s.find(',', at);
+        if (end == std::string::npos) end = s.size();
+        const std::string kv = s.substr(at, end - at);
+        const size_t eq = kv.find('=');
+        if (eq != std::string::npos) set_option_locked(rt, kv.substr(0, eq).c_str(), std::atof(kv.c_str() + eq + 1));
+        at = end + 1;
+    }
+}
 int fmc_set_option(const char* key, double value) {
-    return guarded([&](Runtime& rt) {
-        if (!std::strcmp(key, "flush_threshold")) rt.opt.flush_threshold = (int64_t)value;
-        else if (!std::strcmp(key, "fuse")) { rt.opt.fuse = value != 0.0; if (rt.initialized) rt.flush_all(); }
-        else if (!std::strcmp(key, "profile")) rt.opt.profile = value != 0.0;
-        else if (!std::strcmp(key, "ring_max")) rt.opt.ring_max = std::max(1, std::min((int)value, (int)TAPE_MAX_RING));
-        else if (!std::strcmp(key, "ring_min")) rt.opt.ring_min = std::max(1, std::min((int)value, (int)TAPE_MAX_RING));
-        else if (!std::strcmp(key, "target_ctas")) rt.opt.target_ctas = std::max(1, (int)value);
-        else if (!std::strcmp(key, "horizon")) rt.opt.horizon = std::max(0, (int)value);
-        else if (!std::strcmp(key, "pipeline")) rt.opt.pipeline = value != 0.0;
-        else fail(FMC_ERR_INVALID, "unknown option '%s'", key);
-    });
+    return guarded([&](Runtime& rt) { set_option_locked(rt, key, value); });
 }
 int fmc_get_option(const char* key, double* value) {
     return guarded([&](Runtime& rt) {
@@ -392,6 +413,8 @@ int fmc_get_option(const char* key, double* value) {
         else if (!std::strcmp(key, "target_ctas")) *value = rt.opt.target_ctas;
         else if (!std::strcmp(key, "horizon")) *value = rt.opt.horizon;
         else if (!std::strcmp(key, "pipeline")) *value = rt.opt.pipeline ? 1.0 : 0.0;
+        else if (!std::strcmp(key, "max_sets")) *value = rt.opt.max_sets;
+        else if (!std::strcmp(key, "grid_limit")) *value = rt.opt.grid_limit;
         else fail(FMC_ERR_INVALID, "unknown option '%s'", key);
     });
 }

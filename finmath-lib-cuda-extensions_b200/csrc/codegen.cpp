@@ -11,6 +11,8 @@
 // ("ephemeral" nodes), which is evaluated in registers for the reduction and stays pending.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -435,14 +437,15 @@ struct Gen {
 
         std::vector<TapeInstr> prologue, body;
         int n_ring = 0;
+        // Shared-memory budget of one warp, in 1 KB slots, if target_ctas CTAs are to be resident per SM: short tapes
+        // keep the occupancy high, long ones trade it for ring depth (never below ring_min slots).
+        const size_t est_tables = 8 * (A.size() + 2 * (size_t)n_leaf_refs + 2 * TAPE_MAX_RING + 4) + 8 * ptrs.size() + 256;
+        const long budget_bytes = (long)std::min(rt.smem_per_sm / (size_t)std::max(1, rt.opt.target_ctas), rt.smem_per_cta_max) - 1024 - (long)est_tables;
+        const int slot_budget = (int)std::max<long>(1, budget_bytes / (TAPE_WARPS * TAPE_SLOT_BYTES));
         int ring_max = std::max(1, std::min<int>(rt.opt.ring_max, TAPE_MAX_RING));
-        // keep >= target_ctas CTAs resident per SM when the tape needs few slots; long tapes trade occupancy for ring depth
-        {
-            const int budget = (int)(rt.smem_per_sm / 1024) / std::max(1, rt.opt.target_ctas) / TAPE_WARPS - 1;   // slots per warp
-            ring_max = std::min(ring_max, std::max(rt.opt.ring_min, budget - regs_used));
-        }
+        ring_max = std::min(ring_max, std::max(rt.opt.ring_min, slot_budget - regs_used));
         schedule(ring_max, rt.opt.pipeline, rt.opt.horizon, prologue, body, n_ring);
-        const size_t total = prologue.size() + body.size();
+        const size_t total = prologue.size() + 1 + body.size();
         if (total > (size_t)TAPE_MAX_INSTR + 1 || ptrs.size() > (size_t)TAPE_MAX_PTRS)
             fail(FMC_ERR_UNSUPPORTED, "internal: tape overflow (%zu instr, %zu ptrs)", total, ptrs.size());
         TapeParams& P = *params;
@@ -459,22 +462,39 @@ struct Gen {
         P.result = rt.d_result;
         std::memcpy(P.ptrs, ptrs.data(), sizeof(float*) * ptrs.size());
         if (!prologue.empty()) std::memcpy(P.instr, prologue.data(), sizeof(TapeInstr) * prologue.size());
-        std::memcpy(P.instr + prologue.size(), body.data(), sizeof(TapeInstr) * body.size());
+        P.instr[prologue.size()] = TapeInstr{ T_END, 0u };      // closes the prologue
+        std::memcpy(P.instr + prologue.size() + 1, body.data(), sizeof(TapeInstr) * body.size());
         P.instr[total] = TapeInstr{ T_END, 0u };                // the interpreter prefetches one word ahead
-        const size_t smem = tape_smem_bytes(P.n_ptrs, P.n_instr, P.n_slots);
         const bool red = reduce_mode != RM_NONE;
+        const int64_t chunks = (n + TAPE_CHUNK - 1) / TAPE_CHUNK;
         static OccCache occ;
-        int per_sm;
-        {
-            const auto key = std::make_pair((smem + 1023) / 1024, red);
+        auto blocks_per_sm = [&](size_t smem_bytes) {
+            const auto key = std::make_pair((smem_bytes + 1023) / 1024, red);
             auto it = occ.blocks.find(key);
             if (it == occ.blocks.end()) it = occ.blocks.emplace(key, tape_max_blocks_per_sm(key.first * 1024, red)).first;
-            per_sm = it->second;
+            return it->second;
+        };
+        // slot sets: a tape that leaves most of the budget unused keeps several chunks per warp in flight
+        int n_sets = 1, per_sm = 1, grid = 1;
+        size_t smem = 0;
+        if (rt.opt.pipeline && n_ring > 0) n_sets = std::max(1, std::min(rt.opt.max_sets, slot_budget / std::max(1, P.n_slots)));
+        for (;;) {
+            smem = tape_smem_bytes(P.n_ptrs, P.n_instr, P.n_slots, n_sets);
+            if (smem > rt.smem_per_cta_max && n_sets > 1) { n_sets--; continue; }
+            if (smem > rt.smem_per_cta_max) fail(FMC_ERR_UNSUPPORTED, "internal: tape needs %zu bytes of shared memory per CTA", smem);
+            per_sm = blocks_per_sm(smem);
+            grid = (int)std::min<int64_t>((chunks + TAPE_WARPS - 1) / TAPE_WARPS, (int64_t)per_sm * rt.sm_count);
+            grid = std::max(1, std::min(grid, rt.max_grid));
+            if (rt.opt.grid_limit > 0) grid = std::min(grid, rt.opt.grid_limit);
+            const int64_t chunks_per_warp = (chunks + (int64_t)grid * TAPE_WARPS - 1) / ((int64_t)grid * TAPE_WARPS);
+            if (n_sets > 1 && n_sets > chunks_per_warp) { n_sets = (int)std::max<int64_t>(1, chunks_per_warp); continue; }
+            break;
         }
-        const int64_t chunks = (n + TAPE_CHUNK - 1) / TAPE_CHUNK;
-        int grid = (int)std::min<int64_t>((chunks + TAPE_WARPS - 1) / TAPE_WARPS, (int64_t)per_sm * rt.sm_count);
-        grid = std::min(grid, rt.max_grid);
-        if (grid < 1) grid = 1;
+        P.n_sets = n_sets;
+        static const bool log_tapes = std::getenv("FMC_LOG_TAPES") != nullptr;
+        if (log_tapes)
+            std::fprintf(stderr, "[fmc tape] n=%lld instr=%zu (abstract %zu, prologue %zu) ptrs=%zu leaves=%d stores=%d ring=%d regs=%d sets=%d smem=%zu ctas/sm=%d grid=%d reduce=%d\n",
+                         (long long)n, total, A.size(), prologue.size(), ptrs.size(), n_leaf_slots, n_result_stores, n_ring, regs_used, n_sets, smem, per_sm, grid, reduce_mode);
         if (rt.opt.profile) rt.profile_begin();
         FMC_CUDA(launch_tape(P, grid, rt.stream));
         if (rt.opt.profile) rt.profile_end(4ull * (uint64_t)n * (uint64_t)(n_leaf_slots + n_result_stores));
@@ -490,11 +510,15 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
     if (epoch == 0) { for (auto& nd : nodes) nd.epoch = 0; epoch = 1; }
     stats.n_flushes++;
 
-    // ---- 1. collect the cone of lazy nodes ----
-    std::vector<int32_t> cone, stack;
+    // ---- 1. collect the cone of lazy nodes, in depth-first post-order from the targets ----
+    // Post-order (operands first, each value as late as its first consumer allows) keeps few intermediates alive at a
+    // time: e.g. an Euler step whose caller computed all 80 drifts before applying any of them is emitted component
+    // by component, so the register file holds a handful of values instead of 80.
+    std::vector<int32_t> cone;
+    std::vector<std::pair<int32_t, int>> stack;
     int64_t n = -1;
     for (int32_t t : targets) {
-        Node& nd = nodes[t];
+        const Node& nd = nodes[t];
         if (n < 0) n = nd.n;
         else if (nd.n != n) {
             // targets of different sizes: run them as separate cones
@@ -504,18 +528,23 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
             run_cone(other, red);
             return;
         }
-        if (nd.state == NS_LAZY && nd.epoch != epoch) { nd.epoch = epoch; stack.push_back(t); }
     }
-    while (!stack.empty()) {
-        const int32_t v = stack.back(); stack.pop_back();
-        cone.push_back(v);
-        const Node& nd = nodes[v];
-        for (int k = 0; k < 3; k++) {
-            const int32_t u = nd.in[k];
-            if (u >= 0 && nodes[u].state == NS_LAZY && nodes[u].epoch != epoch) { nodes[u].epoch = epoch; stack.push_back(u); }
+    for (int32_t t : targets) {
+        if (nodes[t].state != NS_LAZY || nodes[t].epoch == epoch) continue;
+        nodes[t].epoch = epoch;
+        stack.emplace_back(t, 0);
+        while (!stack.empty()) {
+            auto& top = stack.back();
+            const int32_t v = top.first;
+            if (top.second < 3) {
+                const int32_t u = nodes[v].in[top.second++];
+                if (u >= 0 && nodes[u].state == NS_LAZY && nodes[u].epoch != epoch) { nodes[u].epoch = epoch; stack.emplace_back(u, 0); }
+            } else {
+                stack.pop_back();
+                cone.push_back(v);
+            }
         }
     }
-    std::sort(cone.begin(), cone.end(), [&](int32_t a, int32_t b) { return nodes[a].seq < nodes[b].seq; });
 
     Gen g(*this, n);
     g.info.reserve(cone.size() * 2 + 4);

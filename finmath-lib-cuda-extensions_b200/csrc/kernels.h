@@ -9,8 +9,8 @@ namespace fmc {
 
 // tape_kernel.cu
 cudaError_t launch_tape(const TapeParams& P, int grid, cudaStream_t stream);
-cudaError_t tape_kernel_setup();
-size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots);   // dynamic shared memory of one CTA
+cudaError_t tape_kernel_setup(size_t* max_smem_per_cta);   // opts the kernel in to the device's full shared memory
+size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots, int n_sets);   // dynamic shared memory of one CTA
 int tape_max_blocks_per_sm(size_t smem_bytes, bool reduce);
 
 // regression_kernel.cu — fused normal equations: one pass over k basis vectors + y.

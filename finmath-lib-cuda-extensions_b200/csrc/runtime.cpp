@@ -1,7 +1,11 @@
 // runtime.cpp — device lifecycle, handles, recording of operations, host<->device copies.
 // (the scheduler / code generator that turns pending nodes into interpreter tapes is in codegen.cpp)
 #include <algorithm>
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <thread>
 
 #include "runtime.h"
 
@@ -38,7 +42,7 @@ void Runtime::init(int device_index) {
     FMC_CUDA(cudaEventCreate(&ev_stop));
     FMC_CUDA(cudaEventCreateWithFlags(&ev_copy[0], cudaEventDisableTiming));
     FMC_CUDA(cudaEventCreateWithFlags(&ev_copy[1], cudaEventDisableTiming));
-    FMC_CUDA(tape_kernel_setup());
+    FMC_CUDA(tape_kernel_setup(&smem_per_cta_max));
     max_grid = sm_count * 8;
     FMC_CUDA(cudaMalloc(&d_partials, sizeof(double) * 128 * (size_t)max_grid));
     FMC_CUDA(cudaMalloc(&d_counter, sizeof(unsigned int) * 4));
@@ -52,6 +56,7 @@ void Runtime::init(int device_index) {
 void Runtime::shutdown() {
     if (!initialized) return;
     cudaStreamSynchronize(stream);
+    staging_busy[0] = staging_busy[1] = false;
     comm_destroy(*this);
     brownian_release_caches(*this);
     for (auto& nd : nodes) {
@@ -214,8 +219,80 @@ void Runtime::profile_read(double* ms, uint64_t* bytes, uint64_t* launches) {
 
 // ---------------------------------------------------------------------------------------------------------
 // host <-> device copies through pinned staging (double buffered, chunked)
+//
+// The (float) cast of createRandomVariable(time, double[]) (RandomVariableCuda.java:768-774) and the widening of
+// getRealizations() (RVC:776-782) are host loops over every element; at 1M paths x 80 vectors they, not PCIe, bound
+// the end-to-end time when run on one core. A small persistent worker pool converts each staging chunk in parallel
+// while the previous chunk's cudaMemcpyAsync is in flight.
 // ---------------------------------------------------------------------------------------------------------
-static constexpr size_t kChunkElems = 4u << 20;   // 16 MiB of floats per staging half
+namespace {
+
+class HostWorkers {
+public:
+    static HostWorkers& get() { static HostWorkers* w = new HostWorkers(); return *w; }   // leaked like Runtime
+    // fn(begin, end) over [0, n) split into contiguous blocks; returns when all blocks are done
+    void parallel_for(int64_t n, const std::function<void(int64_t, int64_t)>& fn) {
+        const int64_t min_block = 1 << 16;
+        const int parts = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)threads_.size() + 1, n / min_block));
+        if (parts <= 1) { fn(0, n); return; }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn; n_ = n; parts_ = parts; next_ = 0; pending_ = parts; gen_++;
+        }
+        cv_.notify_all();
+        work();                                  // the caller takes blocks too
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+private:
+    HostWorkers() {
+        unsigned hc = std::thread::hardware_concurrency();
+        int want = (int)std::min<unsigned>(hc ? hc : 4u, 16u) - 1;
+        if (const char* e = std::getenv("FMC_HOST_THREADS")) want = std::max(0, std::atoi(e) - 1);
+        for (int i = 0; i < want; i++) threads_.emplace_back([this] { loop(); });
+        for (auto& t : threads_) t.detach();
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+            }
+            work();
+        }
+    }
+    void work() {
+        for (;;) {
+            int part; int64_t n; int parts; const std::function<void(int64_t, int64_t)>* fn;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (!fn_ || next_ >= parts_) return;
+                part = next_++; n = n_; parts = parts_; fn = fn_;
+            }
+            const int64_t per = (n + parts - 1) / parts;
+            const int64_t b = std::min<int64_t>(n, per * part), e = std::min<int64_t>(n, b + per);
+            if (b < e) (*fn)(b, e);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int64_t, int64_t)>* fn_ = nullptr;
+    int64_t n_ = 0;
+    int parts_ = 0, next_ = 0, pending_ = 0;
+    uint64_t gen_ = 0;
+};
+
+constexpr size_t kChunkElems = 4u << 20;   // 16 MiB of floats per staging half
+
+}  // namespace
 
 template <typename T>
 static int32_t upload_impl(Runtime& rt, const T* h, int64_t n) {
@@ -225,20 +302,24 @@ static int32_t upload_impl(Runtime& rt, const T* h, int64_t n) {
     rt.staging.ensure(2 * kChunkElems * sizeof(float));
     float* stage[2] = {(float*)rt.staging.host, (float*)rt.staging.host + kChunkElems};
     cudaEvent_t done[2] = {rt.ev_copy[0], rt.ev_copy[1]};
-    bool used[2] = {false, false};
-    int64_t off = 0; int which = 0;
+    int64_t off = 0;
     try {
         while (off < n) {
             const int64_t m = std::min<int64_t>(kChunkElems, n - off);
-            if (used[which]) FMC_CUDA(cudaEventSynchronize(done[which]));
+            const int which = rt.staging_next; rt.staging_next ^= 1;
+            if (rt.staging_busy[which]) { FMC_CUDA(cudaEventSynchronize(done[which])); rt.staging_busy[which] = false; }
             float* s = stage[which];
-            for (int64_t i = 0; i < m; i++) s[i] = (float)h[off + i];      // RandomVariableCuda.java:768-774
+            const T* src = h + off;
+            HostWorkers::get().parallel_for(m, [&](int64_t b, int64_t e) {
+                for (int64_t i = b; i < e; i++) s[i] = (float)src[i];              // RandomVariableCuda.java:768-774
+            });
             FMC_CUDA(cudaMemcpyAsync(dst + off, s, sizeof(float) * (size_t)m, cudaMemcpyHostToDevice, rt.stream));
             FMC_CUDA(cudaEventRecord(done[which], rt.stream));
-            used[which] = true;
-            which ^= 1; off += m;
+            rt.staging_busy[which] = true;
+            off += m;
         }
-        for (int w = 0; w < 2; w++) if (used[w]) FMC_CUDA(cudaEventSynchronize(done[w]));
+        // no wait here: the staging half stays marked busy until its copy's event is seen by the next user, so the
+        // conversion of the next vector overlaps this vector's transfer (the copy is stream-ordered before any kernel)
     } catch (...) {
         rt.release_ext(idx);
         throw;
@@ -249,6 +330,10 @@ static int32_t upload_impl(Runtime& rt, const T* h, int64_t n) {
 int32_t Runtime::upload_f64(const double* h, int64_t n) { return upload_impl(*this, h, n); }
 int32_t Runtime::upload_f32(const float* h, int64_t n) { return upload_impl(*this, h, n); }
 
+void Runtime::staging_quiesce() {
+    for (int w = 0; w < 2; w++) if (staging_busy[w]) { FMC_CUDA(cudaEventSynchronize(ev_copy[w])); staging_busy[w] = false; }
+}
+
 template <typename T>
 static void download_impl(Runtime& rt, int32_t idx, T* h, int64_t n) {
     if (n != rt.nodes[idx].n) fail(FMC_ERR_SIZE, "host buffer has %lld elements, vector has %lld", (long long)n, (long long)rt.nodes[idx].n);
@@ -256,6 +341,7 @@ static void download_impl(Runtime& rt, int32_t idx, T* h, int64_t n) {
     rt.materialize(idx);
     const float* src = rt.nodes[idx].buf;
     rt.staging.ensure(2 * kChunkElems * sizeof(float));
+    rt.staging_quiesce();
     float* stage[2] = {(float*)rt.staging.host, (float*)rt.staging.host + kChunkElems};
     cudaEvent_t done[2] = {rt.ev_copy[0], rt.ev_copy[1]};
     // software pipeline: copy chunk c+1 while widening chunk c
@@ -266,7 +352,9 @@ static void download_impl(Runtime& rt, int32_t idx, T* h, int64_t n) {
         FMC_CUDA(cudaEventSynchronize(done[w]));
         const float* s = stage[w];
         T* d = h + pend_off[w];
-        for (int64_t i = 0; i < pend_m[w]; i++) d[i] = (T)s[i];            // RandomVariableCuda.java:776-782
+        HostWorkers::get().parallel_for(pend_m[w], [&](int64_t b, int64_t e) {
+            for (int64_t i = b; i < e; i++) d[i] = (T)s[i];                        // RandomVariableCuda.java:776-782
+        });
         used[w] = false;
     };
     while (off < n) {

@@ -98,6 +98,8 @@ struct Options {
     int target_ctas = 4;            // CTAs per SM the slot budget aims for
     int horizon = 96;               // uses of a leaf further apart than this many instructions are separate TMA copies
     bool pipeline = true;           // cross-chunk prefetch (prologue + T_LOADN)
+    int max_sets = 1;               // slot sets per warp (cross-chunk prefetch depth), upper bound; measured: >1 costs occupancy and does not pay
+    int grid_limit = 0;             // > 0: cap the interpreter grid (tests: many chunks per warp at small sizes)
 };
 
 struct Stats {
@@ -121,7 +123,7 @@ public:
     // lifecycle
     bool initialized = false;
     int device = -1, sm_count = 0;
-    size_t smem_per_sm = 0;
+    size_t smem_per_sm = 0, smem_per_cta_max = 0;
     cudaDeviceProp prop{};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_copy[2] = {nullptr, nullptr};
@@ -132,6 +134,9 @@ public:
     // memory
     DevicePool pool;
     Staging staging;
+    bool staging_busy[2] = {false, false};   // a host->device copy out of that staging half may still be in flight
+    int staging_next = 0;
+    void staging_quiesce();                  // wait for those copies (before the staging buffer is reused for something else)
     double* d_partials = nullptr;       // reduction scratch
     unsigned int* d_counter = nullptr;
     double* d_result = nullptr;         // [256] doubles

@@ -56,7 +56,7 @@ enum TapeOp : uint32_t {
     T_SQRT = 8, T_EXP = 9, T_LOG = 10, T_SIN = 11, T_COS = 12, T_ABS = 13, T_INV = 14, T_ISNAN = 15,
     T_POW = 16,      // acc = (float) pow((double)acc, (double)imm)
     T_ADDPRODVV = 17,// acc = acc + slot * slot2            (slot2 byte offset in y)
-    T_LOADN = 18,    // ring slot <- ptrs[y][this warp's NEXT chunk]   (cross-chunk prefetch; no-op on the warp's last chunk)
+    T_LOADN = 18,    // ring slot <- ptrs[y][the next chunk that will use this slot set]   (cross-chunk prefetch; no-op near the end)
     T_RESERVED19 = 19,
 #define FMC_X(NAME) T_##NAME##_I, T_##NAME##_S, T_##NAME##_W,
     FMC_TAPE_BINOPS(FMC_X)
@@ -91,7 +91,9 @@ inline TapeInstr enc_idx(uint32_t op, uint32_t slot, uint32_t idx) { return Tape
 struct TapeParams {
     long long n;              // elements per vector
     int n_instr;              // instructions including the final T_END (one more padding word follows)
-    int n_prologue;           // leading T_LOADs executed only before a warp's first chunk; later chunks start behind them
+    int n_prologue;           // leading T_LOADs, closed by a T_END: run once per slot set before the warp's first chunks;
+                              // the body starts at instr[n_prologue + 1]
+    int n_sets;               // slot sets per warp (cross-chunk prefetch depth), see tape_kernel.cu
     int n_ptrs;
     int n_ring;               // ring slots per warp
     int n_slots;              // ring + register-file slots per warp

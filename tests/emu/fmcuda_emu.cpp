@@ -137,23 +137,33 @@ struct Partial { double c = 0, s = 0, s2 = 0, mn = 0, mx = 0; };
 void run_warp(const TapeParams& P, long long first_chunk, long long stride, std::set<const float*>& stored, Partial& part,
               std::vector<double>& values /* RM_MOMENTS two-pass */) {
     const long long n_chunks = (P.n + C - 1) / C;
-    Warp w(P, stored);
-    int ipc0 = 0;
-    for (long long chunk = first_chunk; chunk < n_chunks; chunk += stride) {
+    std::vector<Warp> sets;
+    for (int u = 0; u < P.n_sets; u++) sets.emplace_back(P, stored);
+    if (P.instr[P.n_prologue].x != T_END) bad("prologue is not closed by T_END");
+    // prologue: once per slot set, for the warp's first n_sets chunks
+    for (int u = 0; u < P.n_sets; u++) {
+        const long long chunk = first_chunk + u * stride;
+        if (chunk >= n_chunks) continue;
+        for (int pc = 0; pc < P.n_prologue; pc++) {
+            const TapeInstr in = P.instr[pc];
+            if ((in.x & 1023u) != T_LOAD) bad("prologue instruction %d is not a T_LOAD", pc);
+            sets[u].load(in.x >> TAPE_SLOT_SHIFT, in.y, chunk);
+        }
+    }
+    long long k = 0;
+    for (long long chunk = first_chunk; chunk < n_chunks; chunk += stride, k++) {
+        Warp& w = sets[(size_t)(k % P.n_sets)];
         const long long base = chunk * C;
-        const long long next = chunk + stride;
+        const long long next = chunk + stride * P.n_sets;
         float acc[C]; bool pred[C];
         for (int e = 0; e < C; e++) { acc[e] = 0.f; pred[e] = false; }
         std::fill(w.reg_written.begin(), w.reg_written.end(), 0);
-        int pc = ipc0;
-        ipc0 = P.n_prologue;
         const float* endb = nullptr;
-        for (;; pc++) {
+        for (int pc = P.n_prologue + 1;; pc++) {
             if (pc >= P.n_instr) bad("ran off the end of the tape");
             const TapeInstr in = P.instr[pc];
             const uint32_t op = in.x & ((1u << TAPE_SLOT_SHIFT) - 1u), slot = in.x >> TAPE_SLOT_SHIFT;
             float imm; std::memcpy(&imm, &in.y, 4);
-            if (pc < P.n_prologue && op != T_LOAD) bad("prologue instruction %d is not a T_LOAD", pc);
             if (op == T_END) {
                 if (in.y != 0u) {
                     if ((int)slot < P.n_ring) bad("T_END reads a ring slot");
@@ -163,15 +173,15 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
             }
             if (op >= T_BIN0) {
                 if (op >= T_NUM_OPS) bad("opcode %d out of range", (int)op);
-                const uint32_t k = (op - T_BIN0) / 3u, fl = (op - T_BIN0) % 3u;
+                const uint32_t kk = (op - T_BIN0) / 3u, fl = (op - T_BIN0) % 3u;
                 const float* b = nullptr;
                 if (fl == 2u) { w.wait(slot); b = w.read(slot, chunk); }
                 else if (fl == 1u) b = w.read(slot, chunk);
-                else if (k >= 10u) bad("compound op %d has no immediate-operand form", (int)k);
+                else if (kk >= 10u) bad("compound op %d has no immediate-operand form", (int)kk);
                 for (int e = 0; e < C; e++) {
                     const float x = b ? b[e] : imm;
                     float& a = acc[e];
-                    switch (k) {
+                    switch (kk) {
                     case 0: a = x; break;
                     case 1: a = a + x; break;
                     case 2: a = a - x; break;
@@ -185,7 +195,7 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
                     case 10: { const float t = x * imm; a = a + t; break; }
                     case 11: { float t = x * imm; t = t + 1.0f; a = a * t; break; }
                     case 12: { float t = x * imm; t = t + 1.0f; a = a / t; break; }
-                    default: bad("binary op %d unknown", (int)k);
+                    default: bad("binary op %d unknown", (int)kk);
                     }
                 }
                 continue;
@@ -228,10 +238,10 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
             default: bad("opcode %d unknown", (int)op);
             }
         }
-        // a T_LOADN'ed slot must be the only kind of copy still in flight, and only if there is a next chunk
+        // only T_LOADN'ed copies (for the chunk that uses this slot set next) may still be in flight
         for (int s = 0; s < P.n_ring; s++) {
             if (w.issued[s] != w.waited[s]) {
-                if (next >= n_chunks) bad("ring slot %d has a copy in flight when the warp exits", s);
+                if (next >= n_chunks) bad("ring slot %d has a copy in flight when the warp is done with its slot set", s);
                 if (w.slot_chunk[s] != next) bad("ring slot %d carries a copy of the CURRENT chunk across the chunk boundary", s);
             }
         }
@@ -252,7 +262,6 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
         }
     }
 }
-
 
 void dump_tape(const TapeParams& P, int grid) {
     static const char* names[] = {"END", "LOAD", "WAIT", "STG", "STGS", "STR", "SETP", "SQR", "SQRT", "EXP", "LOG", "SIN", "COS", "ABS", "INV",
@@ -278,8 +287,10 @@ cudaError_t launch_tape(const TapeParams& P, int grid, cudaStream_t) {
     try {
         if (P.n_ring < 0 || P.n_ring > TAPE_MAX_RING || P.n_slots < P.n_ring) bad("bad slot counts: ring %d slots %d", P.n_ring, P.n_slots);
         if (P.n_instr < 1 || P.n_instr > TAPE_MAX_INSTR + 1) bad("bad instruction count %d", P.n_instr);
-        if (P.n_prologue < 0 || P.n_prologue >= P.n_instr) bad("bad prologue length %d", P.n_prologue);
+        if (P.n_prologue < 0 || P.n_prologue + 1 >= P.n_instr) bad("bad prologue length %d", P.n_prologue);
+        if (P.n_sets < 1 || P.n_sets > 4) bad("bad slot-set count %d", P.n_sets);
         if (grid < 1) bad("empty grid");
+        if (tape_smem_bytes(P.n_ptrs, P.n_instr, P.n_slots, P.n_sets) > 232448 - 1024) bad("shared memory of one CTA exceeds the device limit");
         std::set<const float*> stored;
         Partial part;
         std::vector<double> values;
@@ -304,12 +315,12 @@ cudaError_t launch_tape(const TapeParams& P, int grid, cudaStream_t) {
         return cudaErrorLaunchFailure;
     }
 }
-cudaError_t tape_kernel_setup() { return cudaSuccess; }
-size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots) {
-    size_t s = (size_t)TAPE_WARPS * TAPE_MAX_RING * 8;
+cudaError_t tape_kernel_setup(size_t* m) { if (m) *m = 232448 - 1024; return cudaSuccess; }
+size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots, int n_sets) {
+    size_t s = (size_t)TAPE_WARPS * (size_t)n_sets * TAPE_MAX_RING * 8;
     s += ((size_t)n_ptrs * 8 + 15) & ~(size_t)15;
     s = (s + ((size_t)n_instr + 1) * 8 + 127) & ~(size_t)127;
-    return s + (size_t)TAPE_WARPS * (size_t)n_slots * TAPE_SLOT_BYTES;
+    return s + (size_t)TAPE_WARPS * (size_t)n_sets * (size_t)n_slots * TAPE_SLOT_BYTES;
 }
 int tape_max_blocks_per_sm(size_t smem_bytes, bool reduce) {
     const int by_smem = (int)((233472 - 1024) / (smem_bytes + 1024));
@@ -331,8 +342,21 @@ cudaError_t launch_regression(const RegressionParams& P, int, cudaStream_t) {
     return cudaSuccess;
 }
 int regression_max_blocks_per_sm() { return 1; }
-cudaError_t launch_brownian(const BrownianParams&, cudaStream_t) { return cudaErrorNotSupported; }
-cudaError_t launch_mt_jump(const uint32_t*, const uint32_t*, int, const long long*, uint32_t*, int, cudaStream_t) { return cudaErrorNotSupported; }
+// FMC_EMU_FAKE_BROWNIAN=1 (tape-shape studies of the workload drivers only): increments from a throw-away generator,
+// NOT the MT19937 stream — the Brownian parity tests are never run against the emulator.
+static bool fake_brownian() { return std::getenv("FMC_EMU_FAKE_BROWNIAN") != nullptr; }
+cudaError_t launch_brownian(const BrownianParams& P, cudaStream_t) {
+    if (!fake_brownian()) return cudaErrorNotSupported;
+    uint64_t s = 0x9E3779B97F4A7C15ull;
+    for (int v = 0; v < P.T * P.F; v++)
+        for (long long p = 0; p < P.np; p++) {
+            double u = 0.0;
+            for (int k = 0; k < 12; k++) { s = s * 6364136223846793005ull + 1442695040888963407ull; u += (double)(s >> 11) * (1.0 / 9007199254740992.0); }
+            P.out[v][p] = (float)((u - 6.0) * P.sqrt_dt[v / P.F]);
+        }
+    return cudaSuccess;
+}
+cudaError_t launch_mt_jump(const uint32_t*, const uint32_t*, int, const long long*, uint32_t*, int, cudaStream_t) { return fake_brownian() ? cudaSuccess : cudaErrorNotSupported; }
 cudaError_t launch_mt_raw(const uint32_t*, const long long*, int, long long, unsigned long long, long long, uint32_t*, cudaStream_t) { return cudaErrorNotSupported; }
 
 }  // namespace fmc

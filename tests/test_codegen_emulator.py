@@ -35,6 +35,7 @@ def test_parity_suite_on_the_emulator(emulator):
     run_parity(emulator)
 
 
-@pytest.mark.parametrize("opts", ["pipeline=0", "ring_max=2,ring_min=1", "ring_max=3,horizon=4", "ring_max=16,target_ctas=1"])
+@pytest.mark.parametrize("opts", ["pipeline=0", "ring_max=2,ring_min=1", "ring_max=3,horizon=4", "ring_max=16,target_ctas=1",
+                                  "grid_limit=1", "grid_limit=3,max_sets=2", "grid_limit=2,max_sets=3,ring_max=2,ring_min=1"])
 def test_parity_suite_on_the_emulator_with_scheduler_knobs(emulator, opts):
     run_parity(emulator, {"FMC_TEST_OPTIONS": opts}, select="compound or ragged or reductions or fused or long_tape or unfused")

@@ -227,6 +227,42 @@ def test_long_tape_register_pressure_and_cuts(fc, O, data):
     assert bits_equal(c.getRealizationsFloat(), co)
 
 
+SCHED_DEFAULTS = {"ring_max": 16, "ring_min": 4, "target_ctas": 4, "horizon": 96, "pipeline": 1, "max_sets": 1, "grid_limit": 0}
+
+
+@pytest.mark.parametrize("opts", [
+    {"grid_limit": 1}, {"grid_limit": 3, "max_sets": 2}, {"grid_limit": 2, "max_sets": 3, "ring_max": 2, "ring_min": 1},
+    {"grid_limit": 5, "pipeline": 0}, {"ring_max": 3, "horizon": 4, "grid_limit": 7}, {"ring_max": 16, "target_ctas": 1, "grid_limit": 4},
+    {"max_sets": 1, "grid_limit": 2}])
+def test_interpreter_scheduling_variants_bit_exact(fc, O, data, opts):
+    """Same tapes under different ring depths, slot-set counts (cross-chunk prefetch depth), pipelining on/off and grids
+    small enough that every warp walks many chunks (prologue / T_LOADN / ragged last chunk): results must not move."""
+    x, y, z = data
+    n = 77_777
+    xs = [np.float32(v[:n]) for v in (x, y, z)] + [np.float32(x[:n] * 0.5 + 0.25 * k) for k in range(9)]
+    try:
+        for k_, v_ in opts.items():
+            fc.set_option(k_, v_)
+        V = [fc.RandomVariableCuda(0.0, v) for v in xs]
+        # many leaves through a small ring, a leaf reused far apart, two stored results and a fused weighted reduction
+        acc = V[0].mult(V[1]); acc_o = O.op_vv(O.MULT, xs[0], xs[1])
+        for k in range(2, 12):
+            acc = acc.addProduct(V[k], 0.5).sub(V[(k * 5) % 12]); acc_o = O.op_vv(O.SUB, O.op_vvs(O.ADDPRODUCT, acc_o, xs[k], 0.5), xs[(k * 5) % 12])
+        side = acc.mult(V[0]).floor(0.0); side_o = O.op_vs(O.FLOOR, O.op_vv(O.MULT, acc_o, xs[0]), 0.0)
+        got_avg = acc.getAverage(V[2].abs())
+        want_avg = O.average(acc_o, O.op_v(O.ABS, xs[2]))
+        assert bits_equal(acc.getRealizationsFloat(), acc_o)
+        assert bits_equal(side.getRealizationsFloat(), side_o)
+        assert abs(got_avg - want_avg) <= 1e-6 * max(1.0, abs(want_avg))
+        for red, ored in (("getAverage", O.average), ("getVariance", O.variance), ("getMin", O.minimum), ("getMax", O.maximum)):
+            got = getattr(side, red)()
+            want = ored(side_o)
+            assert abs(got - want) <= 1e-5 * max(abs(want), 1e-30), (red, got, want)
+    finally:
+        for k_, v_ in SCHED_DEFAULTS.items():
+            fc.set_option(k_, v_)
+
+
 def test_unfused_mode_matches(fc, O, data):
     x, y, _ = data
     xf, yf = O.from_f64(x), O.from_f64(y)
