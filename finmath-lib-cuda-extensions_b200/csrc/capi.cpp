@@ -383,6 +383,8 @@ static void set_option_locked(Runtime& rt, const char* key, double value) {
     else if (!std::strcmp(key, "pipeline")) rt.opt.pipeline = value != 0.0;
     else if (!std::strcmp(key, "max_sets")) rt.opt.max_sets = std::max(1, std::min((int)value, 4));
     else if (!std::strcmp(key, "grid_limit")) rt.opt.grid_limit = std::max(0, (int)value);
+    else if (!std::strcmp(key, "fuse_ops")) rt.opt.fuse_ops = value != 0.0;
+    else if (!std::strcmp(key, "cta_warps")) rt.opt.cta_warps = (int)value == 2 ? 2 : 4;
     else fail(FMC_ERR_INVALID, "unknown option '%s'", key);
 }
 // FMC_OPTIONS="key=value,key=value": applied once at fmc_init (tuning experiments without touching the caller)
@@ -415,6 +417,8 @@ int fmc_get_option(const char* key, double* value) {
         else if (!std::strcmp(key, "pipeline")) *value = rt.opt.pipeline ? 1.0 : 0.0;
         else if (!std::strcmp(key, "max_sets")) *value = rt.opt.max_sets;
         else if (!std::strcmp(key, "grid_limit")) *value = rt.opt.grid_limit;
+        else if (!std::strcmp(key, "fuse_ops")) *value = rt.opt.fuse_ops ? 1.0 : 0.0;
+        else if (!std::strcmp(key, "cta_warps")) *value = rt.opt.cta_warps;
         else fail(FMC_ERR_INVALID, "unknown option '%s'", key);
     });
 }

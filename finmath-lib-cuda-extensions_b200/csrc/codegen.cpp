@@ -60,7 +60,7 @@ uint16_t rev_op(uint16_t op) {
     }
 }
 
-struct OccCache { std::map<std::pair<size_t, bool>, int> blocks; };
+struct OccCache { std::map<std::pair<size_t, int>, int> blocks; };
 
 struct Gen {
     Runtime& rt;
@@ -319,6 +319,52 @@ struct Gen {
         begin_kernel();
     }
 
+    // ---- peephole fusion on the abstract code: every dispatch costs ~18 issue slots, so fewer, fatter instructions ----
+    //   MUL_I a ; ADD_I b                      -> MULADD_II a, b          (two roundings, like the pair)
+    //   ADD_S r ; STR r                         -> ACCUM_S r               (running sum kept in the register file)
+    //   STR t ; MOV x ; MUL_I a ; ADD_S t       -> ADDPROD x, a            (t dead afterwards; float add commutes exactly)
+    bool reg_dead_after(size_t from, int reg) const {
+        for (size_t i = from; i < A.size(); i++) {
+            const AIns& a = A[i];
+            if (a.op == T_STR && a.kind == K_REG && a.arg == reg) return true;        // overwritten before any read
+            if (a.kind == K_REG && a.arg == reg) return false;                        // read (binary operand, STGS, ACCUM, END)
+        }
+        return true;
+    }
+    void peephole() {
+        std::vector<AIns> out;
+        out.reserve(A.size());
+        int leaf_refs = 0;
+        for (size_t i = 0; i < A.size(); i++) {
+            const AIns& a = A[i];
+            if (i + 3 < A.size() && a.op == T_STR && a.kind == K_REG
+                && A[i + 1].op == (A_BIN | B_MOV) && (A[i + 1].kind == K_REG || A[i + 1].kind == K_LEAF)
+                && !(A[i + 1].kind == K_REG && A[i + 1].arg == a.arg)
+                && A[i + 2].op == (A_BIN | B_MUL) && A[i + 2].kind == K_IMM
+                && A[i + 3].op == (A_BIN | B_ADD) && A[i + 3].kind == K_REG && A[i + 3].arg == a.arg
+                && reg_dead_after(i + 4, a.arg)) {
+                out.push_back(AIns{(uint16_t)(A_BIN | B_ADDPROD), A[i + 1].kind, A[i + 1].arg, A[i + 2].y});
+                if (A[i + 1].kind == K_LEAF) leaf_refs++;
+                i += 3;
+                continue;
+            }
+            if (i + 1 < A.size() && a.op == (A_BIN | B_MUL) && a.kind == K_IMM && A[i + 1].op == (A_BIN | B_ADD) && A[i + 1].kind == K_IMM) {
+                out.push_back(AIns{(uint16_t)T_MULADD_II, K_IMM, (int32_t)A[i + 1].y, a.y});   // arg carries the second immediate's bits
+                i += 1;
+                continue;
+            }
+            if (i + 1 < A.size() && a.op == (A_BIN | B_ADD) && a.kind == K_REG && A[i + 1].op == T_STR && A[i + 1].kind == K_REG && A[i + 1].arg == a.arg) {
+                out.push_back(AIns{(uint16_t)T_ACCUM_S, K_REG, a.arg, 0u});
+                i += 1;
+                continue;
+            }
+            if (a.kind == K_LEAF) leaf_refs++;
+            out.push_back(a);
+        }
+        A.swap(out);
+        n_leaf_refs = leaf_refs;
+    }
+
     // ---- ring scheduling: abstract code -> tape (see tape_isa.h) ----
     struct Event { int32_t leaf; std::vector<int32_t> use; size_t k = 0; int slot = -1; bool waited = false; };
 
@@ -409,6 +455,9 @@ struct Gen {
                 const uint32_t bop = T_BIN0 + 3u * (uint32_t)(a.op & 0xff);
                 if (a.kind == K_IMM) body.push_back(TapeInstr{ bop, a.y });
                 else body.push_back(TapeInstr{ (bop + 1u) | ((R + (uint32_t)a.arg) << TAPE_SLOT_SHIFT), a.y });
+            } else if (a.op == T_MULADD_II) {
+                body.push_back(TapeInstr{ T_MULADD_II, a.y });
+                body.push_back(TapeInstr{ T_END, (uint32_t)a.arg });      // extension word: only its y is read
             } else if (a.op == T_END) {
                 // re-arm whatever prologue slot has not been re-armed yet (only slots that were never freed: none in practice)
                 if (a.kind == K_REG) body.push_back(TapeInstr{ T_END | ((R + (uint32_t)a.arg) << TAPE_SLOT_SHIFT), 1u });
@@ -434,14 +483,18 @@ struct Gen {
             emit(T_END, K_REG, vreg);
         } else emit(T_END);
         if (A.size() <= 1 && reduce_mode == RM_NONE) return;   // nothing to do
+        if (rt.opt.fuse_ops) peephole();
 
         std::vector<TapeInstr> prologue, body;
         int n_ring = 0;
         // Shared-memory budget of one warp, in 1 KB slots, if target_ctas CTAs are to be resident per SM: short tapes
         // keep the occupancy high, long ones trade it for ring depth (never below ring_min slots).
-        const size_t est_tables = 8 * (A.size() + 2 * (size_t)n_leaf_refs + 2 * TAPE_MAX_RING + 4) + 8 * ptrs.size() + 256;
-        const long budget_bytes = (long)std::min(rt.smem_per_sm / (size_t)std::max(1, rt.opt.target_ctas), rt.smem_per_cta_max) - 1024 - (long)est_tables;
-        const int slot_budget = (int)std::max<long>(1, budget_bytes / (TAPE_WARPS * TAPE_SLOT_BYTES));
+        const int64_t chunks = (n + TAPE_CHUNK - 1) / TAPE_CHUNK;
+        const int n_warps = rt.opt.cta_warps == 2 ? 2 : TAPE_WARPS;
+        const size_t est_tables = 8 * (A.size() + 2 * (size_t)n_leaf_refs + 2 * TAPE_MAX_RING + 6) + 8 * ptrs.size() + 256;
+        const size_t cta_share = rt.smem_per_sm / (size_t)(std::max(1, rt.opt.target_ctas) * (TAPE_WARPS / n_warps));
+        const long budget_bytes = (long)std::min(cta_share, rt.smem_per_cta_max) - 1024 - (long)est_tables;
+        const int slot_budget = (int)std::max<long>(1, budget_bytes / (n_warps * TAPE_SLOT_BYTES));
         int ring_max = std::max(1, std::min<int>(rt.opt.ring_max, TAPE_MAX_RING));
         ring_max = std::min(ring_max, std::max(rt.opt.ring_min, slot_budget - regs_used));
         schedule(ring_max, rt.opt.pipeline, rt.opt.horizon, prologue, body, n_ring);
@@ -464,14 +517,13 @@ struct Gen {
         if (!prologue.empty()) std::memcpy(P.instr, prologue.data(), sizeof(TapeInstr) * prologue.size());
         P.instr[prologue.size()] = TapeInstr{ T_END, 0u };      // closes the prologue
         std::memcpy(P.instr + prologue.size() + 1, body.data(), sizeof(TapeInstr) * body.size());
-        P.instr[total] = TapeInstr{ T_END, 0u };                // the interpreter prefetches one word ahead
-        const bool red = reduce_mode != RM_NONE;
-        const int64_t chunks = (n + TAPE_CHUNK - 1) / TAPE_CHUNK;
+        P.instr[total] = TapeInstr{ T_END, 0u };                // the interpreter prefetches two words ahead
+        P.instr[total + 1] = TapeInstr{ T_END, 0u };
         static OccCache occ;
         auto blocks_per_sm = [&](size_t smem_bytes) {
-            const auto key = std::make_pair((smem_bytes + 1023) / 1024, red);
+            const auto key = std::make_pair((smem_bytes + 1023) / 1024, reduce_mode * 8 + n_warps);
             auto it = occ.blocks.find(key);
-            if (it == occ.blocks.end()) it = occ.blocks.emplace(key, tape_max_blocks_per_sm(key.first * 1024, red)).first;
+            if (it == occ.blocks.end()) it = occ.blocks.emplace(key, tape_max_blocks_per_sm(key.first * 1024, reduce_mode, n_warps)).first;
             return it->second;
         };
         // slot sets: a tape that leaves most of the budget unused keeps several chunks per warp in flight
@@ -479,24 +531,24 @@ struct Gen {
         size_t smem = 0;
         if (rt.opt.pipeline && n_ring > 0) n_sets = std::max(1, std::min(rt.opt.max_sets, slot_budget / std::max(1, P.n_slots)));
         for (;;) {
-            smem = tape_smem_bytes(P.n_ptrs, P.n_instr, P.n_slots, n_sets);
+            smem = tape_smem_bytes(P.n_ptrs, P.n_instr, P.n_slots, n_sets, n_warps);
             if (smem > rt.smem_per_cta_max && n_sets > 1) { n_sets--; continue; }
             if (smem > rt.smem_per_cta_max) fail(FMC_ERR_UNSUPPORTED, "internal: tape needs %zu bytes of shared memory per CTA", smem);
             per_sm = blocks_per_sm(smem);
-            grid = (int)std::min<int64_t>((chunks + TAPE_WARPS - 1) / TAPE_WARPS, (int64_t)per_sm * rt.sm_count);
+            grid = (int)std::min<int64_t>((chunks + n_warps - 1) / n_warps, (int64_t)per_sm * rt.sm_count);
             grid = std::max(1, std::min(grid, rt.max_grid));
             if (rt.opt.grid_limit > 0) grid = std::min(grid, rt.opt.grid_limit);
-            const int64_t chunks_per_warp = (chunks + (int64_t)grid * TAPE_WARPS - 1) / ((int64_t)grid * TAPE_WARPS);
+            const int64_t chunks_per_warp = (chunks + (int64_t)grid * n_warps - 1) / ((int64_t)grid * n_warps);
             if (n_sets > 1 && n_sets > chunks_per_warp) { n_sets = (int)std::max<int64_t>(1, chunks_per_warp); continue; }
             break;
         }
         P.n_sets = n_sets;
         static const bool log_tapes = std::getenv("FMC_LOG_TAPES") != nullptr;
         if (log_tapes)
-            std::fprintf(stderr, "[fmc tape] n=%lld instr=%zu (abstract %zu, prologue %zu) ptrs=%zu leaves=%d stores=%d ring=%d regs=%d sets=%d smem=%zu ctas/sm=%d grid=%d reduce=%d\n",
-                         (long long)n, total, A.size(), prologue.size(), ptrs.size(), n_leaf_slots, n_result_stores, n_ring, regs_used, n_sets, smem, per_sm, grid, reduce_mode);
+            std::fprintf(stderr, "[fmc tape] n=%lld instr=%zu (abstract %zu, prologue %zu) ptrs=%zu leaves=%d stores=%d ring=%d regs=%d sets=%d warps=%d smem=%zu ctas/sm=%d grid=%d reduce=%d\n",
+                         (long long)n, total, A.size(), prologue.size(), ptrs.size(), n_leaf_slots, n_result_stores, n_ring, regs_used, n_sets, n_warps, smem, per_sm, grid, reduce_mode);
         if (rt.opt.profile) rt.profile_begin();
-        FMC_CUDA(launch_tape(P, grid, rt.stream));
+        FMC_CUDA(launch_tape(P, grid, n_warps, rt.stream));
         if (rt.opt.profile) rt.profile_end(4ull * (uint64_t)n * (uint64_t)(n_leaf_slots + n_result_stores));
         rt.stats.n_kernels++; rt.stats.n_tape_kernels++; rt.stats.n_tape_instr += total;
     }

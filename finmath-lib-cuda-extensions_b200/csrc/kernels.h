@@ -8,10 +8,10 @@
 namespace fmc {
 
 // tape_kernel.cu
-cudaError_t launch_tape(const TapeParams& P, int grid, cudaStream_t stream);
+cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t stream);   // n_warps per CTA: 2 or 4
 cudaError_t tape_kernel_setup(size_t* max_smem_per_cta);   // opts the kernel in to the device's full shared memory
-size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots, int n_sets);   // dynamic shared memory of one CTA
-int tape_max_blocks_per_sm(size_t smem_bytes, bool reduce);
+size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots, int n_sets, int n_warps);   // dynamic shared memory of one CTA
+int tape_max_blocks_per_sm(size_t smem_bytes, int reduce_mode, int n_warps);
 
 // regression_kernel.cu — fused normal equations: one pass over k basis vectors + y.
 constexpr int REG_MAX_K = 12;

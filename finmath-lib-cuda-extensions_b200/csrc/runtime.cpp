@@ -43,7 +43,7 @@ void Runtime::init(int device_index) {
     FMC_CUDA(cudaEventCreateWithFlags(&ev_copy[0], cudaEventDisableTiming));
     FMC_CUDA(cudaEventCreateWithFlags(&ev_copy[1], cudaEventDisableTiming));
     FMC_CUDA(tape_kernel_setup(&smem_per_cta_max));
-    max_grid = sm_count * 8;
+    max_grid = sm_count * 16;
     FMC_CUDA(cudaMalloc(&d_partials, sizeof(double) * 128 * (size_t)max_grid));
     FMC_CUDA(cudaMalloc(&d_counter, sizeof(unsigned int) * 4));
     FMC_CUDA(cudaMemset(d_counter, 0, sizeof(unsigned int) * 4));

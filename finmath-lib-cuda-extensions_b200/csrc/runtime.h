@@ -99,6 +99,8 @@ struct Options {
     int horizon = 96;               // uses of a leaf further apart than this many instructions are separate TMA copies
     bool pipeline = true;           // cross-chunk prefetch (prologue + T_LOADN)
     int max_sets = 1;               // slot sets per warp (cross-chunk prefetch depth), upper bound; measured: >1 costs occupancy and does not pay
+    int cta_warps = 4;              // warps per interpreter CTA (2 or 4)
+    bool fuse_ops = true;           // peephole fusion of the abstract code (MULADD_II, ACCUM_S, ADDPROD)
     int grid_limit = 0;             // > 0: cap the interpreter grid (tests: many chunks per warp at small sizes)
 };
 

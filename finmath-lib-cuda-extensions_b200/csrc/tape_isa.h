@@ -1,7 +1,7 @@
 // tape_isa.h — instruction set of the op-tape interpreter (shared by the host code generator and the kernel).
 //
 // Machine model. One WARP interprets the tape for one chunk of TAPE_CHUNK consecutive paths at a time
-// (lane l owns elements 4l..4l+3 and 128+4l..128+4l+3 of the chunk, i.e. two 128-bit groups), warps are fully
+// (lane l owns elements 128g+4l..128g+4l+3, g = 0..3, of the chunk, i.e. four 128-bit groups), warps are fully
 // independent of each other (no block barrier on the elementwise path):
 //   acc            accumulator, TAPE_E real registers per lane
 //   p              one predicate per element (for choose)
@@ -17,8 +17,9 @@
 //                                            occupant has been consumed, so every later chunk starts with its first
 //                                            leaves already in flight or landed.
 //                  slots [n_ring, S)         register file for intermediate values (T_STR writes, *_S reads)
-// Instruction word (8 bytes): x = op | slot_byte_offset (slot * TAPE_SLOT_BYTES, low 10 bits are the opcode);
-//                             y = float immediate bits | pointer-table index | second slot byte offset.
+// Instruction word (8 bytes): x = op | slot_byte_offset (slot * TAPE_SLOT_BYTES, low 11 bits are the opcode);
+//                             y = float immediate bits | pointer-table index.
+// Two-word instructions (T_MULADD_II) take the y of the following word as a second immediate.
 // Binary opcodes come in three flavours: _I (operand = immediate), _S (operand = slot), _W (operand = ring slot
 // whose TMA copy has not been waited for yet: wait on its mbarrier, then as _S).
 // Every primitive rounds once, exactly like the Java float code; the compound RandomVariable ops (accrue, discount,
@@ -30,12 +31,11 @@
 
 namespace fmc {
 
-constexpr int TAPE_E = 8;                              // elements per lane
-constexpr int TAPE_WARPS = 4;                          // warps per CTA
-constexpr int TAPE_THREADS = TAPE_WARPS * 32;
-constexpr int TAPE_CHUNK = 32 * TAPE_E;                // 256 paths per warp iteration
-constexpr int TAPE_SLOT_BYTES = TAPE_CHUNK * 4;        // 1 KB
-constexpr int TAPE_SLOT_SHIFT = 10;
+constexpr int TAPE_E = 16;                             // elements per lane
+constexpr int TAPE_WARPS = 4;                          // warps per CTA (2 for small vectors: finer CTA granularity)
+constexpr int TAPE_CHUNK = 32 * TAPE_E;                // 512 paths per warp iteration
+constexpr int TAPE_SLOT_BYTES = TAPE_CHUNK * 4;        // 2 KB
+constexpr int TAPE_SLOT_SHIFT = 11;
 constexpr int TAPE_MAX_RING = 16;                      // ring slots per warp (mbarriers per warp)
 constexpr int TAPE_REGS = 16;                          // register-file slots the code generator may use
 constexpr int TAPE_MAX_INSTR = 2046;
@@ -55,9 +55,9 @@ enum TapeOp : uint32_t {
     T_SQR = 7,       // acc = acc * acc
     T_SQRT = 8, T_EXP = 9, T_LOG = 10, T_SIN = 11, T_COS = 12, T_ABS = 13, T_INV = 14, T_ISNAN = 15,
     T_POW = 16,      // acc = (float) pow((double)acc, (double)imm)
-    T_ADDPRODVV = 17,// acc = acc + slot * slot2            (slot2 byte offset in y)
+    T_MULADD_II = 17,// acc = acc * imm + imm2              (two words, two roundings)
     T_LOADN = 18,    // ring slot <- ptrs[y][the next chunk that will use this slot set]   (cross-chunk prefetch; no-op near the end)
-    T_RESERVED19 = 19,
+    T_ACCUM_S = 19,  // acc = acc + slot; slot = acc        (register-file slot)
 #define FMC_X(NAME) T_##NAME##_I, T_##NAME##_S, T_##NAME##_W,
     FMC_TAPE_BINOPS(FMC_X)
 #undef FMC_X
@@ -103,7 +103,7 @@ struct TapeParams {
     unsigned int* counter;    // last-block ticket
     double* result;           // [4]
     float* ptrs[TAPE_MAX_PTRS];
-    TapeInstr instr[TAPE_MAX_INSTR + 2];
+    TapeInstr instr[TAPE_MAX_INSTR + 3];   // + closing T_END + two padding words (the interpreter prefetches two ahead)
 };
 
 }  // namespace fmc

@@ -146,7 +146,7 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
         if (chunk >= n_chunks) continue;
         for (int pc = 0; pc < P.n_prologue; pc++) {
             const TapeInstr in = P.instr[pc];
-            if ((in.x & 1023u) != T_LOAD) bad("prologue instruction %d is not a T_LOAD", pc);
+            if ((in.x & ((1u << TAPE_SLOT_SHIFT) - 1u)) != T_LOAD) bad("prologue instruction %d is not a T_LOAD", pc);
             sets[u].load(in.x >> TAPE_SLOT_SHIFT, in.y, chunk);
         }
     }
@@ -229,10 +229,18 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
             case T_INV: for (int e = 0; e < C; e++) acc[e] = 1.0f / acc[e]; break;
             case T_ISNAN: for (int e = 0; e < C; e++) acc[e] = (acc[e] != acc[e]) ? 1.0f : 0.0f; break;
             case T_POW: for (int e = 0; e < C; e++) acc[e] = jpow(acc[e], imm); break;
-            case T_ADDPRODVV: {
+            case T_MULADD_II: {
+                if (pc + 1 >= P.n_instr) bad("two-word instruction at the end of the tape");
+                float imm2; std::memcpy(&imm2, &P.instr[pc + 1].y, 4);
+                for (int e = 0; e < C; e++) { const float t = acc[e] * imm; acc[e] = t + imm2; }
+                pc++;                                   // the extension word is not an instruction
+                break;
+            }
+            case T_ACCUM_S: {
+                if ((int)slot < P.n_ring) bad("T_ACCUM_S on a ring slot");
                 const float* b = w.read(slot, chunk);
-                const float* c = w.read(in.y >> TAPE_SLOT_SHIFT, chunk);
-                for (int e = 0; e < C; e++) { const float t = b[e] * c[e]; acc[e] = acc[e] + t; }
+                for (int e = 0; e < C; e++) acc[e] = acc[e] + b[e];
+                std::memcpy(&w.slots[(size_t)slot * C], acc, sizeof(acc));
                 break;
             }
             default: bad("opcode %d unknown", (int)op);
@@ -265,24 +273,24 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
 
 void dump_tape(const TapeParams& P, int grid) {
     static const char* names[] = {"END", "LOAD", "WAIT", "STG", "STGS", "STR", "SETP", "SQR", "SQRT", "EXP", "LOG", "SIN", "COS", "ABS", "INV",
-                                  "ISNAN", "POW", "ADDPRODVV", "LOADN", "?"};
+                                  "ISNAN", "POW", "MULADD_II", "LOADN", "ACCUM_S", "?"};
     static const char* bins[] = {"MOV", "ADD", "SUB", "BUS", "MUL", "DIV", "VID", "MIN", "MAX", "SEL", "ADDPROD", "ACCRUE", "DISCOUNT"};
     std::fprintf(stderr, "[tape] n=%lld grid=%d instr=%d prologue=%d ptrs=%d ring=%d slots=%d reduce=%d\n", P.n, grid, P.n_instr, P.n_prologue,
                  P.n_ptrs, P.n_ring, P.n_slots, P.reduce_mode);
     for (int i = 0; i < P.n_instr; i++) {
-        const uint32_t op = P.instr[i].x & 1023u, slot = P.instr[i].x >> TAPE_SLOT_SHIFT;
+        const uint32_t op = P.instr[i].x & ((1u << TAPE_SLOT_SHIFT) - 1u), slot = P.instr[i].x >> TAPE_SLOT_SHIFT;
         float imm; std::memcpy(&imm, &P.instr[i].y, 4);
         if (op >= T_BIN0) {
             const uint32_t k = (op - T_BIN0) / 3u, fl = (op - T_BIN0) % 3u;
             if (fl == 0) std::fprintf(stderr, "  %4d %s_I %g\n", i, bins[k], imm);
             else std::fprintf(stderr, "  %4d %s_%c s%u%s (imm %g)\n", i, bins[k], fl == 1 ? 'S' : 'W', slot, (int)slot < P.n_ring ? "" : "r", imm);
-        } else std::fprintf(stderr, "  %4d %s s%u y=%u\n", i, names[op < 19 ? op : 19], slot, P.instr[i].y);
+        } else std::fprintf(stderr, "  %4d %s s%u y=%u\n", i, names[op < 20 ? op : 20], slot, P.instr[i].y);
     }
 }
 
 }  // namespace
 
-cudaError_t launch_tape(const TapeParams& P, int grid, cudaStream_t) {
+cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t) {
     if (std::getenv("FMC_EMU_DUMP")) dump_tape(P, grid);
     try {
         if (P.n_ring < 0 || P.n_ring > TAPE_MAX_RING || P.n_slots < P.n_ring) bad("bad slot counts: ring %d slots %d", P.n_ring, P.n_slots);
@@ -290,11 +298,12 @@ cudaError_t launch_tape(const TapeParams& P, int grid, cudaStream_t) {
         if (P.n_prologue < 0 || P.n_prologue + 1 >= P.n_instr) bad("bad prologue length %d", P.n_prologue);
         if (P.n_sets < 1 || P.n_sets > 4) bad("bad slot-set count %d", P.n_sets);
         if (grid < 1) bad("empty grid");
-        if (tape_smem_bytes(P.n_ptrs, P.n_instr, P.n_slots, P.n_sets) > 232448 - 1024) bad("shared memory of one CTA exceeds the device limit");
+        if (tape_smem_bytes(P.n_ptrs, P.n_instr, P.n_slots, P.n_sets, n_warps) > 232448 - 1024) bad("shared memory of one CTA exceeds the device limit");
         std::set<const float*> stored;
         Partial part;
         std::vector<double> values;
-        const long long stride = (long long)grid * TAPE_WARPS;
+        if (n_warps != 2 && n_warps != 4) bad("bad warp count %d", n_warps);
+        const long long stride = (long long)grid * n_warps;
         for (long long w = 0; w < stride; w++) run_warp(P, w, stride, stored, part, values);
         if (P.reduce_mode != RM_NONE) {
             double v = part.s, m2 = 0.0;
@@ -316,15 +325,16 @@ cudaError_t launch_tape(const TapeParams& P, int grid, cudaStream_t) {
     }
 }
 cudaError_t tape_kernel_setup(size_t* m) { if (m) *m = 232448 - 1024; return cudaSuccess; }
-size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots, int n_sets) {
-    size_t s = (size_t)TAPE_WARPS * (size_t)n_sets * TAPE_MAX_RING * 8;
+size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots, int n_sets, int n_warps) {
+    size_t s = (size_t)n_warps * (size_t)n_sets * TAPE_MAX_RING * 8;
     s += ((size_t)n_ptrs * 8 + 15) & ~(size_t)15;
-    s = (s + ((size_t)n_instr + 1) * 8 + 127) & ~(size_t)127;
-    return s + (size_t)TAPE_WARPS * (size_t)n_sets * (size_t)n_slots * TAPE_SLOT_BYTES;
+    s = (s + ((size_t)n_instr + 2) * 8 + 127) & ~(size_t)127;
+    return s + (size_t)n_warps * (size_t)n_sets * (size_t)n_slots * TAPE_SLOT_BYTES;
 }
-int tape_max_blocks_per_sm(size_t smem_bytes, bool reduce) {
+int tape_max_blocks_per_sm(size_t smem_bytes, int reduce_mode, int n_warps) {
     const int by_smem = (int)((233472 - 1024) / (smem_bytes + 1024));
-    return std::max(1, std::min(by_smem, reduce ? 6 : 8));
+    const int by_regs = (reduce_mode != RM_NONE ? 6 : 8) * (4 / n_warps);
+    return std::max(1, std::min(by_smem, by_regs));
 }
 
 // the other kernels are not ISA-driven; the emulator gives the regression its plain meaning and declines the rest
