@@ -22,6 +22,7 @@ GPU fixed), the only exchange is the all-reduce of reduction partials inside the
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -194,6 +195,11 @@ def run_ours(args) -> None:
     prof = capi.profile_read()
     capi.set_option("profile", 0)
     st = fc.stats()
+    host_prof = {}
+    for key in ("host_us_codegen", "host_us_launch", "host_us_sync"):
+        v = ctypes.c_double()
+        capi.check(capi.load().fmc_get_option(key.encode(), ctypes.byref(v)))
+        host_prof[key.replace("host_us_", "") + "_ms_per_step"] = v.value / 1e3 / args.steps
     step_ms = max_over_ranks(max(dev_ms, 0.0)) / args.steps
     value = total_paths * N_PERIODS / (step_ms * 1e-3)
 
@@ -254,7 +260,7 @@ def run_ours(args) -> None:
         "gpu_launches_per_step": st["n_kernels"] / args.steps,
         "ops_recorded_per_step": st["n_ops_recorded"] / args.steps,
         "nodes_stored_per_step": st["n_nodes_stored"] / args.steps, "nodes_fused_per_step": st["n_nodes_fused"] / args.steps,
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "host_profile": host_prof,
         "price_check": {"first_values": [float(v) for v in values[:3]], "e2e_equal": bool((values == values_e2e).all())},
     }
     print(json.dumps(line), flush=True)

@@ -23,6 +23,8 @@ y = fc.RandomVariableCuda(0.0, rng.random(n, dtype=np.float32).astype(np.float64
 for _ in range(2):
     z = x.add(y)
     capi.check(capi.load().fmc_sync())          # launch: add(vec)
+    z = x.add(1.5)
+    capi.check(capi.load().fmc_sync())          # launch: add(scalar)
     a = x.getAverage()                          # launch: getAverage
     p = x.sub(0.5).floor(0.0).div(1.1).getAverage()   # launch: payoff chain -> getAverage
 del x, y, z

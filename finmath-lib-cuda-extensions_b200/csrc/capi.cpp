@@ -384,6 +384,7 @@ static void set_option_locked(Runtime& rt, const char* key, double value) {
     else if (!std::strcmp(key, "max_sets")) rt.opt.max_sets = std::max(1, std::min((int)value, 4));
     else if (!std::strcmp(key, "grid_limit")) rt.opt.grid_limit = std::max(0, (int)value);
     else if (!std::strcmp(key, "fuse_ops")) rt.opt.fuse_ops = value != 0.0;
+    else if (!std::strcmp(key, "zero_copy_reduce")) rt.opt.zero_copy_reduce = value != 0.0;
     else if (!std::strcmp(key, "cta_warps")) rt.opt.cta_warps = (int)value == 2 ? 2 : 4;
     else fail(FMC_ERR_INVALID, "unknown option '%s'", key);
 }
@@ -418,7 +419,11 @@ int fmc_get_option(const char* key, double* value) {
         else if (!std::strcmp(key, "max_sets")) *value = rt.opt.max_sets;
         else if (!std::strcmp(key, "grid_limit")) *value = rt.opt.grid_limit;
         else if (!std::strcmp(key, "fuse_ops")) *value = rt.opt.fuse_ops ? 1.0 : 0.0;
+        else if (!std::strcmp(key, "zero_copy_reduce")) *value = rt.opt.zero_copy_reduce ? 1.0 : 0.0;
         else if (!std::strcmp(key, "cta_warps")) *value = rt.opt.cta_warps;
+        else if (!std::strcmp(key, "host_us_codegen")) *value = rt.hostprof.codegen;
+        else if (!std::strcmp(key, "host_us_launch")) *value = rt.hostprof.launch;
+        else if (!std::strcmp(key, "host_us_sync")) *value = rt.hostprof.sync;
         else fail(FMC_ERR_INVALID, "unknown option '%s'", key);
     });
 }
@@ -437,7 +442,7 @@ int fmc_get_stats(fmc_stats* out) {
     });
 }
 int fmc_reset_stats(void) {
-    return guarded([&](Runtime& rt) { rt.stats = Stats{}; rt.pool.n_alloc = rt.pool.n_reused = 0; rt.pool.high_water = rt.pool.bytes_in_use; });
+    return guarded([&](Runtime& rt) { rt.stats = Stats{}; rt.hostprof = HostProfile{}; rt.pool.n_alloc = rt.pool.n_reused = 0; rt.pool.high_water = rt.pool.bytes_in_use; });
 }
 int fmc_pool_trim(void) {
     return guarded([&](Runtime& rt) { rt.require_init(); FMC_CUDA(cudaStreamSynchronize(rt.stream)); rt.pool.trim(); });

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <map>
 
@@ -492,7 +493,15 @@ struct Gen {
         const int64_t chunks = (n + TAPE_CHUNK - 1) / TAPE_CHUNK;
         const int n_warps = rt.opt.cta_warps == 2 ? 2 : TAPE_WARPS;
         const size_t est_tables = 8 * (A.size() + 2 * (size_t)n_leaf_refs + 2 * TAPE_MAX_RING + 6) + 8 * ptrs.size() + 256;
-        const size_t cta_share = rt.smem_per_sm / (size_t)(std::max(1, rt.opt.target_ctas) * (TAPE_WARPS / n_warps));
+        // CTAs per SM to aim for: the configured target, raised when that lets the whole vector be resident at once
+        // (at ~1 chunk per warp a grid that needs a second round of CTAs runs it at a fraction of the occupancy)
+        int target = std::max(1, rt.opt.target_ctas) * (TAPE_WARPS / n_warps);
+        {
+            const int64_t need = (chunks + (int64_t)n_warps * rt.sm_count - 1) / ((int64_t)n_warps * rt.sm_count);
+            const int hw_max = (reduce_mode != RM_NONE ? 6 : 8) * (TAPE_WARPS / n_warps);
+            if (need > target && need <= hw_max) target = (int)need;
+        }
+        const size_t cta_share = rt.smem_per_sm / (size_t)target;
         const long budget_bytes = (long)std::min(cta_share, rt.smem_per_cta_max) - 1024 - (long)est_tables;
         const int slot_budget = (int)std::max<long>(1, budget_bytes / (n_warps * TAPE_SLOT_BYTES));
         int ring_max = std::max(1, std::min<int>(rt.opt.ring_max, TAPE_MAX_RING));
@@ -513,6 +522,8 @@ struct Gen {
         P.partials = rt.d_partials;
         P.counter = rt.d_counter;
         P.result = rt.d_result;
+        P.host_result = nullptr; P.ticket = 0.0;
+        if (reduce_mode != RM_NONE && rt.comm_size == 1 && rt.opt.zero_copy_reduce) { P.host_result = rt.h_ticket_dev; P.ticket = (rt.reduce_ticket += 1.0); }
         std::memcpy(P.ptrs, ptrs.data(), sizeof(float*) * ptrs.size());
         if (!prologue.empty()) std::memcpy(P.instr, prologue.data(), sizeof(TapeInstr) * prologue.size());
         P.instr[prologue.size()] = TapeInstr{ T_END, 0u };      // closes the prologue
@@ -548,7 +559,9 @@ struct Gen {
             std::fprintf(stderr, "[fmc tape] n=%lld instr=%zu (abstract %zu, prologue %zu) ptrs=%zu leaves=%d stores=%d ring=%d regs=%d sets=%d warps=%d smem=%zu ctas/sm=%d grid=%d reduce=%d\n",
                          (long long)n, total, A.size(), prologue.size(), ptrs.size(), n_leaf_slots, n_result_stores, n_ring, regs_used, n_sets, n_warps, smem, per_sm, grid, reduce_mode);
         if (rt.opt.profile) rt.profile_begin();
+        const auto t_launch0 = std::chrono::steady_clock::now();
         FMC_CUDA(launch_tape(P, grid, n_warps, rt.stream));
+        rt.hostprof.launch += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_launch0).count();
         if (rt.opt.profile) rt.profile_end(4ull * (uint64_t)n * (uint64_t)(n_leaf_slots + n_result_stores));
         rt.stats.n_kernels++; rt.stats.n_tape_kernels++; rt.stats.n_tape_instr += total;
     }
@@ -558,6 +571,11 @@ struct Gen {
 
 void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* red) {
     require_init();
+    struct Timer {
+        HostProfile& hp; double launch0; std::chrono::steady_clock::time_point t0;
+        explicit Timer(HostProfile& h) : hp(h), launch0(h.launch), t0(std::chrono::steady_clock::now()) {}
+        ~Timer() { hp.codegen += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() - (hp.launch - launch0); }
+    } timer(hostprof);
     epoch++;
     if (epoch == 0) { for (auto& nd : nodes) nd.epoch = 0; epoch = 1; }
     stats.n_flushes++;
@@ -717,8 +735,27 @@ void Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
     if (nodes[idx].n == 0) { out[0] = 0.0; out[1] = NAN; out[2] = NAN; return; }
     std::vector<int32_t> t{idx};
     run_cone(t, &spec);
+    const auto t_sync0 = std::chrono::steady_clock::now();
+    if (comm_size == 1 && opt.zero_copy_reduce) {
+        // the last block of the reduction wrote {count, value, M2} and then the ticket into mapped pinned memory:
+        // spin on the ticket (a host read per poll) instead of a 32-byte copy plus a stream synchronisation
+        volatile double* h = h_ticket;
+        unsigned spins = 0;
+        while (h[3] != reduce_ticket) {
+            if ((++spins & 0x3ffu) == 0u) {
+                const cudaError_t q = cudaStreamQuery(stream);
+                if (q == cudaSuccess) { if (h[3] == reduce_ticket) break; fail(FMC_ERR_CUDA, "reduction finished without publishing its result"); }
+                if (q != cudaErrorNotReady) FMC_CUDA(q);
+            }
+        }
+        out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
+        hostprof.sync += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_sync0).count();
+        stats.d2h += 32;
+        return;
+    }
     FMC_CUDA(cudaMemcpyAsync(h_result, d_result, sizeof(double) * 4, cudaMemcpyDeviceToHost, stream));
     FMC_CUDA(cudaStreamSynchronize(stream));
+    hostprof.sync += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_sync0).count();
     stats.d2h += 32;
     out[0] = h_result[0]; out[1] = h_result[1]; out[2] = h_result[2];
 }

@@ -49,6 +49,9 @@ void Runtime::init(int device_index) {
     FMC_CUDA(cudaMemset(d_counter, 0, sizeof(unsigned int) * 4));
     FMC_CUDA(cudaMalloc(&d_result, sizeof(double) * 256));
     FMC_CUDA(cudaMallocHost(&h_result, sizeof(double) * 256));
+    FMC_CUDA(cudaHostAlloc(&h_ticket, sizeof(double) * 4, cudaHostAllocMapped));
+    FMC_CUDA(cudaHostGetDevicePointer(&h_ticket_dev, h_ticket, 0));
+    h_ticket[3] = 0.0; reduce_ticket = 0.0;
     nodes.reserve(1 << 16);
     initialized = true;
 }
@@ -67,8 +70,8 @@ void Runtime::shutdown() {
     n_lazy = 0; n_live_handles = 0;
     pool.purge();
     staging.release();
-    cudaFree(d_partials); cudaFree(d_counter); cudaFree(d_result); cudaFreeHost(h_result);
-    d_partials = nullptr; d_counter = nullptr; d_result = nullptr; h_result = nullptr;
+    cudaFree(d_partials); cudaFree(d_counter); cudaFree(d_result); cudaFreeHost(h_result); cudaFreeHost(h_ticket);
+    d_partials = nullptr; d_counter = nullptr; d_result = nullptr; h_result = nullptr; h_ticket = nullptr; h_ticket_dev = nullptr;
     for (auto& pe : prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
     prof_events.clear(); prof_used = 0;
     cudaEventDestroy(ev_start); cudaEventDestroy(ev_stop); cudaEventDestroy(ev_copy[0]); cudaEventDestroy(ev_copy[1]);

@@ -94,11 +94,12 @@ struct Options {
     bool profile = false;       // time every interpreter launch with CUDA events (benchmarks)
     // interpreter scheduling knobs (see codegen.cpp: Gen::schedule / Gen::launch)
     int ring_max = TAPE_MAX_RING;   // TMA ring slots per warp, upper bound
-    int ring_min = 4;               // ... lower bound when shared memory is tight
+    int ring_min = 2;               // ... lower bound when shared memory is tight
     int target_ctas = 4;            // CTAs per SM the slot budget aims for
     int horizon = 96;               // uses of a leaf further apart than this many instructions are separate TMA copies
     bool pipeline = true;           // cross-chunk prefetch (prologue + T_LOADN)
     int max_sets = 1;               // slot sets per warp (cross-chunk prefetch depth), upper bound; measured: >1 costs occupancy and does not pay
+    bool zero_copy_reduce = true;   // reductions publish their result through mapped pinned memory (single-rank runs)
     int cta_warps = 4;              // warps per interpreter CTA (2 or 4)
     bool fuse_ops = true;           // peephole fusion of the abstract code (MULADD_II, ACCUM_S, ADDPROD)
     int grid_limit = 0;             // > 0: cap the interpreter grid (tests: many chunks per warp at small sizes)
@@ -108,6 +109,9 @@ struct Stats {
     uint64_t n_ops = 0, n_kernels = 0, n_tape_kernels = 0, n_tape_instr = 0, n_stored = 0, n_fused = 0, n_flushes = 0;
     uint64_t h2d = 0, d2h = 0;
 };
+
+// host-side time spent per phase (microseconds since the last reset); read with fmc_get_option("host_us_*")
+struct HostProfile { double codegen = 0, launch = 0, sync = 0; };
 
 struct Operand { int32_t node; float imm; };   // node < 0 => scalar
 
@@ -143,6 +147,9 @@ public:
     unsigned int* d_counter = nullptr;
     double* d_result = nullptr;         // [256] doubles
     double* h_result = nullptr;         // pinned mirror
+    double* h_ticket = nullptr;         // mapped pinned [4]: {count, value, M2, ticket} written by the reduction's last block
+    double* h_ticket_dev = nullptr;     // device-side address of h_ticket
+    double reduce_ticket = 0.0;
     int max_grid = 0;
 
     // graph
@@ -154,6 +161,7 @@ public:
     int64_t n_lazy = 0, n_live_handles = 0;
     Options opt;
     Stats stats;
+    HostProfile hostprof;
 
     // profile mode: event pairs around interpreter launches + their algorithmic bytes
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;

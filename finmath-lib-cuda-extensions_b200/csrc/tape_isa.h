@@ -102,6 +102,8 @@ struct TapeParams {
     double* partials;         // [gridDim.x][4]
     unsigned int* counter;    // last-block ticket
     double* result;           // [4]
+    double* host_result;      // [4] the same result through mapped pinned host memory ([3] = ticket), or nullptr
+    double ticket;            // written to host_result[3] last: the host spins on it instead of a copy + stream sync
     float* ptrs[TAPE_MAX_PTRS];
     TapeInstr instr[TAPE_MAX_INSTR + 3];   // + closing T_END + two padding words (the interpreter prefetches two ahead)
 };

@@ -39,6 +39,8 @@ cudaError_t cudaMalloc(void** p, size_t n) { return posix_memalign(p, 512, n ? n
 cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
 cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return cudaMalloc(p, n); }
+cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) { *d = h; return cudaSuccess; }
+cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return cudaSuccess; }
 cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
@@ -316,6 +318,7 @@ cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t
                 v = mean; part.c = (double)values.size();
             }
             P.result[0] = part.c; P.result[1] = v; P.result[2] = m2;
+            if (P.host_result) { P.host_result[0] = part.c; P.host_result[1] = v; P.host_result[2] = m2; P.host_result[3] = P.ticket; }
         }
         return cudaSuccess;
     } catch (const Check& c) {

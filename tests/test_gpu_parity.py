@@ -227,7 +227,7 @@ def test_long_tape_register_pressure_and_cuts(fc, O, data):
     assert bits_equal(c.getRealizationsFloat(), co)
 
 
-SCHED_DEFAULTS = {"ring_max": 16, "ring_min": 4, "target_ctas": 4, "horizon": 96, "pipeline": 1, "max_sets": 1, "grid_limit": 0}
+SCHED_DEFAULTS = {"ring_max": 16, "ring_min": 2, "target_ctas": 4, "horizon": 96, "pipeline": 1, "max_sets": 1, "grid_limit": 0}
 
 
 @pytest.mark.parametrize("opts", [
