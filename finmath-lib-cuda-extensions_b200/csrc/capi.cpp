@@ -278,16 +278,9 @@ namespace {
 // merge (count, value, M2) triples of the ranks in rank order (deterministic)
 void merge_ranks(Runtime& rt, int mode, double part[3]) {
     if (rt.comm_size <= 1) return;
-    // all-gather through an all-reduce of a zero-padded [size][4] table (tiny: <= 8*4 doubles)
+    // Runtime::reduce left every rank's partial in h_result[4 * r + 0..2] (ncclAllGather behind the reduction kernel)
     const int R = rt.comm_size;
-    for (int i = 0; i < 4 * R; i++) rt.h_result[i] = 0.0;
-    rt.h_result[4 * rt.comm_rank + 0] = part[0];
-    rt.h_result[4 * rt.comm_rank + 1] = part[1];
-    rt.h_result[4 * rt.comm_rank + 2] = part[2];
-    FMC_CUDA(cudaMemcpyAsync(rt.d_result + 8, rt.h_result, sizeof(double) * 4 * R, cudaMemcpyHostToDevice, rt.stream));
-    rt.allreduce_sum(rt.d_result + 8, 4 * R);
-    FMC_CUDA(cudaMemcpyAsync(rt.h_result, rt.d_result + 8, sizeof(double) * 4 * R, cudaMemcpyDeviceToHost, rt.stream));
-    FMC_CUDA(cudaStreamSynchronize(rt.stream));
+    (void)part;
     double c = 0.0, v = 0.0, m = 0.0;
     for (int r = 0; r < R; r++) {
         const double bc = rt.h_result[4 * r], bv = rt.h_result[4 * r + 1], bm = rt.h_result[4 * r + 2];
@@ -385,6 +378,7 @@ static void set_option_locked(Runtime& rt, const char* key, double value) {
     else if (!std::strcmp(key, "grid_limit")) rt.opt.grid_limit = std::max(0, (int)value);
     else if (!std::strcmp(key, "fuse_ops")) rt.opt.fuse_ops = value != 0.0;
     else if (!std::strcmp(key, "zero_copy_reduce")) rt.opt.zero_copy_reduce = value != 0.0;
+    else if (!std::strcmp(key, "leaf_reduce_kernel")) rt.opt.leaf_reduce_kernel = value != 0.0;
     else if (!std::strcmp(key, "cta_warps")) rt.opt.cta_warps = (int)value == 2 ? 2 : 4;
     else fail(FMC_ERR_INVALID, "unknown option '%s'", key);
 }
@@ -420,6 +414,7 @@ int fmc_get_option(const char* key, double* value) {
         else if (!std::strcmp(key, "grid_limit")) *value = rt.opt.grid_limit;
         else if (!std::strcmp(key, "fuse_ops")) *value = rt.opt.fuse_ops ? 1.0 : 0.0;
         else if (!std::strcmp(key, "zero_copy_reduce")) *value = rt.opt.zero_copy_reduce ? 1.0 : 0.0;
+        else if (!std::strcmp(key, "leaf_reduce_kernel")) *value = rt.opt.leaf_reduce_kernel ? 1.0 : 0.0;
         else if (!std::strcmp(key, "cta_warps")) *value = rt.opt.cta_warps;
         else if (!std::strcmp(key, "host_us_codegen")) *value = rt.hostprof.codegen;
         else if (!std::strcmp(key, "host_us_launch")) *value = rt.hostprof.launch;

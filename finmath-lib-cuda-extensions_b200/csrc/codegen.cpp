@@ -732,9 +732,32 @@ void Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
     require_init();
     ReduceSpec spec = spec_in;
     if (spec.weight >= 0) materialize(spec.weight);
-    if (nodes[idx].n == 0) { out[0] = 0.0; out[1] = NAN; out[2] = NAN; return; }
-    std::vector<int32_t> t{idx};
-    run_cone(t, &spec);
+    const bool empty = nodes[idx].n == 0;
+    if (empty && comm_size == 1) { out[0] = 0.0; out[1] = NAN; out[2] = NAN; return; }
+    if (empty) FMC_CUDA(cudaMemsetAsync(d_result, 0, sizeof(double) * 4, stream));      // an empty slice still joins the exchange
+    if (empty) {
+    } else if (nodes[idx].state == NS_MAT && opt.leaf_reduce_kernel) {
+        // nothing to interpret: plain streaming reduction (reduce_kernel.cu)
+        ReduceParams P;
+        P.n = nodes[idx].n; P.mode = spec.mode; P.param = spec.param;
+        P.x = nodes[idx].buf; P.w = spec.weight >= 0 ? nodes[spec.weight].buf : nullptr;
+        P.partials = d_partials; P.counter = d_counter; P.result = d_result;
+        P.host_result = nullptr; P.ticket = 0.0;
+        if (comm_size == 1 && opt.zero_copy_reduce) { P.host_result = h_ticket_dev; P.ticket = (reduce_ticket += 1.0); }
+        const int64_t tiles = (P.n + reduce_tile_elems() - 1) / reduce_tile_elems();
+        int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)sm_count * 8));
+        grid = std::min(grid, max_grid);
+        if (opt.grid_limit > 0) grid = std::min(grid, opt.grid_limit);
+        if (opt.profile) profile_begin();
+        const auto t_launch0 = std::chrono::steady_clock::now();
+        FMC_CUDA(launch_reduce(P, grid, stream));
+        hostprof.launch += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_launch0).count();
+        if (opt.profile) profile_end(4ull * (uint64_t)P.n * (P.w ? 2u : 1u));
+        stats.n_kernels++; stats.n_flushes++;
+    } else {
+        std::vector<int32_t> t{idx};
+        run_cone(t, &spec);
+    }
     const auto t_sync0 = std::chrono::steady_clock::now();
     if (comm_size == 1 && opt.zero_copy_reduce) {
         // the last block of the reduction wrote {count, value, M2} and then the ticket into mapped pinned memory:
@@ -751,6 +774,16 @@ void Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
         out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
         hostprof.sync += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_sync0).count();
         stats.d2h += 32;
+        return;
+    }
+    if (comm_size > 1) {
+        // exchange step: every rank's {count, value, M2} into one table, merged on the host in rank order (capi.cpp)
+        allgather(d_result, d_result + 8, 4);
+        FMC_CUDA(cudaMemcpyAsync(h_result, d_result + 8, sizeof(double) * 4 * (size_t)comm_size, cudaMemcpyDeviceToHost, stream));
+        FMC_CUDA(cudaStreamSynchronize(stream));
+        hostprof.sync += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_sync0).count();
+        stats.d2h += 32 * (uint64_t)comm_size;
+        out[0] = h_result[4 * comm_rank]; out[1] = h_result[4 * comm_rank + 1]; out[2] = h_result[4 * comm_rank + 2];
         return;
     }
     FMC_CUDA(cudaMemcpyAsync(h_result, d_result, sizeof(double) * 4, cudaMemcpyDeviceToHost, stream));

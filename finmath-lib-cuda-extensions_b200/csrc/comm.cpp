@@ -28,6 +28,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -41,8 +42,9 @@ NcclApi& api() {
     a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.handle, "ncclCommInitRank");
     a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.handle, "ncclCommDestroy");
     a.AllReduce = (decltype(a.AllReduce))dlsym(a.handle, "ncclAllReduce");
+    a.AllGather = (decltype(a.AllGather))dlsym(a.handle, "ncclAllGather");
     a.GetErrorString = (decltype(a.GetErrorString))dlsym(a.handle, "ncclGetErrorString");
-    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce)
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.AllGather)
         fail(FMC_ERR_COMM, "libnccl.so.2 lacks a required symbol");
     return a;
 }
@@ -86,6 +88,12 @@ void comm_destroy(Runtime& rt) {
 void Runtime::allreduce_sum(double* dev, int count) {
     if (comm_size <= 1) return;
     check(api().AllReduce(dev, dev, (size_t)count, ncclFloat64, ncclSum, (ncclComm_t)nccl_comm, stream), "ncclAllReduce");
+    stats.n_kernels++;
+}
+
+void Runtime::allgather(const double* dev_send, double* dev_recv, int count_per_rank) {
+    if (comm_size <= 1) return;
+    check(api().AllGather(dev_send, dev_recv, (size_t)count_per_rank, ncclFloat64, (ncclComm_t)nccl_comm, stream), "ncclAllGather");
     stats.n_kernels++;
 }
 

@@ -13,6 +13,22 @@ cudaError_t tape_kernel_setup(size_t* max_smem_per_cta);   // opts the kernel in
 size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots, int n_sets, int n_warps);   // dynamic shared memory of one CTA
 int tape_max_blocks_per_sm(size_t smem_bytes, int reduce_mode, int n_warps);
 
+// reduce_kernel.cu — streaming reduction of a materialised vector (no chain to interpret)
+struct ReduceParams {
+    long long n;
+    int mode;                 // ReduceMode
+    double param;             // RM_WSQ: the mean
+    const float* x;
+    const float* w;           // weights (RM_DOT / RM_WSQ) or nullptr
+    double* partials;         // [gridDim.x][4]
+    unsigned int* counter;
+    double* result;           // {count, value, M2}
+    double* host_result;      // mapped pinned mirror (+ ticket in [3]) or nullptr
+    double ticket;
+};
+cudaError_t launch_reduce(const ReduceParams& P, int grid, cudaStream_t stream);
+int reduce_tile_elems();
+
 // regression_kernel.cu — fused normal equations: one pass over k basis vectors + y.
 constexpr int REG_MAX_K = 12;
 struct RegressionParams {

@@ -1,0 +1,192 @@
+// reduce_kernel.cu — streaming reduction of a MATERIALISED vector (getAverage / getVariance / getMin / getMax and the
+// weighted forms on a vector that already lives in HBM). A fused "chain -> reduce" goes through the op-tape interpreter
+// (tape_kernel.cu); when there is no chain to interpret, the interpreter's per-chunk dispatch is pure overhead and this
+// kernel does the same job as a plain bandwidth-bound stream: 128-bit loads, 4 independent loads per thread in flight,
+// double accumulation in a fixed pairwise order (deterministic for a given grid), warp shuffles, one partial per block,
+// last block merges. Replaces the host loops behind RandomVariableCuda.getAverage()/getVariance()
+// (/root/reference/src/main/java/net/finmath/cuda/montecarlo/RandomVariableCuda.java:869-907: full device->host copy + CPU sum)
+// and the two unused shared-memory reduction kernels of RandomVariableCudaKernel.cu:268-349.
+// Semantics per mode as in tape_isa.h (RM_*); result layout {count, value, M2} like the interpreter's epilogue.
+//
+// Bound: HBM. Algorithmic bytes: 4 per element (8 for the weighted modes).
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "kernels.h"
+#include "tape_isa.h"
+
+namespace fmc {
+
+namespace {
+
+constexpr int RT = 256;            // threads per block
+constexpr int RU = 4;              // float4 loads per thread per iteration
+constexpr int RTILE = RT * RU * 4; // elements per block iteration
+
+struct Part { double c, v, m; };
+
+__device__ __forceinline__ double jmin(double a, double b) {
+    if (a != a) return a;
+    if (b != b) return b;
+    if (a == 0.0 && b == 0.0) return (signbit(a) || signbit(b)) ? -0.0 : 0.0;
+    return a < b ? a : b;
+}
+__device__ __forceinline__ double jmax(double a, double b) {
+    if (a != a) return a;
+    if (b != b) return b;
+    if (a == 0.0 && b == 0.0) return (signbit(a) && signbit(b)) ? -0.0 : 0.0;
+    return a > b ? a : b;
+}
+__device__ __forceinline__ float jminf(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float jmaxf(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+
+__device__ __forceinline__ Part merge(int mode, Part a, Part b) {
+    if (b.c == 0.0) return a;
+    if (a.c == 0.0) return b;
+    Part r;
+    r.c = a.c + b.c;
+    r.m = 0.0;
+    if (mode == RM_MOMENTS) {          // Chan et al. pairwise update
+        const double delta = b.v - a.v;
+        const double w = b.c / r.c;
+        r.v = a.v + delta * w;
+        r.m = a.m + b.m + delta * delta * a.c * w;
+    } else if (mode == RM_MIN) r.v = jmin(a.v, b.v);
+    else if (mode == RM_MAX) r.v = jmax(a.v, b.v);
+    else r.v = a.v + b.v;
+    return r;
+}
+__device__ __forceinline__ Part shfl_down(Part p, int d) {
+    Part r;
+    r.c = __shfl_down_sync(0xffffffffu, p.c, d);
+    r.v = __shfl_down_sync(0xffffffffu, p.v, d);
+    r.m = __shfl_down_sync(0xffffffffu, p.m, d);
+    return r;
+}
+__device__ Part block_reduce(int mode, Part p, Part* smem) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) p = merge(mode, p, shfl_down(p, d));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) smem[warp] = p;
+    __syncthreads();
+    if (warp == 0) {
+        Part q = (lane < RT / 32) ? smem[lane] : Part{0.0, 0.0, 0.0};
+#pragma unroll
+        for (int d = RT / 64; d > 0; d >>= 1) q = merge(mode, q, shfl_down(q, d));
+        p = q;
+    }
+    return p;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// MODE is a compile-time ReduceMode: each variant carries only its own state
+template <int MODE>
+__global__ void __launch_bounds__(RT)
+reduce_kernel(const __grid_constant__ ReduceParams P)
+{
+    const long long n = P.n;
+    const int tid = threadIdx.x;
+    double acc = 0.0, s1 = 0.0, s2 = 0.0, shiftK = 0.0;
+    float fext = 0.0f;
+    long long cnt = 0;
+    constexpr bool W = (MODE == RM_DOT || MODE == RM_WSQ);
+
+    auto fold4 = [&](const float4 x, const float4 w) {
+        if (MODE == RM_SUM) acc += ((double)x.x + (double)x.y) + ((double)x.z + (double)x.w);
+        else if (MODE == RM_MOMENTS) {
+            if (cnt == 0) shiftK = (double)x.x;
+            const double d0 = (double)x.x - shiftK, d1 = (double)x.y - shiftK, d2 = (double)x.z - shiftK, d3 = (double)x.w - shiftK;
+            s1 += (d0 + d1) + (d2 + d3);
+            s2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        } else if (MODE == RM_MIN) { const float m = jminf(jminf(x.x, x.y), jminf(x.z, x.w)); fext = cnt == 0 ? m : jminf(fext, m); }
+        else if (MODE == RM_MAX) { const float m = jmaxf(jmaxf(x.x, x.y), jmaxf(x.z, x.w)); fext = cnt == 0 ? m : jmaxf(fext, m); }
+        else if (MODE == RM_DOT) acc += ((double)x.x * (double)w.x + (double)x.y * (double)w.y) + ((double)x.z * (double)w.z + (double)x.w * (double)w.w);
+        else {
+            const double d0 = (double)x.x - P.param, d1 = (double)x.y - P.param, d2 = (double)x.z - P.param, d3 = (double)x.w - P.param;
+            acc += (d0 * d0 * (double)w.x + d1 * d1 * (double)w.y) + (d2 * d2 * (double)w.z + d3 * d3 * (double)w.w);
+        }
+        cnt += 4;
+    };
+    auto fold1 = [&](const float x, const float w) {
+        if (MODE == RM_SUM) acc += (double)x;
+        else if (MODE == RM_MOMENTS) { if (cnt == 0) shiftK = (double)x; const double d = (double)x - shiftK; s1 += d; s2 += d * d; }
+        else if (MODE == RM_MIN) fext = cnt == 0 ? x : jminf(fext, x);
+        else if (MODE == RM_MAX) fext = cnt == 0 ? x : jmaxf(fext, x);
+        else if (MODE == RM_DOT) acc += (double)x * (double)w;
+        else { const double d = (double)x - P.param; acc += d * d * (double)w; }
+        cnt += 1;
+    };
+
+    const long long n_tiles = n / RTILE;            // full tiles: 4 independent 128-bit loads per thread (8 when weighted)
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const long long base = t * RTILE + (long long)tid * 4;
+        float4 x[RU], w[RU];
+#pragma unroll
+        for (int u = 0; u < RU; u++) {
+            x[u] = ldg4(P.x + base + (long long)u * RT * 4);
+            w[u] = W ? ldg4(P.w + base + (long long)u * RT * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < RU; u++) fold4(x[u], w[u]);
+    }
+    // ragged tail (less than one tile): block 0 walks it element by element
+    if (blockIdx.x == 0)
+        for (long long i = n_tiles * RTILE + tid; i < n; i += RT) fold1(P.x[i], W ? P.w[i] : 0.f);
+
+    Part part;
+    part.c = (double)cnt; part.v = acc; part.m = 0.0;
+    if (MODE == RM_MIN || MODE == RM_MAX) part.v = (double)fext;
+    if (MODE == RM_MOMENTS && cnt > 0) { part.v = shiftK + s1 / part.c; part.m = s2 - s1 * s1 / part.c; }
+    constexpr int MM = W ? RM_SUM : MODE;
+
+    __shared__ Part red_smem[RT / 32];
+    __shared__ bool is_last;
+    Part blk = block_reduce(MM, part, red_smem);
+    if (tid == 0) {
+        double* dst = P.partials + 4ll * blockIdx.x;
+        dst[0] = blk.c; dst[1] = blk.v; dst[2] = blk.m;
+        __threadfence();
+        const unsigned ticket = atomicAdd(P.counter, 1u);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    Part q = {0.0, 0.0, 0.0};
+    for (unsigned k = tid; k < gridDim.x; k += RT) {
+        const volatile double* src = P.partials + 4ll * k;
+        Part t = { src[0], src[1], src[2] };
+        q = merge(MM, q, t);
+    }
+    q = block_reduce(MM, q, red_smem);
+    if (tid == 0) {
+        P.result[0] = q.c; P.result[1] = q.v; P.result[2] = q.m;
+        *P.counter = 0u;
+        if (P.host_result) {
+            volatile double* h = P.host_result;
+            h[0] = q.c; h[1] = q.v; h[2] = q.m;
+            __threadfence_system();
+            h[3] = P.ticket;
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_reduce(const ReduceParams& P, int grid, cudaStream_t stream) {
+    switch (P.mode) {
+    case RM_SUM: reduce_kernel<RM_SUM><<<grid, RT, 0, stream>>>(P); break;
+    case RM_MOMENTS: reduce_kernel<RM_MOMENTS><<<grid, RT, 0, stream>>>(P); break;
+    case RM_MIN: reduce_kernel<RM_MIN><<<grid, RT, 0, stream>>>(P); break;
+    case RM_MAX: reduce_kernel<RM_MAX><<<grid, RT, 0, stream>>>(P); break;
+    case RM_DOT: reduce_kernel<RM_DOT><<<grid, RT, 0, stream>>>(P); break;
+    case RM_WSQ: reduce_kernel<RM_WSQ><<<grid, RT, 0, stream>>>(P); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+int reduce_tile_elems() { return RTILE; }
+
+}  // namespace fmc

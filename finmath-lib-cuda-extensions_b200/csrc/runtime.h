@@ -100,6 +100,7 @@ struct Options {
     bool pipeline = true;           // cross-chunk prefetch (prologue + T_LOADN)
     int max_sets = 1;               // slot sets per warp (cross-chunk prefetch depth), upper bound; measured: >1 costs occupancy and does not pay
     bool zero_copy_reduce = true;   // reductions publish their result through mapped pinned memory (single-rank runs)
+    bool leaf_reduce_kernel = true; // reductions of a materialised vector use the streaming kernel, not the interpreter
     int cta_warps = 4;              // warps per interpreter CTA (2 or 4)
     bool fuse_ops = true;           // peephole fusion of the abstract code (MULADD_II, ACCUM_S, ADDPROD)
     int grid_limit = 0;             // > 0: cap the interpreter grid (tests: many chunks per warp at small sizes)
@@ -187,7 +188,9 @@ public:
     void flush_all();                                     // materialise every referenced pending node
     void materialize(int32_t idx);                        // make node idx NS_MAT
     void run_cone(const std::vector<int32_t>& targets, const ReduceSpec* red);   // core scheduler
-    void reduce(int32_t idx, const ReduceSpec& spec, double out[3]);            // {count, value, M2} of the LOCAL slice
+    // {count, value, M2} of the LOCAL slice; with several ranks the partials of ALL ranks are left in h_result[4 * r + 0..2]
+    // (one ncclAllGather behind the reduction kernel, one copy, one synchronisation)
+    void reduce(int32_t idx, const ReduceSpec& spec, double out[3]);
     void auto_flush();
 
     // host copies
@@ -200,6 +203,7 @@ public:
     int comm_rank = 0, comm_size = 1;
     void* nccl_comm = nullptr;
     void allreduce_sum(double* dev, int count);           // in place on the compute stream
+    void allgather(const double* dev_send, double* dev_recv, int count_per_rank);
     void allreduce_minmax(double* dev, int count, bool is_max);
 };
 

@@ -43,6 +43,7 @@ cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) { *d = h; retu
 cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
 cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = 4ull << 30; *t = 8ull << 30; return cudaSuccess; }
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)0x1; return cudaSuccess; }
@@ -355,6 +356,34 @@ cudaError_t launch_regression(const RegressionParams& P, int, cudaStream_t) {
     return cudaSuccess;
 }
 int regression_max_blocks_per_sm() { return 1; }
+cudaError_t launch_reduce(const ReduceParams& P, int, cudaStream_t) {
+    double c = 0, s = 0, m2 = 0, mn = 0, mx = 0;
+    std::vector<double> vals;
+    for (long long i = 0; i < P.n; i++) {
+        const double x = (double)P.x[i], w = P.w ? (double)P.w[i] : 0.0;
+        switch (P.mode) {
+        case RM_SUM: s += x; break;
+        case RM_MOMENTS: vals.push_back(x); break;
+        case RM_MIN: mn = c == 0 ? x : std::fmin(mn, x); if (x != x) mn = x; break;
+        case RM_MAX: mx = c == 0 ? x : std::fmax(mx, x); if (x != x) mx = x; break;
+        case RM_DOT: s += x * w; break;
+        case RM_WSQ: s += (x - P.param) * (x - P.param) * w; break;
+        default: return cudaErrorInvalidValue;
+        }
+        c += 1.0;
+    }
+    double v = s;
+    if (P.mode == RM_MIN) v = mn; else if (P.mode == RM_MAX) v = mx;
+    else if (P.mode == RM_MOMENTS) {
+        double t = 0; for (double x : vals) t += x;
+        v = vals.empty() ? 0.0 : t / (double)vals.size();
+        for (double x : vals) m2 += (x - v) * (x - v);
+    }
+    P.result[0] = c; P.result[1] = v; P.result[2] = m2;
+    if (P.host_result) { P.host_result[0] = c; P.host_result[1] = v; P.host_result[2] = m2; P.host_result[3] = P.ticket; }
+    return cudaSuccess;
+}
+int reduce_tile_elems() { return 4096; }
 // FMC_EMU_FAKE_BROWNIAN=1 (tape-shape studies of the workload drivers only): increments from a throw-away generator,
 // NOT the MT19937 stream — the Brownian parity tests are never run against the emulator.
 static bool fake_brownian() { return std::getenv("FMC_EMU_FAKE_BROWNIAN") != nullptr; }
