@@ -126,6 +126,27 @@ def main():
                 ms, mn = timed(f)
                 report("B3 " + name, n, 8 if "prob" in name else 4, ms, mn, l2note)
 
+        if sel("ref"):  # the reference's own kernels (oracle/_ref cubin), reference geometry: the bar to beat on the same box
+            from oracle import ref_kernels
+            if ref_kernels.available():
+                import ctypes
+                rk = ref_kernels.ReferenceKernels(0)
+                L = capi.load()
+
+                def ptr(rv):
+                    p = ctypes.c_void_p(); capi.check(L.fmc_vec_device_ptr(rv.handle, ctypes.byref(p))); return p.value
+                h = ctypes.c_uint64(); capi.check(L.fmc_vec_alloc(n, ctypes.byref(h)))
+                po = ctypes.c_void_p(); capi.check(L.fmc_vec_device_ptr(h.value, ctypes.byref(po)))
+                capi.check(L.fmc_sync())
+                for name, kern, a, b in (("add(scalar)", "addScalar", [("p", ptr(x)), ("f", 1.0 / 3.0)], 8), ("exp", "cuExp", [("p", ptr(x))], 8),
+                                         ("add(vec)", "add", [("p", ptr(x)), ("p", ptr(y))], 12), ("div(vec)", "cuDiv", [("p", ptr(x)), ("p", ptr(y))], 12),
+                                         ("accrue", "accrue", [("p", ptr(x)), ("p", ptr(y)), ("f", 0.5)], 12),
+                                         ("addProduct(vec,vec)", "addProduct", [("p", ptr(x)), ("p", ptr(y)), ("p", ptr(z))], 16)):
+                    ms = rk.time_ms(kern, n, a + [("p", po.value)])
+                    report("REF kernel " + name, n, b, ms, ms, l2note + " reference kernel, 1024 thr/block, 1 elt/thread, kernel time only")
+                # the BS-Euler step as the reference executes it: 3 kernels, every intermediate through HBM
+                capi.check(L.fmc_vec_release(h.value))
+
         if sel("b4"):   # regression normal equations
             from finmath_cuda.conditional_expectation import normal_equations
             one = fc.RandomVariableCuda(1.0)

@@ -125,7 +125,11 @@ int fmc_flush(void);                    /* execute every pending node that is st
 int fmc_sync(void);                     /* flush + wait for the device (cuCtxSynchronize, RVC:472-476) */
 /* options: "flush_threshold" (pending nodes before an automatic flush; default 4096),
  *          "fuse" (1 default; 0 = execute every op as its own kernel, the reference's execution model),
- *          "profile" (0 default; see fmc_profile_read) */
+ *          "profile" (0 default; see fmc_profile_read);
+ *          interpreter scheduling knobs (tuning / tests; defaults in csrc/runtime.h): "ring_max", "ring_min", "target_ctas",
+ *          "horizon", "pipeline", "max_sets", "grid_limit", "fuse_ops", "cta_warps", "zero_copy_reduce", "leaf_reduce_kernel";
+ *          read-only host-side timers in microseconds since fmc_reset_stats: "host_us_codegen", "host_us_launch", "host_us_sync".
+ *          The environment variable FMC_OPTIONS="key=value,..." is applied once at fmc_init. */
 int fmc_set_option(const char* key, double value);
 int fmc_get_option(const char* key, double* value);
 
@@ -160,8 +164,9 @@ int fmc_timer_start(void);
 int fmc_timer_stop(float* elapsed_ms);  /* synchronises on the stop event */
 
 /* ---- multi GPU: one process per GPU, each holding a contiguous path slice of every vector ----
- * After fmc_comm_init, fmc_reduce / fmc_regression_normal_eq all-reduce their partials (ncclAllReduce on the
- * compute stream) and return the statistics of the GLOBAL vector. Vector data never crosses NVLink. */
+ * After fmc_comm_init, fmc_reduce gathers the ranks' {count, value, M2} partials (one ncclAllGather on the compute
+ * stream, merged in rank order) and fmc_regression_normal_eq all-reduces its sums (ncclAllReduce); both return the
+ * statistics of the GLOBAL vector. Vector data never crosses NVLink. */
 #define FMC_UNIQUE_ID_BYTES 128
 int fmc_comm_get_unique_id(char* id /* FMC_UNIQUE_ID_BYTES */);
 int fmc_comm_init(int rank, int nranks, const char* id);
