@@ -322,8 +322,11 @@ struct Gen {
 
     // ---- peephole fusion on the abstract code: every dispatch costs ~18 issue slots, so fewer, fatter instructions ----
     //   MUL_I a ; ADD_I b                      -> MULADD_II a, b          (two roundings, like the pair)
+    //   ADD_I a | SUB_I a ; MUL_I b             -> ADDMUL_II +-a, b
     //   ADD_S r ; STR r                         -> ACCUM_S r               (running sum kept in the register file)
     //   STR t ; MOV x ; MUL_I a ; ADD_S t       -> ADDPROD x, a            (t dead afterwards; float add commutes exactly)
+    //   (acc -> t) ; MOV x ; MUL_I a ; ADD_I 1 ; VID_S t  -> DISCOUNT x, a     acc / (1 + x * a), the same three roundings
+    //   (acc -> t) ; MOV x ; MUL_I a ; ADD_I 1 ; MUL_S t  -> ACCRUE x, a       acc * (1 + x * a)
     bool reg_dead_after(size_t from, int reg) const {
         for (size_t i = from; i < A.size(); i++) {
             const AIns& a = A[i];
@@ -349,8 +352,30 @@ struct Gen {
                 i += 3;
                 continue;
             }
+            // (acc -> t) ; MOV x ; MUL_I a ; ADD_I 1 ; VID_S t | MUL_S t     -> DISCOUNT x, a | ACCRUE x, a   on acc   (t dead afterwards)
+            if (i + 3 < A.size() && !out.empty() && a.op == (A_BIN | B_MOV) && (a.kind == K_REG || a.kind == K_LEAF)
+                && A[i + 1].op == (A_BIN | B_MUL) && A[i + 1].kind == K_IMM
+                && A[i + 2].op == (A_BIN | B_ADD) && A[i + 2].kind == K_IMM && A[i + 2].y == f2u(1.0f)
+                && (A[i + 3].op == (A_BIN | B_VID) || A[i + 3].op == (A_BIN | B_MUL)) && A[i + 3].kind == K_REG
+                && (out.back().op == T_STR || out.back().op == T_ACCUM_S) && out.back().kind == K_REG && out.back().arg == A[i + 3].arg
+                && !(a.kind == K_REG && a.arg == A[i + 3].arg) && reg_dead_after(i + 4, A[i + 3].arg)) {
+                const int t = A[i + 3].arg;
+                if (out.back().op == T_STR) out.pop_back();                                   // acc still holds the value
+                else out.back() = AIns{(uint16_t)(A_BIN | B_ADD), K_REG, t, 0u};              // ACCUM without the write-back
+                out.push_back(AIns{(uint16_t)(A_BIN | (A[i + 3].op == (A_BIN | B_VID) ? B_DISCOUNT : B_ACCRUE)), a.kind, a.arg, A[i + 1].y});
+                if (a.kind == K_LEAF) leaf_refs++;
+                i += 3;
+                continue;
+            }
             if (i + 1 < A.size() && a.op == (A_BIN | B_MUL) && a.kind == K_IMM && A[i + 1].op == (A_BIN | B_ADD) && A[i + 1].kind == K_IMM) {
                 out.push_back(AIns{(uint16_t)T_MULADD_II, K_IMM, (int32_t)A[i + 1].y, a.y});   // arg carries the second immediate's bits
+                i += 1;
+                continue;
+            }
+            if (i + 1 < A.size() && (a.op == (A_BIN | B_ADD) || a.op == (A_BIN | B_SUB)) && a.kind == K_IMM && A[i + 1].op == (A_BIN | B_MUL) && A[i + 1].kind == K_IMM) {
+                // x - a == x + (-a) bit for bit
+                const uint32_t first = a.op == (A_BIN | B_SUB) ? (a.y ^ 0x80000000u) : a.y;
+                out.push_back(AIns{(uint16_t)T_ADDMUL_II, K_IMM, (int32_t)A[i + 1].y, first});
                 i += 1;
                 continue;
             }
@@ -456,8 +481,8 @@ struct Gen {
                 const uint32_t bop = T_BIN0 + 3u * (uint32_t)(a.op & 0xff);
                 if (a.kind == K_IMM) body.push_back(TapeInstr{ bop, a.y });
                 else body.push_back(TapeInstr{ (bop + 1u) | ((R + (uint32_t)a.arg) << TAPE_SLOT_SHIFT), a.y });
-            } else if (a.op == T_MULADD_II) {
-                body.push_back(TapeInstr{ T_MULADD_II, a.y });
+            } else if (a.op == T_MULADD_II || a.op == T_ADDMUL_II) {
+                body.push_back(TapeInstr{ (uint32_t)a.op, a.y });
                 body.push_back(TapeInstr{ T_END, (uint32_t)a.arg });      // extension word: only its y is read
             } else if (a.op == T_END) {
                 // re-arm whatever prologue slot has not been re-armed yet (only slots that were never freed: none in practice)

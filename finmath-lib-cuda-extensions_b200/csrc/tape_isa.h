@@ -61,6 +61,7 @@ enum TapeOp : uint32_t {
 #define FMC_X(NAME) T_##NAME##_I, T_##NAME##_S, T_##NAME##_W,
     FMC_TAPE_BINOPS(FMC_X)
 #undef FMC_X
+    T_ADDMUL_II,     // acc = (acc + imm) * imm2            (two words, two roundings; SUB_I a is ADD_I -a exactly)
     T_NUM_OPS
 };
 constexpr uint32_t T_BIN0 = 20;
@@ -69,7 +70,7 @@ constexpr uint32_t T_BIN0 = 20;
 //   MIN Math.min(acc, b)   MAX Math.max(acc, b)   (NaN propagating, -0 < +0)      SEL p ? acc : b
 //   ADDPROD  acc + b * s        ACCRUE  acc * (1 + b * s)        DISCOUNT  acc / (1 + b * s)     (_S/_W only)
 static_assert(T_MOV_I == T_BIN0, "binary opcode layout");
-static_assert(T_NUM_OPS == T_BIN0 + 39, "binary opcode layout");
+static_assert(T_ADDMUL_II == T_BIN0 + 39 && T_NUM_OPS == T_BIN0 + 40, "binary opcode layout");
 
 enum ReduceMode : int {
     RM_NONE = 0,

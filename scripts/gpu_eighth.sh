@@ -1,0 +1,4 @@
+timeout -s KILL 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout -s KILL 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print('ms_per_step',round(d['ms_per_step'],2),'kernel_ms',round(d['roofline']['kernel_ms_per_step'],2),'launches',d['gpu_launches_per_step'],'e2e_ms',round(d['e2e']['ms_per_step'],1), d['host_profile'], 'frac', round(d['roofline']['frac'],3))"

@@ -174,6 +174,13 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
                 }
                 break;
             }
+            if (op == T_ADDMUL_II) {
+                if (pc + 1 >= P.n_instr) bad("two-word instruction at the end of the tape");
+                float imm2; std::memcpy(&imm2, &P.instr[pc + 1].y, 4);
+                for (int e = 0; e < C; e++) { const float t = acc[e] + imm; acc[e] = t * imm2; }
+                pc++;
+                continue;
+            }
             if (op >= T_BIN0) {
                 if (op >= T_NUM_OPS) bad("opcode %d out of range", (int)op);
                 const uint32_t kk = (op - T_BIN0) / 3u, fl = (op - T_BIN0) % 3u;
@@ -283,7 +290,8 @@ void dump_tape(const TapeParams& P, int grid) {
     for (int i = 0; i < P.n_instr; i++) {
         const uint32_t op = P.instr[i].x & ((1u << TAPE_SLOT_SHIFT) - 1u), slot = P.instr[i].x >> TAPE_SLOT_SHIFT;
         float imm; std::memcpy(&imm, &P.instr[i].y, 4);
-        if (op >= T_BIN0) {
+        if (op == T_ADDMUL_II) std::fprintf(stderr, "  %4d ADDMUL_II %g\n", i, imm);
+        else if (op >= T_BIN0) {
             const uint32_t k = (op - T_BIN0) / 3u, fl = (op - T_BIN0) % 3u;
             if (fl == 0) std::fprintf(stderr, "  %4d %s_I %g\n", i, bins[k], imm);
             else std::fprintf(stderr, "  %4d %s_%c s%u%s (imm %g)\n", i, bins[k], fl == 1 ? 'S' : 'W', slot, (int)slot < P.n_ring ? "" : "r", imm);

@@ -139,6 +139,38 @@ def test_edge_values_min_max_nan_zero(fc, O):
         assert ulp_diff(A.pow(e).getRealizationsFloat(), O.op_vs(O.POW, a, e)) <= 1, e
 
 
+def test_division_exact_over_the_whole_float_range(fc, O):
+    """The interpreter's division is a hand-scheduled Markstein sequence with a conservative range check and an
+    out-of-line div.rn.f32 for everything else: exercise both sides of the check and the boundary, per lane and mixed
+    within a warp — random bit patterns (all exponents, denormals, NaN, inf), exact powers of two around 2^-57 / 2^58,
+    signed zeros, and quotients that under/overflow. div, vid, discount and both scalar forms must be bit exact."""
+    rng = np.random.default_rng(99)
+    n = 1 << 16
+    bits_a = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    bits_b = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    a = bits_a.view(np.float32).copy(); b = bits_b.view(np.float32).copy()
+    # boundary exponents and special values sprinkled through otherwise ordinary data
+    special = np.array([0.0, -0.0, 1.0, -1.0, 2.0 ** -57, 2.0 ** -58, 2.0 ** 57, 2.0 ** 58, np.nextafter(np.float32(2.0 ** 58), np.float32(0)),
+                        1e-45, -1e-45, 1.17549435e-38, 3.4028235e38, np.inf, -np.inf, np.nan, 1.1, 3.1415, 1e30, 1e-30], dtype=np.float32)
+    ordinary = (rng.random(n, dtype=np.float32) * 4 - 2).astype(np.float32)
+    a2 = ordinary.copy(); b2 = (rng.random(n, dtype=np.float32) + np.float32(0.5)).astype(np.float32)
+    idx = rng.integers(0, n, 4096)
+    a2[idx] = special[rng.integers(0, special.size, idx.size)]
+    idx = rng.integers(0, n, 4096)
+    b2[idx] = special[rng.integers(0, special.size, idx.size)]
+    a2[::7] = 0.0                                   # out-of-the-money payoffs: zero numerators in every warp
+    for x, y in ((a, b), (a2, b2)):
+        X, Y = fc.RandomVariableCuda(0.0, x), fc.RandomVariableCuda(0.0, y)
+        assert bits_equal(X.div(Y).getRealizationsFloat(), O.op_vv(O.DIV, x, y))
+        assert bits_equal(X.vid(Y).getRealizationsFloat(), O.op_vv(O.VID, x, y))
+        assert bits_equal(X.discount(Y, 0.5).getRealizationsFloat(), O.op_vvs(O.DISCOUNT, x, y, 0.5))
+        # accumulator-side chains reach the _S / fused forms: (x*1) / y and y / (x*1)
+        assert bits_equal(X.mult(1.0).add(0.0).div(Y).getRealizationsFloat(), O.op_vv(O.DIV, O.op_vs(O.ADD, O.op_vs(O.MULT, x, 1.0), 0.0), y))
+        for s in (1.1, 3.0, 2.0 ** -60, 2.0 ** 60, 0.0, -0.0, float("inf"), float("nan"), 1e-45):
+            assert bits_equal(X.div(s).getRealizationsFloat(), O.op_vs(O.DIV, x, s)), s
+            assert bits_equal(X.vid(s).getRealizationsFloat(), O.op_vs(O.VID, x, s)), s
+
+
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 4, 5, 7, 2047, 2048, 2049, 4097, 65536 + 3])
 def test_ragged_sizes(fc, O, n):
     rng = np.random.RandomState(n + 1)
