@@ -32,12 +32,14 @@ def chain(kind):
         elif kind == "VID_I": c = c.vid(1.0001)
         elif kind == "MULADD_II": c = c.mult(1.0001).add(0.001)
         elif kind == "DISCOUNT_S": c = c.discount(y, 0.001)
-        elif kind == "MUL_I,ADD_S alternating": c = c.mult(1.0001).add(y) if k % 2 == 0 else c
+        elif kind == "MIX of 8 cheap handlers":
+            c = (c.mult(1.0001), c.add(0.001), c.sub(0.001), c.bus(3.0), c.cap(1e9), c.floor(-1e9), c.abs(), c.squared())[k % 8] if k % 8 != 7 else c.sqrt()
     return c
 
 
 capi.set_option("flush_threshold", 1e9)
-for kind in ("MUL_I", "ADD_S(leaf)", "MULADD_II", "DIV_I", "VID_I", "DISCOUNT_S"):
+capi.set_option("fuse_ops", 0)
+for kind in ("MUL_I", "MIX of 8 cheap handlers", "ADD_S(leaf)", "DIV_I", "VID_I", "DISCOUNT_S"):
     for _ in range(2):
         r = chain(kind); capi.check(L.fmc_sync()); del r
     capi.set_option("profile", 1); capi.profile_read()
