@@ -138,6 +138,11 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (an LMM Euler-step launch of tape_kernel<0> at
+# 1 Mi paths, 158 pointers), one `ncu --set full` capture: profiles/prof_micro_r1g.txt (337.2 MB read + 282.9 MB written)
+NCU_TRAFFIC_PER_LAUNCH = 620.1e6
+
+
 def run_ours(args) -> None:
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
     rank = int(os.environ.get("RANK", "0"))
@@ -193,6 +198,8 @@ def run_ours(args) -> None:
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
     clocks = sampler.stop()
+    touched = ctypes.c_double()
+    capi.check(capi.load().fmc_get_option(b"profile_touched_bytes", ctypes.byref(touched)))
     prof = capi.profile_read()
     capi.set_option("profile", 0)
     st = fc.stats()
@@ -232,7 +239,13 @@ def run_ours(args) -> None:
                 "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
                 "launches": prof["tape_launches"], "kernel_ms_per_step": prof["tape_ms"] / args.steps,
                 "kernel_share_of_step": (prof["tape_ms"] / args.steps) / step_ms if step_ms > 0 else None,
-                "algorithmic_bytes_per_step": prof["tape_algorithmic_bytes"] / args.steps}
+                "algorithmic_bytes_per_step": prof["tape_algorithmic_bytes"] / args.steps,
+                # every vector the kernels read or wrote, INCLUDING the re-read of results an earlier kernel of the same
+                # flush stored (each Euler-step kernel re-reads the rates the previous one wrote): what HBM actually moves
+                "touched_bytes_per_step": touched.value / args.steps,
+                "achieved_touched": touched.value / (prof["tape_ms"] * 1e-3) / 1e9 if prof["tape_ms"] > 0 else 0.0,
+                "frac_touched": (touched.value / (prof["tape_ms"] * 1e-3) / 1e9) / peak if prof["tape_ms"] > 0 else 0.0}
+    roofline["traffic"] = NCU_TRAFFIC_PER_LAUNCH
 
     cpu_baseline = None
     if not args.no_cpu_baseline:

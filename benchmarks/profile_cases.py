@@ -30,6 +30,6 @@ for _ in range(2):
 del x, y, z
 paths = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 m = DriverLib().lmm(paths, 80, 0.5, 1, 31415, 0, (0, paths))
-m.simulate()
+v = m.step()          # 75 Euler-step kernels (simulation) + 144 swaption kernels (fused chain -> getAverage)
 capi.check(capi.load().fmc_sync())
-print("ok", a, p)
+print("ok", a, p, v[:2])

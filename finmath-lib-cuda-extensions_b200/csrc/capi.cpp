@@ -416,6 +416,7 @@ int fmc_get_option(const char* key, double* value) {
         else if (!std::strcmp(key, "zero_copy_reduce")) *value = rt.opt.zero_copy_reduce ? 1.0 : 0.0;
         else if (!std::strcmp(key, "leaf_reduce_kernel")) *value = rt.opt.leaf_reduce_kernel ? 1.0 : 0.0;
         else if (!std::strcmp(key, "cta_warps")) *value = rt.opt.cta_warps;
+        else if (!std::strcmp(key, "profile_touched_bytes")) *value = (double)rt.prof_touched;
         else if (!std::strcmp(key, "host_us_codegen")) *value = rt.hostprof.codegen;
         else if (!std::strcmp(key, "host_us_launch")) *value = rt.hostprof.launch;
         else if (!std::strcmp(key, "host_us_sync")) *value = rt.hostprof.sync;

@@ -587,7 +587,7 @@ struct Gen {
         const auto t_launch0 = std::chrono::steady_clock::now();
         FMC_CUDA(launch_tape(P, grid, n_warps, rt.stream));
         rt.hostprof.launch += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_launch0).count();
-        if (rt.opt.profile) rt.profile_end(4ull * (uint64_t)n * (uint64_t)(n_leaf_slots + n_result_stores));
+        if (rt.opt.profile) rt.profile_end(4ull * (uint64_t)n * (uint64_t)(n_leaf_slots + n_result_stores), 4ull * (uint64_t)n * (uint64_t)ptrs.size());
         rt.stats.n_kernels++; rt.stats.n_tape_kernels++; rt.stats.n_tape_instr += total;
     }
 };

@@ -203,10 +203,11 @@ void Runtime::profile_begin() {
     }
     FMC_CUDA(cudaEventRecord(prof_events[prof_used].first, stream));
 }
-void Runtime::profile_end(uint64_t algorithmic_bytes) {
+void Runtime::profile_end(uint64_t algorithmic_bytes, uint64_t touched_bytes) {
     FMC_CUDA(cudaEventRecord(prof_events[prof_used].second, stream));
     prof_used++;
     prof_bytes += algorithmic_bytes;
+    prof_touched += touched_bytes ? touched_bytes : algorithmic_bytes;
     prof_launches++;
 }
 void Runtime::profile_read(double* ms, uint64_t* bytes, uint64_t* launches) {
@@ -220,7 +221,7 @@ void Runtime::profile_read(double* ms, uint64_t* bytes, uint64_t* launches) {
     if (ms) *ms = total;
     if (bytes) *bytes = prof_bytes;
     if (launches) *launches = prof_launches;
-    prof_used = 0; prof_bytes = 0; prof_launches = 0;
+    prof_used = 0; prof_bytes = 0; prof_launches = 0; prof_touched = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------

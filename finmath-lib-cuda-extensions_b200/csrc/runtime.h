@@ -167,9 +167,9 @@ public:
     // profile mode: event pairs around interpreter launches + their algorithmic bytes
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
-    uint64_t prof_bytes = 0, prof_launches = 0;
+    uint64_t prof_bytes = 0, prof_launches = 0, prof_touched = 0;   // touched: every vector a kernel reads or writes, re-reads of earlier results included
     void profile_begin();                                  // records the start event of the next launch
-    void profile_end(uint64_t algorithmic_bytes);
+    void profile_end(uint64_t algorithmic_bytes, uint64_t touched_bytes = 0);
     void profile_read(double* ms, uint64_t* bytes, uint64_t* launches);   // synchronises, sums, resets
 
     // handles
