@@ -496,9 +496,10 @@ int fmc_regression_normal_eq(const fmc_vec* basis, const double* scalars, int k,
             P.scalars[i] = bidx[i] >= 0 ? 0.f : (float)scalars[i];
         }
         P.partials = rt.d_partials; P.counter = rt.d_counter + 1; P.result = rt.d_result + 64;
-        static int per_sm = 0;
-        if (!per_sm) per_sm = regression_max_blocks_per_sm();
-        const int64_t tiles = (n + 1023) / 1024;
+        static int per_sm_k[REG_MAX_K + 1] = {0};
+        if (!per_sm_k[k]) per_sm_k[k] = regression_max_blocks_per_sm(k);
+        const int per_sm = per_sm_k[k];
+        const int64_t tiles = (n + regression_tile_elems() - 1) / regression_tile_elems();
         int grid = (int)std::min<int64_t>(tiles, (int64_t)per_sm * rt.sm_count);
         grid = std::max(1, std::min(grid, rt.max_grid));
         FMC_CUDA(launch_regression(P, grid, rt.stream));

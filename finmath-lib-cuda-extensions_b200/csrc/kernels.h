@@ -42,7 +42,8 @@ struct RegressionParams {
     double* result;                  // [k*(k+1)/2 + k] sums (not yet divided by n)
 };
 cudaError_t launch_regression(const RegressionParams& P, int grid, cudaStream_t stream);
-int regression_max_blocks_per_sm();
+int regression_max_blocks_per_sm(int k);
+int regression_tile_elems();
 
 // brownian_kernel.cu — MT19937 (commons-math3 stream) with jump-ahead + AS241 inverse normal.
 constexpr int MT_N = 624;

@@ -363,7 +363,8 @@ cudaError_t launch_regression(const RegressionParams& P, int, cudaStream_t) {
     for (size_t t = 0; t < acc.size(); t++) P.result[t] = acc[t];
     return cudaSuccess;
 }
-int regression_max_blocks_per_sm() { return 1; }
+int regression_max_blocks_per_sm(int) { return 1; }
+int regression_tile_elems() { return 2048; }
 cudaError_t launch_reduce(const ReduceParams& P, int, cudaStream_t) {
     double c = 0, s = 0, m2 = 0, mn = 0, mx = 0;
     std::vector<double> vals;
