@@ -16,12 +16,26 @@
 #include <chrono>
 #include <cstring>
 #include <map>
+#include <memory>
 
 #include "runtime.h"
 
 namespace fmc {
 
 namespace {
+
+// FMC_HOST_PROFILE=1: wall time per code-generation phase, printed at exit (development aid)
+struct PhaseClock {
+    double us[8] = {0}; const char* name[8] = {"collect", "classify", "emit", "peephole", "schedule", "launch-prep", "bookkeeping", "other"};
+    bool on = std::getenv("FMC_HOST_PROFILE") != nullptr;
+    ~PhaseClock() { if (on) for (int i = 0; i < 8; i++) std::fprintf(stderr, "[fmc host] %-12s %10.1f us\n", name[i], us[i]); }
+};
+PhaseClock g_phase;
+struct PhaseTimer {
+    int id; std::chrono::steady_clock::time_point t0;
+    explicit PhaseTimer(int i) : id(i), t0(std::chrono::steady_clock::now()) {}
+    ~PhaseTimer() { if (g_phase.on) g_phase.us[id] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 constexpr int32_t NO_USE = 0x7fffffff;
 
@@ -42,6 +56,7 @@ struct Info {
 enum AKind : uint8_t { K_NONE = 0, K_IMM, K_REG, K_LEAF };
 enum BinOp : uint16_t { B_MOV = 0, B_ADD, B_SUB, B_BUS, B_MUL, B_DIV, B_VID, B_MIN, B_MAX, B_SEL, B_ADDPROD, B_ACCRUE, B_DISCOUNT };
 constexpr uint16_t A_BIN = 0x100;   // AIns::op = A_BIN | BinOp for binary instructions, a plain TapeOp otherwise
+constexpr uint16_t A_EXT = 0x200;   // extension word of the two-word instruction before it: y = second immediate
 struct AIns {
     uint16_t op;
     uint8_t kind;
@@ -341,6 +356,22 @@ struct Gen {
         int leaf_refs = 0;
         for (size_t i = 0; i < A.size(); i++) {
             const AIns& a = A[i];
+            // STR t ; MOV x ; ADD_I|SUB_I a ; MUL_I b ; ADD_S t   -> ADDAFF x, +-a, b     (t dead afterwards)
+            if (i + 4 < A.size() && a.op == T_STR && a.kind == K_REG
+                && A[i + 1].op == (A_BIN | B_MOV) && (A[i + 1].kind == K_REG || A[i + 1].kind == K_LEAF)
+                && !(A[i + 1].kind == K_REG && A[i + 1].arg == a.arg)
+                && (A[i + 2].op == (A_BIN | B_ADD) || A[i + 2].op == (A_BIN | B_SUB)) && A[i + 2].kind == K_IMM
+                && A[i + 3].op == (A_BIN | B_MUL) && A[i + 3].kind == K_IMM
+                && A[i + 4].op == (A_BIN | B_ADD) && A[i + 4].kind == K_REG && A[i + 4].arg == a.arg
+                && reg_dead_after(i + 5, a.arg)) {
+                const uint32_t first = A[i + 2].op == (A_BIN | B_SUB) ? (A[i + 2].y ^ 0x80000000u) : A[i + 2].y;
+                // y = first immediate, arg of the following pseudo-entry = second immediate (see schedule)
+                out.push_back(AIns{(uint16_t)T_ADDAFF_S, A[i + 1].kind, A[i + 1].arg, first});
+                out.push_back(AIns{A_EXT, K_NONE, 0, A[i + 3].y});
+                if (A[i + 1].kind == K_LEAF) leaf_refs++;
+                i += 4;
+                continue;
+            }
             if (i + 3 < A.size() && a.op == T_STR && a.kind == K_REG
                 && A[i + 1].op == (A_BIN | B_MOV) && (A[i + 1].kind == K_REG || A[i + 1].kind == K_LEAF)
                 && !(A[i + 1].kind == K_REG && A[i + 1].arg == a.arg)
@@ -474,13 +505,17 @@ struct Gen {
                 Event& E = ev[e];
                 const uint32_t fl = E.waited ? 1u : 2u;        // _S / _W
                 E.waited = true;
-                body.push_back(TapeInstr{ (T_BIN0 + 3u * (uint32_t)(a.op & 0xff) + fl) | ((uint32_t)E.slot << TAPE_SLOT_SHIFT), a.y });
+                const uint32_t opc = (a.op == T_ADDAFF_S) ? (fl == 1u ? (uint32_t)T_ADDAFF_S : (uint32_t)T_ADDAFF_W)
+                                                          : T_BIN0 + 3u * (uint32_t)(a.op & 0xff) + fl;
+                body.push_back(TapeInstr{ opc | ((uint32_t)E.slot << TAPE_SLOT_SHIFT), a.y });
                 E.k++;
                 if (E.k >= E.use.size()) refill(E.slot);
             } else if (a.op & A_BIN) {
                 const uint32_t bop = T_BIN0 + 3u * (uint32_t)(a.op & 0xff);
                 if (a.kind == K_IMM) body.push_back(TapeInstr{ bop, a.y });
                 else body.push_back(TapeInstr{ (bop + 1u) | ((R + (uint32_t)a.arg) << TAPE_SLOT_SHIFT), a.y });
+            } else if (a.op == A_EXT) {
+                body.push_back(TapeInstr{ T_END, a.y });                  // only its y is read
             } else if (a.op == T_MULADD_II || a.op == T_ADDMUL_II) {
                 body.push_back(TapeInstr{ (uint32_t)a.op, a.y });
                 body.push_back(TapeInstr{ T_END, (uint32_t)a.arg });      // extension word: only its y is read
@@ -509,7 +544,7 @@ struct Gen {
             emit(T_END, K_REG, vreg);
         } else emit(T_END);
         if (A.size() <= 1 && reduce_mode == RM_NONE) return;   // nothing to do
-        if (rt.opt.fuse_ops) peephole();
+        { PhaseTimer pt(3); if (rt.opt.fuse_ops) peephole(); }
 
         std::vector<TapeInstr> prologue, body;
         int n_ring = 0;
@@ -531,7 +566,8 @@ struct Gen {
         const int slot_budget = (int)std::max<long>(1, budget_bytes / (n_warps * TAPE_SLOT_BYTES));
         int ring_max = std::max(1, std::min<int>(rt.opt.ring_max, TAPE_MAX_RING));
         ring_max = std::min(ring_max, std::max(rt.opt.ring_min, slot_budget - regs_used));
-        schedule(ring_max, rt.opt.pipeline, rt.opt.horizon, prologue, body, n_ring);
+        { PhaseTimer pt(4); schedule(ring_max, rt.opt.pipeline, rt.opt.horizon, prologue, body, n_ring); }
+        PhaseTimer pt_prep(5);
         const size_t total = prologue.size() + 1 + body.size();
         if (total > (size_t)TAPE_MAX_INSTR + 1 || ptrs.size() > (size_t)TAPE_MAX_PTRS)
             fail(FMC_ERR_UNSUPPORTED, "internal: tape overflow (%zu instr, %zu ptrs)", total, ptrs.size());
@@ -605,6 +641,7 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
     if (epoch == 0) { for (auto& nd : nodes) nd.epoch = 0; epoch = 1; }
     stats.n_flushes++;
 
+    std::unique_ptr<PhaseTimer> ph(new PhaseTimer(0));
     // ---- 1. collect the cone of lazy nodes, in depth-first post-order from the targets ----
     // Post-order (operands first, each value as late as its first consumer allows) keeps few intermediates alive at a
     // time: e.g. an Euler step whose caller computed all 80 drifts before applying any of them is emitted component
@@ -678,6 +715,7 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
         g.info[target_local].uses++;   // the reduction epilogue reads it from acc
     }
 
+    ph.reset(); ph.reset(new PhaseTimer(1));
     // ---- 2. store / ephemeral classification (reverse topological order) ----
     for (int32_t L = n_cone - 1; L >= 0; L--) {
         Info& f = g.info[L];
@@ -714,6 +752,7 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
         if (target_local >= 0) add_use(target_local, n_cone);
     }
 
+    ph.reset(); ph.reset(new PhaseTimer(2));
     // ---- 3. emit ----
     g.begin_kernel();
     for (int32_t L = 0; L < n_cone; L++) {
@@ -733,6 +772,7 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
         g.launch(RM_NONE, 0.0, -1);
     }
 
+    ph.reset(); ph.reset(new PhaseTimer(6));
     // ---- 4. bookkeeping: stored / spilled nodes become materialised and drop their operands ----
     for (int32_t L = 0; L < n_cone; L++) {
         Info& f = g.info[L];

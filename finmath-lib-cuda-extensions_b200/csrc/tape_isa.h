@@ -62,6 +62,8 @@ enum TapeOp : uint32_t {
     FMC_TAPE_BINOPS(FMC_X)
 #undef FMC_X
     T_ADDMUL_II,     // acc = (acc + imm) * imm2            (two words, two roundings; SUB_I a is ADD_I -a exactly)
+    T_ADDAFF_S,      // acc = acc + (slot + imm) * imm2     (two words, three roundings: a payoff added to a running value)
+    T_ADDAFF_W,      //   ... on a ring slot whose copy has not been waited for yet
     T_NUM_OPS
 };
 constexpr uint32_t T_BIN0 = 20;
@@ -70,7 +72,7 @@ constexpr uint32_t T_BIN0 = 20;
 //   MIN Math.min(acc, b)   MAX Math.max(acc, b)   (NaN propagating, -0 < +0)      SEL p ? acc : b
 //   ADDPROD  acc + b * s        ACCRUE  acc * (1 + b * s)        DISCOUNT  acc / (1 + b * s)     (_S/_W only)
 static_assert(T_MOV_I == T_BIN0, "binary opcode layout");
-static_assert(T_ADDMUL_II == T_BIN0 + 39 && T_NUM_OPS == T_BIN0 + 40, "binary opcode layout");
+static_assert(T_ADDMUL_II == T_BIN0 + 39 && T_ADDAFF_W == T_BIN0 + 41 && T_NUM_OPS == T_BIN0 + 42, "binary opcode layout");
 
 enum ReduceMode : int {
     RM_NONE = 0,

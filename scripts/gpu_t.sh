@@ -1,2 +1,4 @@
-timeout -s KILL 600 python -m pytest tests -m gpu -q 2>&1 | tail -6
-timeout -s KILL 300 python benchmarks/raw_ops.py --sizes 1000000,100000000 --cases b4 --out gpurun_out/raw_b4.json 2>&1 | grep B4
+timeout -s KILL 600 python -m pytest tests -m gpu -q 2>&1 | tail -4
+timeout -s KILL 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print('ms_per_step',round(d['ms_per_step'],2),'kernel_ms',round(d['roofline']['kernel_ms_per_step'],2),'e2e_ms',round(d['e2e']['ms_per_step'],1), 'frac', round(d['roofline']['frac'],3), d['host_profile'])"

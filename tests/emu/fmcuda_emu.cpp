@@ -174,6 +174,15 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
                 }
                 break;
             }
+            if (op == T_ADDAFF_S || op == T_ADDAFF_W) {
+                if (pc + 1 >= P.n_instr) bad("two-word instruction at the end of the tape");
+                float imm2; std::memcpy(&imm2, &P.instr[pc + 1].y, 4);
+                if (op == T_ADDAFF_W) w.wait(slot);
+                const float* b = w.read(slot, chunk);
+                for (int e = 0; e < C; e++) { float t = b[e] + imm; t = t * imm2; acc[e] = acc[e] + t; }
+                pc++;
+                continue;
+            }
             if (op == T_ADDMUL_II) {
                 if (pc + 1 >= P.n_instr) bad("two-word instruction at the end of the tape");
                 float imm2; std::memcpy(&imm2, &P.instr[pc + 1].y, 4);
@@ -291,6 +300,7 @@ void dump_tape(const TapeParams& P, int grid) {
         const uint32_t op = P.instr[i].x & ((1u << TAPE_SLOT_SHIFT) - 1u), slot = P.instr[i].x >> TAPE_SLOT_SHIFT;
         float imm; std::memcpy(&imm, &P.instr[i].y, 4);
         if (op == T_ADDMUL_II) std::fprintf(stderr, "  %4d ADDMUL_II %g\n", i, imm);
+        else if (op == T_ADDAFF_S || op == T_ADDAFF_W) std::fprintf(stderr, "  %4d ADDAFF_%c s%u %g\n", i, op == T_ADDAFF_S ? 'S' : 'W', slot, imm);
         else if (op >= T_BIN0) {
             const uint32_t k = (op - T_BIN0) / 3u, fl = (op - T_BIN0) % 3u;
             if (fl == 0) std::fprintf(stderr, "  %4d %s_I %g\n", i, bins[k], imm);
