@@ -10,9 +10,10 @@ from ._capi import CudaError, ensure_init, set_option, shutdown, stats
 from .random_variable import RandomVariable, RandomVariableCuda, RandomVariableCudaFactory
 from .brownian_motion import BrownianMotionCuda, TimeDiscretization
 from .conditional_expectation import MonteCarloConditionalExpectationRegression
+from .differentiable import RandomVariableDifferentiableAAD, RandomVariableDifferentiableAADFactory
 from . import distributed
 
 __all__ = [
     "RandomVariable", "RandomVariableCuda", "RandomVariableCudaFactory", "BrownianMotionCuda", "TimeDiscretization",
-    "MonteCarloConditionalExpectationRegression", "CudaError", "ensure_init", "shutdown", "stats", "set_option", "distributed",
+    "MonteCarloConditionalExpectationRegression", "RandomVariableDifferentiableAAD", "RandomVariableDifferentiableAADFactory", "CudaError", "ensure_init", "shutdown", "stats", "set_option", "distributed",
 ]

@@ -1,0 +1,104 @@
+"""Config 4 of BASELINE.json: delta / vega by backward-mode AAD with RandomVariableDifferentiableAAD wrapping
+RandomVariableCuda (README.md:50-52 of the reference: the AAD wrapper composes with the GPU type and has the higher
+type priority). Every primal AND adjoint operation goes through RandomVariableCuda's own methods, i.e. through the C ABI
+and the fused interpreter; gradients are checked against finite differences of the same GPU computation, against
+numpy, and against the Black-Scholes closed forms."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_type_priority_aad_over_gpu_over_cpu(fc):
+    x = fc.RandomVariableCuda(0.0, np.linspace(0.5, 1.5, 1000))
+    ax = fc.RandomVariableDifferentiableAAD(x)
+    assert ax.getTypePriority() > x.getTypePriority() == 20
+    # a plain GPU vector hands the operation over to the differentiable operand (mirror methods, RVF:962-1178)
+    for name in ("add", "sub", "mult", "div", "cap", "floor"):
+        r = getattr(x, name)(ax)
+        assert isinstance(r, fc.RandomVariableDifferentiableAAD), name
+        want = getattr(x, name)(x).getRealizationsFloat()
+        assert np.array_equal(r.getRealizations().astype(np.float32), want), name
+    assert isinstance(x.accrue(ax, 0.5), fc.RandomVariableDifferentiableAAD)
+    assert isinstance(x.discount(ax, 0.5), fc.RandomVariableDifferentiableAAD)
+    assert isinstance(x.addProduct(ax, 2.0), fc.RandomVariableDifferentiableAAD)
+
+
+def test_gradient_of_an_op_chain_matches_finite_differences(fc):
+    n = 50_000
+    rng = np.random.default_rng(5)
+    x0 = (rng.random(n) + 0.5); y0 = (rng.random(n) + 0.5)
+
+    def f_np(x, y):
+        u = x * y + np.exp(0.3 * x) - np.log(y) / (1.0 + 0.5 * x)
+        v = np.sqrt(u * u + 1.0) * (1.0 + y * 0.25)             # accrue(y, 0.25)
+        w = np.maximum(v - 2.0, 0.0) + np.minimum(x, 1.0) + 1.0 / y
+        return np.where(x - 1.0 >= 0, w * x, w + y * y)         # choose
+
+    def f_rv(X, Y):
+        u = X.mult(Y).add(X.mult(0.3).exp()).sub(Y.log().div(X.mult(0.5).add(1.0)))
+        v = u.squared().add(1.0).sqrt().accrue(Y, 0.25)
+        w = v.sub(2.0).floor(0.0).add(X.cap(1.0)).add(Y.invert())
+        return X.sub(1.0).choose(w.mult(X), w.addProduct(Y, Y))
+
+    X = fc.RandomVariableDifferentiableAAD(fc.RandomVariableCuda(0.0, x0))
+    Y = fc.RandomVariableDifferentiableAAD(fc.RandomVariableCuda(0.0, y0))
+    F = f_rv(X, Y)
+    x32, y32 = x0.astype(np.float32).astype(np.float64), y0.astype(np.float32).astype(np.float64)
+    assert np.allclose(F.getRealizations(), f_np(x32, y32), rtol=2e-5, atol=2e-5)
+    g = F.getGradient()
+    h = 1e-6
+    dfdx = (f_np(x32 + h, y32) - f_np(x32 - h, y32)) / (2 * h)
+    dfdy = (f_np(x32, y32 + h) - f_np(x32, y32 - h)) / (2 * h)
+    # away from the kinks of floor / cap / choose
+    smooth = (np.abs(x32 - 1.0) > 1e-3) & (np.abs(np.sqrt((x32 * y32 + np.exp(0.3 * x32) - np.log(y32) / (1.0 + 0.5 * x32)) ** 2 + 1.0) * (1.0 + y32 * 0.25) - 2.0) > 1e-3)
+    gx, gy = g[X.getID()].getRealizations(), g[Y.getID()].getRealizations()
+    assert np.allclose(gx[smooth], dfdx[smooth], rtol=2e-3, atol=2e-3)
+    assert np.allclose(gy[smooth], dfdy[smooth], rtol=2e-3, atol=2e-3)
+
+
+def _norm_cdf(x): return 0.5 * (1.0 + math.erf(x / math.sqrt(2.0)))
+
+
+def test_black_scholes_delta_and_vega_by_aad_on_the_gpu(fc):
+    """MonteCarloBlackScholesModelTest.java:62-76 constants; Euler scheme in log-coordinates over BrownianMotionCuda."""
+    n, steps, T = 200_000, 20, 2.0
+    S0, r, sigma, K = 1.0, 0.05, 0.30, 1.05
+    dt = T / steps
+    td = fc.TimeDiscretization(0.0, steps, dt)
+    bm = fc.BrownianMotionCuda(td, 1, n, 31415)
+    fac = fc.RandomVariableDifferentiableAADFactory(fc.RandomVariableCudaFactory())
+
+    def price(s0, sig):
+        x = s0.log()
+        drift = sig.squared().mult(-0.5).add(r).mult(dt)
+        for t in range(steps):
+            x = x.add(drift).add(sig.mult(bm.getBrownianIncrement(t, 0)))
+        payoff = x.exp().sub(K).floor(0.0).mult(math.exp(-r * T))
+        return payoff.average()
+
+    s0, sig = fac.createRandomVariable(0.0, S0), fac.createRandomVariable(0.0, sigma)
+    k0 = fc.stats()["n_tape_kernels"]
+    V = price(s0, sig)
+    grad = V.getGradient()
+    delta, vega = grad[s0.getID()].getAverage(), grad[sig.getID()].getAverage()
+    kernels = fc.stats()["n_tape_kernels"] - k0
+    d1 = (math.log(S0 / K) + (r + 0.5 * sigma * sigma) * T) / (sigma * math.sqrt(T))
+    delta_bs, vega_bs = _norm_cdf(d1), S0 * math.sqrt(T) * math.exp(-0.5 * d1 * d1) / math.sqrt(2 * math.pi)
+    value_bs = S0 * _norm_cdf(d1) - K * math.exp(-r * T) * _norm_cdf(d1 - sigma * math.sqrt(T))
+    assert abs(V.doubleValue() - value_bs) < 0.005                     # MonteCarloBlackScholesModelTest.java:156
+    assert abs(delta - delta_bs) < 0.01 and abs(vega - vega_bs) < 0.02
+    # against bump-and-revalue of the SAME GPU computation (same Brownian paths): pathwise derivative == finite difference
+    plain = fc.RandomVariableCudaFactory()
+
+    def price_plain(s0v, sigv):
+        class W:                                                       # plain GPU variables through the same code
+            pass
+        return price(fc.RandomVariableDifferentiableAAD(plain.createRandomVariable(0.0, s0v)),
+                     fc.RandomVariableDifferentiableAAD(plain.createRandomVariable(0.0, sigv))).doubleValue()
+    h = 1e-3
+    assert abs(delta - (price_plain(S0 + h, sigma) - price_plain(S0 - h, sigma)) / (2 * h)) < 2e-3
+    assert abs(vega - (price_plain(S0, sigma + h) - price_plain(S0, sigma - h)) / (2 * h)) < 3e-3
+    assert kernels < 40, f"primal + adjoint sweep should fuse into a few launches, used {kernels}"
