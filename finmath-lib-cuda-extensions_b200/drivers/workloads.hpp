@@ -286,23 +286,50 @@ public:
         for (size_t i = 1; i < basis_.size(); i++) est = est->addProduct(basis_[i], c[i]);
         return est;
     }
-    // symmetric positive (semi-)definite solve by Cholesky with diagonal regularisation (k <= 12, host double)
+    // Minimum-norm least-squares solution of the symmetric k x k system (k <= 12, host double), the job finmath-lib gives to
+    // commons-math3's SingularValueDecomposition solver: cyclic Jacobi eigen-decomposition A = V diag(w) V^T, components
+    // whose eigenvalue is below 1e-10 of the largest are dropped. The basis of a Bermudan regression (1, discount factor,
+    // its square, ...) is nearly collinear: the normal equations have condition numbers of 1e12 and beyond, and a plain
+    // Cholesky solve turns the last bits of the float products into O(1) coefficient noise (exercise decisions flip).
     static std::vector<double> solve_spd(std::vector<double> A, std::vector<double> b, int k) {
-        double tr = 0; for (int i = 0; i < k; i++) tr += A[(size_t)i * k + i];
-        const double eps = 1e-14 * (tr > 0 ? tr : 1.0);
-        for (int i = 0; i < k; i++) A[(size_t)i * k + i] += eps;
-        for (int j = 0; j < k; j++) {
-            for (int m = 0; m < j; m++) A[(size_t)j * k + j] -= A[(size_t)j * k + m] * A[(size_t)j * k + m];
-            const double d = std::sqrt(std::max(A[(size_t)j * k + j], 1e-300));
-            A[(size_t)j * k + j] = d;
-            for (int i = j + 1; i < k; i++) {
-                for (int m = 0; m < j; m++) A[(size_t)i * k + j] -= A[(size_t)i * k + m] * A[(size_t)j * k + m];
-                A[(size_t)i * k + j] /= d;
-            }
+        std::vector<double> V((size_t)k * k, 0.0);
+        for (int i = 0; i < k; i++) V[(size_t)i * k + i] = 1.0;
+        auto a = [&](int i, int j) -> double& { return A[(size_t)i * k + j]; };
+        for (int sweep = 0; sweep < 60; sweep++) {
+            double off = 0.0, diag = 0.0;
+            for (int i = 0; i < k; i++) { diag += a(i, i) * a(i, i); for (int j = i + 1; j < k; j++) off += a(i, j) * a(i, j); }
+            if (off <= 1e-32 * diag) break;
+            for (int p = 0; p < k; p++)
+                for (int q = p + 1; q < k; q++) {
+                    if (a(p, q) == 0.0) continue;
+                    const double theta = (a(q, q) - a(p, p)) / (2.0 * a(p, q));
+                    const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                    const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+                    for (int m = 0; m < k; m++) {                      // A <- A J  (columns p, q)
+                        const double amp = a(m, p), amq = a(m, q);
+                        a(m, p) = c * amp - sn * amq; a(m, q) = sn * amp + c * amq;
+                    }
+                    for (int m = 0; m < k; m++) {                      // A <- J^T A  (rows p, q)
+                        const double apm = a(p, m), aqm = a(q, m);
+                        a(p, m) = c * apm - sn * aqm; a(q, m) = sn * apm + c * aqm;
+                    }
+                    for (int m = 0; m < k; m++) {                      // V <- V J
+                        const double vmp = V[(size_t)m * k + p], vmq = V[(size_t)m * k + q];
+                        V[(size_t)m * k + p] = c * vmp - sn * vmq; V[(size_t)m * k + q] = sn * vmp + c * vmq;
+                    }
+                }
         }
-        for (int i = 0; i < k; i++) { for (int m = 0; m < i; m++) b[(size_t)i] -= A[(size_t)i * k + m] * b[(size_t)m]; b[(size_t)i] /= A[(size_t)i * k + i]; }
-        for (int i = k - 1; i >= 0; i--) { for (int m = i + 1; m < k; m++) b[(size_t)i] -= A[(size_t)m * k + i] * b[(size_t)m]; b[(size_t)i] /= A[(size_t)i * k + i]; }
-        return b;
+        double wmax = 0.0;
+        for (int i = 0; i < k; i++) wmax = std::max(wmax, std::fabs(a(i, i)));
+        std::vector<double> x((size_t)k, 0.0);
+        for (int e = 0; e < k; e++) {
+            const double w = a(e, e);
+            if (!(std::fabs(w) > 1e-10 * wmax)) continue;
+            double proj = 0.0;
+            for (int m = 0; m < k; m++) proj += V[(size_t)m * k + e] * b[(size_t)m];
+            for (int m = 0; m < k; m++) x[(size_t)m] += V[(size_t)m * k + e] * proj / w;
+        }
+        return x;
     }
 private:
     std::vector<RV> basis_;

@@ -43,7 +43,7 @@ class MonteCarloConditionalExpectationRegression:
     def getLinearRegressionParameters(self, dependents: RandomVariable) -> np.ndarray:
         XtX, XtY = normal_equations(self.basisFunctionsEstimator, dependents)
         # commons-math3 SingularValueDecomposition(XTX).getSolver().solve(XTY): minimum-norm least squares
-        return np.linalg.lstsq(XtX, XtY, rcond=None)[0]
+        return np.linalg.lstsq(XtX, XtY, rcond=1e-10)[0]
 
     def getConditionalExpectation(self, randomVariable: RandomVariable) -> RandomVariable:
         coeff = self.getLinearRegressionParameters(randomVariable)
