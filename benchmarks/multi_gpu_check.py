@@ -3,6 +3,7 @@
 seeded global vectors; reductions and regression normal equations must equal the single-process numpy values of the FULL
 vectors within 1e-5 relative (north-star tolerance), for every world size.
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 benchmarks/multi_gpu_check.py"""
+import math
 import os
 import sys
 
@@ -42,6 +43,12 @@ checks = {
     "min(chain)": (Z.getMin(), float(z.min())),
     "max(leaf)": (X.getMax(), float(x.max())),
     "average(leaf, prob)": (X.getAverage(Y), (x.astype(np.float64) * y.astype(np.float64)).sum() / n),
+    # order statistics of the SHARDED vector: radix-select histograms are all-reduced, the selected element is exact
+    "quantile(0.95)": (X.getQuantile(0.95), float(np.sort(x)[min(max(int(math.floor((n + 1) * 0.95 - 1.0 + 0.5)), 0), n - 1)])),
+    "quantile(0.0)": (X.getQuantile(0.0), float(x.min())),
+    "quantileExpectation(0.1,0.9)": (X.getQuantileExpectation(0.1, 0.9), float(np.sort(x).astype(np.float64)[
+        min(max(int(math.floor((n + 1) * 0.1 - 0.5)), 0), n - 1):min(max(int(math.floor((n + 1) * 0.9 - 0.5)), 0), n - 1) + 1].mean())),
+    "histogram[2]": (float(X.getHistogram(np.array([-1.0, 0.0, 1.0]))[2]), float(((x > 0.0) & (x <= 1.0)).sum()) / n),
 }
 ok = True
 for name, (got, want) in checks.items():

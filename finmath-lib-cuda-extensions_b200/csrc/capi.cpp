@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 
 #include "runtime.h"
@@ -540,66 +541,118 @@ int fmc_mt19937_raw(int seed_mode, int64_t seed, uint64_t skip, int64_t count, u
     return guarded([&](Runtime& rt) { rt.require_init(); mt19937_raw(rt, seed_mode, seed, skip, count, host_out); });
 }
 
-// ---- order statistics (RVF:472-602) ----
-// Round 1: the vector is downloaded through the pinned staging path and sorted on the host exactly like the
-// reference does (RandomVariableCuda.java:970-1091); an on-device radix select is the "next" item n2 of SURVEY §8f.
+// ---- order statistics (RVF:472-602): radix select on the device (order_kernel.cu), also for sharded vectors ----
 namespace {
-std::vector<float> sorted_host_copy(Runtime& rt, int32_t idx) {
-    std::vector<float> v((size_t)rt.nodes[idx].n);
-    rt.download_f32(idx, v.data(), (int64_t)v.size());
-    // java.util.Arrays.sort(float[]) order: -0.0f < 0.0f, NaN last
-    std::sort(v.begin(), v.end(), [](float a, float b) {
-        if (a != a) return false;
-        if (b != b) return true;
-        if (a == 0.f && b == 0.f) return std::signbit(a) && !std::signbit(b);
-        return a < b;
-    });
-    return v;
-}
 int64_t quantile_index(int64_t n, double q) {                                    // RVF:484
     long long idx = (long long)std::floor((double)(n + 1) * q - 1.0 + 0.5);
     return std::min<long long>(std::max<long long>(idx, 0), n - 1);
+}
+uint32_t sort_key_host(float f) {
+    if (f != f) return 0xffffffffu;
+    uint32_t u; std::memcpy(&u, &f, 4);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+float key_to_float(uint32_t key) {
+    if (key == 0xffffffffu) return NAN;
+    const uint32_t u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+    float f; std::memcpy(&f, &u, 4);
+    return f;
+}
+int order_grid(Runtime& rt, int64_t n) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>((n + 4095) / 4096, (int64_t)rt.sm_count * 8));
+}
+// device scratch d_result[512 .. 512+count) zeroed, kernel by `launch`, summed over the ranks, copied to h_result[512..]
+const double* order_pass(Runtime& rt, int count, const std::function<void(double*)>& launch) {
+    double* d = rt.d_result + 512;
+    FMC_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * (size_t)count, rt.stream));
+    launch(d);
+    rt.stats.n_kernels++;
+    if (rt.comm_size > 1) rt.allreduce_sum(d, count);
+    FMC_CUDA(cudaMemcpyAsync(rt.h_result + 512, d, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, rt.stream));
+    FMC_CUDA(cudaStreamSynchronize(rt.stream));
+    rt.stats.d2h += sizeof(double) * (uint64_t)count;
+    return rt.h_result + 512;
+}
+int64_t global_size(Runtime& rt, int64_t local_n) {
+    if (rt.comm_size <= 1) return local_n;
+    double cnt = (double)local_n;
+    FMC_CUDA(cudaMemcpyAsync(rt.d_result + 200, &cnt, sizeof(double), cudaMemcpyHostToDevice, rt.stream));
+    rt.allreduce_sum(rt.d_result + 200, 1);
+    FMC_CUDA(cudaMemcpyAsync(rt.h_result + 200, rt.d_result + 200, sizeof(double), cudaMemcpyDeviceToHost, rt.stream));
+    FMC_CUDA(cudaStreamSynchronize(rt.stream));
+    return (int64_t)rt.h_result[200];
+}
+// key of the element with (global) rank r in Arrays.sort order; optionally the number of elements below that key
+uint32_t select_key(Runtime& rt, const float* x, int64_t n, int64_t r) {
+    uint32_t prefix = 0u, mask = 0u;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        const double* h = order_pass(rt, 256, [&](double* d) { FMC_CUDA(launch_select_hist(x, n, prefix, mask, shift, d, order_grid(rt, n), rt.stream)); });
+        int64_t cum = 0; int digit = 255;
+        for (int b = 0; b < 256; b++) {
+            const int64_t c = (int64_t)h[b];
+            if (r < cum + c) { digit = b; break; }
+            cum += c;
+        }
+        r -= cum;
+        prefix |= (uint32_t)digit << shift;
+        mask |= 0xffu << shift;
+    }
+    return prefix;
 }
 }  // namespace
 
 int fmc_quantile(fmc_vec a, double q, double* out) {
     return guarded([&](Runtime& rt) {
         rt.require_init();
-        if (rt.comm_size > 1) fail(FMC_ERR_UNSUPPORTED, "quantile of a sharded vector is not implemented");
         const int32_t x = rt.resolve(a);
-        if (rt.nodes[x].n == 0) { *out = NAN; return; }
-        auto v = sorted_host_copy(rt, x);
-        *out = v[(size_t)quantile_index((int64_t)v.size(), q)];
+        rt.materialize(x);
+        const int64_t n = rt.nodes[x].n, N = global_size(rt, n);
+        if (N == 0) { *out = NAN; return; }
+        *out = (double)key_to_float(select_key(rt, rt.nodes[x].buf, n, quantile_index(N, q)));
     });
 }
 int fmc_quantile_expectation(fmc_vec a, double q0, double q1, double* out) {
     return guarded([&](Runtime& rt) {
         rt.require_init();
-        if (rt.comm_size > 1) fail(FMC_ERR_UNSUPPORTED, "quantile of a sharded vector is not implemented");
         const int32_t x = rt.resolve(a);
-        if (rt.nodes[x].n == 0) { *out = NAN; return; }
+        rt.materialize(x);
+        const int64_t n = rt.nodes[x].n, N = global_size(rt, n);
+        if (N == 0) { *out = NAN; return; }
         if (q0 > q1) std::swap(q0, q1);                                          // RVF:509-511
-        auto v = sorted_host_copy(rt, x);
-        const int64_t i0 = quantile_index((int64_t)v.size(), q0), i1 = quantile_index((int64_t)v.size(), q1);
-        double e = 0.0;
-        for (int64_t i = i0; i <= i1; i++) e += v[(size_t)i];                    // RVF:519-523
+        const int64_t i0 = quantile_index(N, q0), i1 = quantile_index(N, q1);
+        const float* buf = rt.nodes[x].buf;
+        const uint32_t k0 = select_key(rt, buf, n, i0), k1 = select_key(rt, buf, n, i1);
+        // mean of sorted[i0 .. i1] (RVF:519-523): everything strictly between the two values plus the copies of the boundary
+        // values whose ranks fall inside the range
+        const double* s = order_pass(rt, 5, [&](double* d) { FMC_CUDA(launch_range_stats(buf, n, k0, k1, d, order_grid(rt, n), rt.stream)); });
+        const double v0 = (double)key_to_float(k0), v1 = (double)key_to_float(k1);
+        const int64_t lt0 = (int64_t)s[0], eq0 = (int64_t)s[1], mid = (int64_t)s[2], eq1 = (int64_t)s[4];
+        double e;
+        if (k0 == k1) e = v0 * (double)(i1 - i0 + 1);
+        else {
+            const int64_t n0 = lt0 + eq0 - i0;                                   // copies of v0 with rank >= i0
+            const int64_t n1 = i1 - (lt0 + eq0 + mid) + 1;                       // copies of v1 with rank <= i1
+            (void)eq1;
+            e = v0 * (double)n0 + s[3] + v1 * (double)n1;
+        }
         *out = e / (double)(i1 - i0 + 1);
     });
 }
 int fmc_histogram(fmc_vec a, const double* pts, int m, double* out) {
     return guarded([&](Runtime& rt) {
         rt.require_init();
-        if (rt.comm_size > 1) fail(FMC_ERR_UNSUPPORTED, "histogram of a sharded vector is not implemented");
+        if (m < 0 || m > 100) fail(FMC_ERR_INVALID, "histogram: %d interval points (at most 100)", m);
         const int32_t x = rt.resolve(a);
-        auto v = sorted_host_copy(rt, x);
-        size_t si = 0;
-        for (int k = 0; k < m; k++) {                                            // RVF:558-569
-            size_t c = 0;
-            while (si < v.size() && (double)v[si] <= pts[k]) { si++; c++; }
-            out[k] = (double)c;
+        rt.materialize(x);
+        const int64_t n = rt.nodes[x].n, N = global_size(rt, n);
+        if (m > 0) {
+            FMC_CUDA(cudaMemcpyAsync(rt.d_result + 256, pts, sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, rt.stream));
+            FMC_CUDA(cudaStreamSynchronize(rt.stream));                          // pageable source
         }
-        out[m] = (double)(v.size() - si);
-        if (!v.empty()) for (int k = 0; k <= m; k++) out[k] /= (double)v.size();
+        const double* c = order_pass(rt, m + 1, [&](double* d) {
+            if (n > 0) FMC_CUDA(launch_histogram(rt.nodes[x].buf, n, rt.d_result + 256, m, d, order_grid(rt, n), rt.stream));
+        });
+        for (int k = 0; k <= m; k++) out[k] = (N > 0) ? c[k] / (double)N : c[k];  // RVF:571-600
     });
 }
 

@@ -29,6 +29,11 @@ struct ReduceParams {
 cudaError_t launch_reduce(const ReduceParams& P, int grid, cudaStream_t stream);
 int reduce_tile_elems();
 
+// order_kernel.cu — radix select / range statistics / histogram (order statistics without a sort)
+cudaError_t launch_select_hist(const float* x, long long n, uint32_t prefix, uint32_t mask, int shift, double* hist /* [256], zeroed */, int grid, cudaStream_t s);
+cudaError_t launch_range_stats(const float* x, long long n, uint32_t key_lo, uint32_t key_hi, double* out /* [5], zeroed */, int grid, cudaStream_t s);
+cudaError_t launch_histogram(const float* x, long long n, const double* pts /* device [m] */, int m, double* counts /* [m+1], zeroed */, int grid, cudaStream_t s);
+
 // regression_kernel.cu — fused normal equations: one pass over k basis vectors + y.
 constexpr int REG_MAX_K = 12;
 struct RegressionParams {

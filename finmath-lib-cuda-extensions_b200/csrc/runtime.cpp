@@ -50,8 +50,8 @@ void Runtime::init(int device_index) {
     FMC_CUDA(cudaMalloc(&d_partials, sizeof(double) * 128 * (size_t)max_grid));
     FMC_CUDA(cudaMalloc(&d_counter, sizeof(unsigned int) * 4));
     FMC_CUDA(cudaMemset(d_counter, 0, sizeof(unsigned int) * 4));
-    FMC_CUDA(cudaMalloc(&d_result, sizeof(double) * 256));
-    FMC_CUDA(cudaMallocHost(&h_result, sizeof(double) * 256));
+    FMC_CUDA(cudaMalloc(&d_result, sizeof(double) * 1024));
+    FMC_CUDA(cudaMallocHost(&h_result, sizeof(double) * 1024));
     FMC_CUDA(cudaHostAlloc(&h_ticket, sizeof(double) * 4, cudaHostAllocMapped));
     FMC_CUDA(cudaHostGetDevicePointer(&h_ticket_dev, h_ticket, 0));
     h_ticket[3] = 0.0; reduce_ticket = 0.0;

@@ -146,7 +146,8 @@ public:
     void staging_quiesce();                  // wait for those copies (before the staging buffer is reused for something else)
     double* d_partials = nullptr;       // reduction scratch
     unsigned int* d_counter = nullptr;
-    double* d_result = nullptr;         // [256] doubles
+    double* d_result = nullptr;         // [1024] doubles: [0,4) reduction, [8,40) rank gather, [64,160) regression, [200] path count,
+                                        //   [256,356) histogram points, [512,768) order-statistics scratch
     double* h_result = nullptr;         // pinned mirror
     double* h_ticket = nullptr;         // mapped pinned [4]: {count, value, M2, ticket} written by the reduction's last block
     double* h_ticket_dev = nullptr;     // device-side address of h_ticket

@@ -374,6 +374,26 @@ cudaError_t launch_regression(const RegressionParams& P, int, cudaStream_t) {
     return cudaSuccess;
 }
 int regression_max_blocks_per_sm(int) { return 1; }
+static uint32_t emu_sort_key(float f) {
+    if (f != f) return 0xffffffffu;
+    uint32_t u; std::memcpy(&u, &f, 4);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+cudaError_t launch_select_hist(const float* x, long long n, uint32_t prefix, uint32_t mask, int shift, double* hist, int, cudaStream_t) {
+    for (long long i = 0; i < n; i++) { const uint32_t k = emu_sort_key(x[i]); if (((k ^ prefix) & mask) == 0u) hist[(k >> shift) & 255u] += 1.0; }
+    return cudaSuccess;
+}
+cudaError_t launch_range_stats(const float* x, long long n, uint32_t lo, uint32_t hi, double* out, int, cudaStream_t) {
+    for (long long i = 0; i < n; i++) {
+        const uint32_t k = emu_sort_key(x[i]);
+        if (k < lo) out[0] += 1.0; else if (k == lo) out[1] += 1.0; else if (k < hi) { out[2] += 1.0; out[3] += (double)x[i]; } else if (k == hi) out[4] += 1.0;
+    }
+    return cudaSuccess;
+}
+cudaError_t launch_histogram(const float* x, long long n, const double* pts, int m, double* counts, int, cudaStream_t) {
+    for (long long i = 0; i < n; i++) { int k = 0; while (k < m && !((double)x[i] <= pts[k])) k++; counts[k] += 1.0; }
+    return cudaSuccess;
+}
 int regression_tile_elems() { return 2048; }
 cudaError_t launch_reduce(const ReduceParams& P, int, cudaStream_t) {
     double c = 0, s = 0, m2 = 0, mn = 0, mx = 0;

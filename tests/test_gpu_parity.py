@@ -211,6 +211,30 @@ def test_reductions(fc, O, data):
     assert np.allclose(X.getHistogram(pts), O.histogram(O.from_f64(x), pts), atol=0, rtol=0)
 
 
+def test_order_statistics_on_the_device(fc, O):
+    """getQuantile / getQuantileExpectation / getHistogram by radix select on the device must return exactly what
+    Arrays.sort-based RVF:472-602 returns: ties, -0.0 < +0.0, NaN last, ragged sizes, boundary quantiles."""
+    rng = np.random.default_rng(17)
+    cases = [
+        (rng.standard_normal(100_003)).astype(np.float32),
+        np.round(rng.standard_normal(50_000) * 3).astype(np.float32),                 # heavy ties
+        np.concatenate([rng.random(997).astype(np.float32), np.array([0.0, -0.0, -0.0, np.inf, -np.inf, np.nan, np.nan], dtype=np.float32)]),
+        np.array([2.5], dtype=np.float32),
+        np.full(4096, -1.25, dtype=np.float32),
+    ]
+    for x in cases:
+        rng.shuffle(x)
+        X = fc.RandomVariableCuda(0.0, x)
+        for q in (0.0, 1e-6, 0.05, 0.25, 0.5, 0.75, 0.95, 0.999, 1.0):
+            got, want = X.getQuantile(q), O.quantile(x, q)
+            assert got == want or (got != got and want != want), (x.size, q, got, want)
+        for q0, q1 in ((0.1, 0.9), (0.0, 1.0), (0.5, 0.5), (0.9, 0.1), (0.0, 0.0)):
+            got, want = X.getQuantileExpectation(q0, q1), O.quantile_expectation(x, q0, q1)
+            assert got == want or (got != got and want != want) or abs(got - want) <= 1e-12 * max(1.0, abs(want)), (x.size, q0, q1, got, want)
+        pts = np.array([-2.0, -0.5, 0.0, 0.3, 1.0, 4.0])
+        assert np.array_equal(X.getHistogram(pts), O.histogram(x, pts)), x.size
+
+
 def test_fused_chain_and_lazy_semantics(fc, O, data):
     x, y, z = data
     X, Y, Z = (fc.RandomVariableCuda(0.0, v) for v in (x, y, z))
