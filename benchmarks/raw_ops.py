@@ -130,7 +130,8 @@ def main():
             from oracle import ref_kernels
             if ref_kernels.available():
                 import ctypes
-                rk = ref_kernels.ReferenceKernels(0)
+                dv = ctypes.c_double(); capi.check(capi.load().fmc_get_option(b"device_index", ctypes.byref(dv)))
+                rk = ref_kernels.ReferenceKernels(int(dv.value))
                 L = capi.load()
 
                 def ptr(rv):

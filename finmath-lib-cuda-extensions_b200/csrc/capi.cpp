@@ -278,7 +278,7 @@ namespace {
 
 // merge (count, value, M2) triples of the ranks in rank order (deterministic)
 void merge_ranks(Runtime& rt, int mode, double part[3]) {
-    if (rt.comm_size <= 1) return;
+    if (rt.comm_size <= 1 || rt.last_reduce_global) return;      // in-kernel exchange: already the result of all ranks
     // Runtime::reduce left every rank's partial in h_result[4 * r + 0..2] (ncclAllGather behind the reduction kernel)
     const int R = rt.comm_size;
     (void)part;
@@ -378,6 +378,7 @@ static void set_option_locked(Runtime& rt, const char* key, double value) {
     else if (!std::strcmp(key, "max_sets")) rt.opt.max_sets = std::max(1, std::min((int)value, 4));
     else if (!std::strcmp(key, "grid_limit")) rt.opt.grid_limit = std::max(0, (int)value);
     else if (!std::strcmp(key, "fuse_ops")) rt.opt.fuse_ops = value != 0.0;
+    else if (!std::strcmp(key, "p2p_reduce")) rt.opt.p2p_reduce = value != 0.0;
     else if (!std::strcmp(key, "zero_copy_reduce")) rt.opt.zero_copy_reduce = value != 0.0;
     else if (!std::strcmp(key, "leaf_reduce_kernel")) rt.opt.leaf_reduce_kernel = value != 0.0;
     else if (!std::strcmp(key, "cta_warps")) rt.opt.cta_warps = (int)value == 2 ? 2 : 4;
@@ -414,6 +415,9 @@ int fmc_get_option(const char* key, double* value) {
         else if (!std::strcmp(key, "max_sets")) *value = rt.opt.max_sets;
         else if (!std::strcmp(key, "grid_limit")) *value = rt.opt.grid_limit;
         else if (!std::strcmp(key, "fuse_ops")) *value = rt.opt.fuse_ops ? 1.0 : 0.0;
+        else if (!std::strcmp(key, "p2p_reduce")) *value = rt.opt.p2p_reduce ? 1.0 : 0.0;
+        else if (!std::strcmp(key, "p2p_ready")) *value = rt.p2p_ready ? 1.0 : 0.0;
+        else if (!std::strcmp(key, "device_index")) *value = rt.device;
         else if (!std::strcmp(key, "zero_copy_reduce")) *value = rt.opt.zero_copy_reduce ? 1.0 : 0.0;
         else if (!std::strcmp(key, "leaf_reduce_kernel")) *value = rt.opt.leaf_reduce_kernel ? 1.0 : 0.0;
         else if (!std::strcmp(key, "cta_warps")) *value = rt.opt.cta_warps;

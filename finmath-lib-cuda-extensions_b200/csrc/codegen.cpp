@@ -584,7 +584,14 @@ struct Gen {
         P.counter = rt.d_counter;
         P.result = rt.d_result;
         P.host_result = nullptr; P.ticket = 0.0;
-        if (reduce_mode != RM_NONE && rt.comm_size == 1 && rt.opt.zero_copy_reduce) { P.host_result = rt.h_ticket_dev; P.ticket = (rt.reduce_ticket += 1.0); }
+        for (int r = 0; r < XMAX_RANKS; r++) P.xchg.tables[r] = nullptr;
+        P.xchg.rank = 0; P.xchg.nranks = 1;
+        if (reduce_mode != RM_NONE) {
+            rt.fill_exchange(P.xchg, &P.ticket);                                          // sharded run: ticket = the exchange's own sequence
+            if (P.xchg.nranks > 1) P.host_result = rt.h_ticket_dev;
+            else if (rt.comm_size == 1 && rt.opt.zero_copy_reduce) { P.host_result = rt.h_ticket_dev; P.ticket = (rt.reduce_ticket += 1.0); }
+        }
+        if (reduce_mode != RM_NONE) rt.last_tape_ticket = P.host_result ? P.ticket : 0.0;
         std::memcpy(P.ptrs, ptrs.data(), sizeof(float*) * ptrs.size());
         if (!prologue.empty()) std::memcpy(P.instr, prologue.data(), sizeof(TapeInstr) * prologue.size());
         P.instr[prologue.size()] = TapeInstr{ T_END, 0u };      // closes the prologue
@@ -796,19 +803,24 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
 void Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
     require_init();
     ReduceSpec spec = spec_in;
+    last_reduce_global = false;
     if (spec.weight >= 0) materialize(spec.weight);
     const bool empty = nodes[idx].n == 0;
     if (empty && comm_size == 1) { out[0] = 0.0; out[1] = NAN; out[2] = NAN; return; }
-    if (empty) FMC_CUDA(cudaMemsetAsync(d_result, 0, sizeof(double) * 4, stream));      // an empty slice still joins the exchange
-    if (empty) {
-    } else if (nodes[idx].state == NS_MAT && opt.leaf_reduce_kernel) {
-        // nothing to interpret: plain streaming reduction (reduce_kernel.cu)
+    const bool p2p = comm_size > 1 && p2p_ready;
+    double ticket = 0.0;                      // what the host spins on (0: result comes by copy + stream synchronisation)
+    if (empty || (nodes[idx].state == NS_MAT && opt.leaf_reduce_kernel)) {
+        // nothing to interpret: plain streaming reduction (reduce_kernel.cu); an empty slice of a sharded vector
+        // contributes {0, 0, 0} and still takes part in the exchange
         ReduceParams P;
         P.n = nodes[idx].n; P.mode = spec.mode; P.param = spec.param;
-        P.x = nodes[idx].buf; P.w = spec.weight >= 0 ? nodes[spec.weight].buf : nullptr;
+        P.x = empty ? nullptr : nodes[idx].buf; P.w = (!empty && spec.weight >= 0) ? nodes[spec.weight].buf : nullptr;
         P.partials = d_partials; P.counter = d_counter; P.result = d_result;
         P.host_result = nullptr; P.ticket = 0.0;
-        if (comm_size == 1 && opt.zero_copy_reduce) { P.host_result = h_ticket_dev; P.ticket = (reduce_ticket += 1.0); }
+        fill_exchange(P.xchg, &P.ticket);
+        if (P.xchg.nranks > 1) P.host_result = h_ticket_dev;
+        else if (comm_size == 1 && opt.zero_copy_reduce) { P.host_result = h_ticket_dev; P.ticket = (reduce_ticket += 1.0); }
+        ticket = P.host_result ? P.ticket : 0.0;
         const int64_t tiles = (P.n + reduce_tile_elems() - 1) / reduce_tile_elems();
         int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)sm_count * 8));
         grid = std::min(grid, max_grid);
@@ -821,28 +833,32 @@ void Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
         stats.n_kernels++; stats.n_flushes++;
     } else {
         std::vector<int32_t> t{idx};
-        run_cone(t, &spec);
+        run_cone(t, &spec);                   // the fused chain -> reduce launch sets params->ticket (Gen::launch)
+        ticket = last_tape_ticket;
     }
     const auto t_sync0 = std::chrono::steady_clock::now();
-    if (comm_size == 1 && opt.zero_copy_reduce) {
-        // the last block of the reduction wrote {count, value, M2} and then the ticket into mapped pinned memory:
-        // spin on the ticket (a host read per poll) instead of a 32-byte copy plus a stream synchronisation
+    if (ticket != 0.0) {
+        // the last block of the reduction wrote {count, value, M2} (after the in-kernel exchange: of ALL ranks) and then the
+        // ticket into mapped pinned memory: spin on the ticket instead of a 32-byte copy plus a stream synchronisation
         volatile double* h = h_ticket;
         unsigned spins = 0;
-        while (h[3] != reduce_ticket) {
+        while (h[3] != ticket) {
+            if (h[3] == -ticket) fail(FMC_ERR_COMM, "reduction exchange timed out: a peer rank did not deliver its partial");
             if ((++spins & 0x3ffu) == 0u) {
                 const cudaError_t q = cudaStreamQuery(stream);
-                if (q == cudaSuccess) { if (h[3] == reduce_ticket) break; fail(FMC_ERR_CUDA, "reduction finished without publishing its result"); }
+                if (q == cudaSuccess) { if (h[3] == ticket) break; fail(FMC_ERR_CUDA, "reduction finished without publishing its result"); }
                 if (q != cudaErrorNotReady) FMC_CUDA(q);
             }
         }
         out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
+        last_reduce_global = p2p;
         hostprof.sync += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_sync0).count();
         stats.d2h += 32;
         return;
     }
     if (comm_size > 1) {
-        // exchange step: every rank's {count, value, M2} into one table, merged on the host in rank order (capi.cpp)
+        // NCCL exchange (peer tables unavailable): every rank's {count, value, M2} into one table, merged on the host in
+        // rank order (capi.cpp)
         allgather(d_result, d_result + 8, 4);
         FMC_CUDA(cudaMemcpyAsync(h_result, d_result + 8, sizeof(double) * 4 * (size_t)comm_size, cudaMemcpyDeviceToHost, stream));
         FMC_CUDA(cudaStreamSynchronize(stream));

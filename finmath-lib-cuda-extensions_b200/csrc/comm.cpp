@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 
 #include <cstring>
+#include <vector>
 
 #include "runtime.h"
 
@@ -65,6 +66,52 @@ void comm_get_unique_id(char* id) {
     std::memcpy(id, &uid, sizeof(uid));
 }
 
+// Peer tables for the in-kernel exchange: every rank allocates XSLOTS * XMAX_RANKS * 4 doubles, the cudaIpc handles go
+// round with one ncclAllGather, every rank maps the others' tables. Falls back to the NCCL exchange if a peer cannot be mapped.
+static void setup_peer_tables(Runtime& rt) {
+    rt.p2p_ready = false;
+    if (!rt.opt.p2p_reduce || rt.comm_size > XMAX_RANKS) return;
+    const size_t bytes = sizeof(double) * XSLOTS * XMAX_RANKS * 4;
+    FMC_CUDA(cudaMalloc(&rt.xtable, bytes));
+    FMC_CUDA(cudaMemset(rt.xtable, 0, bytes));
+    cudaIpcMemHandle_t mine;
+    FMC_CUDA(cudaIpcGetMemHandle(&mine, rt.xtable));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    const int R = rt.comm_size;
+    char* d_handles = nullptr;
+    FMC_CUDA(cudaMalloc(&d_handles, 64 * (size_t)(R + 1)));
+    FMC_CUDA(cudaMemcpyAsync(d_handles + 64 * (size_t)R, &mine, 64, cudaMemcpyHostToDevice, rt.stream));
+    check(api().AllGather(d_handles + 64 * (size_t)R, d_handles, 8, ncclFloat64, (ncclComm_t)rt.nccl_comm, rt.stream), "ncclAllGather(ipc handles)");
+    std::vector<cudaIpcMemHandle_t> all((size_t)R);
+    FMC_CUDA(cudaMemcpyAsync(all.data(), d_handles, 64 * (size_t)R, cudaMemcpyDeviceToHost, rt.stream));
+    FMC_CUDA(cudaStreamSynchronize(rt.stream));
+    cudaFree(d_handles);
+    bool ok = true;
+    for (int r = 0; r < R; r++) {
+        if (r == rt.comm_rank) { rt.peer_tables[r] = rt.xtable; continue; }
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        rt.peer_tables[r] = (double*)p;
+    }
+    // everybody must agree: one rank that cannot map a peer sends all of them to the NCCL path
+    double flag = ok ? 0.0 : 1.0;
+    FMC_CUDA(cudaMemcpyAsync(rt.d_result + 200, &flag, sizeof(double), cudaMemcpyHostToDevice, rt.stream));
+    rt.allreduce_sum(rt.d_result + 200, 1);
+    FMC_CUDA(cudaMemcpyAsync(&flag, rt.d_result + 200, sizeof(double), cudaMemcpyDeviceToHost, rt.stream));
+    FMC_CUDA(cudaStreamSynchronize(rt.stream));
+    rt.p2p_ready = (flag == 0.0);
+    rt.xticket = 0.0;
+}
+
+static void release_peer_tables(Runtime& rt) {
+    for (int r = 0; r < XMAX_RANKS; r++) {
+        if (rt.peer_tables[r] && rt.peer_tables[r] != rt.xtable) cudaIpcCloseMemHandle(rt.peer_tables[r]);
+        rt.peer_tables[r] = nullptr;
+    }
+    if (rt.xtable) { cudaFree(rt.xtable); rt.xtable = nullptr; }
+    rt.p2p_ready = false;
+}
+
 void comm_init(Runtime& rt, int rank, int nranks, const char* id) {
     if (nranks < 1 || rank < 0 || rank >= nranks) fail(FMC_ERR_INVALID, "bad rank %d / %d", rank, nranks);
     comm_destroy(rt);
@@ -74,15 +121,27 @@ void comm_init(Runtime& rt, int rank, int nranks, const char* id) {
     ncclComm_t c = nullptr;
     check(api().CommInitRank(&c, nranks, uid, rank), "ncclCommInitRank");
     rt.nccl_comm = c; rt.comm_rank = rank; rt.comm_size = nranks;
+    setup_peer_tables(rt);
 }
 
 void comm_destroy(Runtime& rt) {
     if (rt.nccl_comm) {
         if (rt.stream) cudaStreamSynchronize(rt.stream);
+        release_peer_tables(rt);
         api().CommDestroy((ncclComm_t)rt.nccl_comm);
         rt.nccl_comm = nullptr;
     }
     rt.comm_rank = 0; rt.comm_size = 1;
+}
+
+void Runtime::fill_exchange(Exchange& x, double* ticket) {
+    for (int r = 0; r < XMAX_RANKS; r++) x.tables[r] = nullptr;
+    x.rank = 0; x.nranks = 1;
+    if (comm_size > 1 && p2p_ready) {
+        for (int r = 0; r < comm_size; r++) x.tables[r] = peer_tables[r];
+        x.rank = comm_rank; x.nranks = comm_size;
+        *ticket = (xticket += 1.0);
+    }
 }
 
 void Runtime::allreduce_sum(double* dev, int count) {

@@ -25,6 +25,7 @@ struct ReduceParams {
     double* result;           // {count, value, M2}
     double* host_result;      // mapped pinned mirror (+ ticket in [3]) or nullptr
     double ticket;
+    Exchange xchg;            // peer tables of a path-sharded run (reduce_common.cuh)
 };
 cudaError_t launch_reduce(const ReduceParams& P, int grid, cudaStream_t stream);
 int reduce_tile_elems();

@@ -14,6 +14,7 @@
 
 #include "kernels.h"
 #include "tape_isa.h"
+#include "reduce_common.cuh"
 
 namespace fmc {
 
@@ -23,46 +24,9 @@ constexpr int RT = 256;            // threads per block
 constexpr int RU = 4;              // float4 loads per thread per iteration
 constexpr int RTILE = RT * RU * 4; // elements per block iteration
 
-struct Part { double c, v, m; };
-
-__device__ __forceinline__ double jmin(double a, double b) {
-    if (a != a) return a;
-    if (b != b) return b;
-    if (a == 0.0 && b == 0.0) return (signbit(a) || signbit(b)) ? -0.0 : 0.0;
-    return a < b ? a : b;
-}
-__device__ __forceinline__ double jmax(double a, double b) {
-    if (a != a) return a;
-    if (b != b) return b;
-    if (a == 0.0 && b == 0.0) return (signbit(a) && signbit(b)) ? -0.0 : 0.0;
-    return a > b ? a : b;
-}
 __device__ __forceinline__ float jminf(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ float jmaxf(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 
-__device__ __forceinline__ Part merge(int mode, Part a, Part b) {
-    if (b.c == 0.0) return a;
-    if (a.c == 0.0) return b;
-    Part r;
-    r.c = a.c + b.c;
-    r.m = 0.0;
-    if (mode == RM_MOMENTS) {          // Chan et al. pairwise update
-        const double delta = b.v - a.v;
-        const double w = b.c / r.c;
-        r.v = a.v + delta * w;
-        r.m = a.m + b.m + delta * delta * a.c * w;
-    } else if (mode == RM_MIN) r.v = jmin(a.v, b.v);
-    else if (mode == RM_MAX) r.v = jmax(a.v, b.v);
-    else r.v = a.v + b.v;
-    return r;
-}
-__device__ __forceinline__ Part shfl_down(Part p, int d) {
-    Part r;
-    r.c = __shfl_down_sync(0xffffffffu, p.c, d);
-    r.v = __shfl_down_sync(0xffffffffu, p.v, d);
-    r.m = __shfl_down_sync(0xffffffffu, p.m, d);
-    return r;
-}
 __device__ Part block_reduce(int mode, Part p, Part* smem) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) p = merge(mode, p, shfl_down(p, d));
@@ -162,14 +126,8 @@ reduce_kernel(const __grid_constant__ ReduceParams P)
     }
     q = block_reduce(MM, q, red_smem);
     if (tid == 0) {
-        P.result[0] = q.c; P.result[1] = q.v; P.result[2] = q.m;
         *P.counter = 0u;
-        if (P.host_result) {
-            volatile double* h = P.host_result;
-            h[0] = q.c; h[1] = q.v; h[2] = q.m;
-            __threadfence_system();
-            h[3] = P.ticket;
-        }
+        finish_reduction(MM, q, P.xchg, P.ticket, P.result, P.host_result);
     }
 }
 

@@ -101,6 +101,7 @@ struct Options {
     int max_sets = 1;               // slot sets per warp (cross-chunk prefetch depth), upper bound; measured: >1 costs occupancy and does not pay
     bool zero_copy_reduce = true;   // reductions publish their result through mapped pinned memory (single-rank runs)
     bool leaf_reduce_kernel = true; // reductions of a materialised vector use the streaming kernel, not the interpreter
+    bool p2p_reduce = true;         // sharded runs: exchange reduction partials inside the kernel over NVLink peer memory (else NCCL)
     int cta_warps = 4;              // warps per interpreter CTA (2 or 4)
     bool fuse_ops = true;           // peephole fusion of the abstract code (MULADD_II, ACCUM_S, ADDPROD)
     int grid_limit = 0;             // > 0: cap the interpreter grid (tests: many chunks per warp at small sizes)
@@ -152,6 +153,7 @@ public:
     double* h_ticket = nullptr;         // mapped pinned [4]: {count, value, M2, ticket} written by the reduction's last block
     double* h_ticket_dev = nullptr;     // device-side address of h_ticket
     double reduce_ticket = 0.0;
+    double last_tape_ticket = 0.0;      // ticket of the last fused chain -> reduce launch (0: none published)
     int max_grid = 0;
 
     // graph
@@ -203,6 +205,13 @@ public:
     // comm (NCCL, loaded with dlopen; see comm.cpp)
     int comm_rank = 0, comm_size = 1;
     void* nccl_comm = nullptr;
+    // peer-memory exchange of reduction partials (reduce_common.cuh): own table + the peers' tables mapped through cudaIpc
+    double* xtable = nullptr;
+    double* peer_tables[XMAX_RANKS] = {nullptr};
+    bool p2p_ready = false;
+    double xticket = 0.0;                                 // same sequence on every rank: reset by comm_init
+    bool last_reduce_global = false;                      // the last reduce() already returned the merged result of all ranks
+    void fill_exchange(Exchange& x, double* ticket);      // parameters of the next reduction kernel
     void allreduce_sum(double* dev, int count);           // in place on the compute stream
     void allgather(const double* dev_send, double* dev_recv, int count_per_rank);
     void allreduce_minmax(double* dev, int count, bool is_max);

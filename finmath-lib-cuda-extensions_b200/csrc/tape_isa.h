@@ -83,6 +83,12 @@ enum ReduceMode : int {
     RM_WSQ = 6        // sum(((double)acc - param)^2 * (double)b)
 };
 
+// exchange step of a reduction over a path-sharded vector (reduce_common.cuh): tables[r] = rank r's exchange table as mapped
+// in this process (cudaIpc), slot [ticket % XSLOTS][rank] = {count, value, M2, ticket}
+constexpr int XMAX_RANKS = 8;
+constexpr int XSLOTS = 64;
+struct Exchange { double* tables[XMAX_RANKS]; int rank, nranks; };   // nranks <= 1: no exchange
+
 struct TapeInstr { uint32_t x, y; };
 
 inline TapeInstr enc_imm(uint32_t op, uint32_t slot, float imm) {
@@ -107,6 +113,7 @@ struct TapeParams {
     double* result;           // [4]
     double* host_result;      // [4] the same result through mapped pinned host memory ([3] = ticket), or nullptr
     double ticket;            // written to host_result[3] last: the host spins on it instead of a copy + stream sync
+    Exchange xchg;            // peer tables of a path-sharded run (reduce_common.cuh)
     float* ptrs[TAPE_MAX_PTRS];
     TapeInstr instr[TAPE_MAX_INSTR + 3];   // + closing T_END + two padding words (the interpreter prefetches two ahead)
 };

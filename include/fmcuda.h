@@ -127,7 +127,9 @@ int fmc_sync(void);                     /* flush + wait for the device (cuCtxSyn
  *          "fuse" (1 default; 0 = execute every op as its own kernel, the reference's execution model),
  *          "profile" (0 default; see fmc_profile_read);
  *          interpreter scheduling knobs (tuning / tests; defaults in csrc/runtime.h): "ring_max", "ring_min", "target_ctas",
- *          "horizon", "pipeline", "max_sets", "grid_limit", "fuse_ops", "cta_warps", "zero_copy_reduce", "leaf_reduce_kernel";
+ *          "horizon", "pipeline", "max_sets", "grid_limit", "fuse_ops", "cta_warps", "zero_copy_reduce", "leaf_reduce_kernel",
+ *          "p2p_reduce" (1 default: sharded runs exchange reduction partials inside the kernel over NVLink peer memory; 0: NCCL);
+ *          read-only: "p2p_ready", "device_index";
  *          read-only host-side timers in microseconds since fmc_reset_stats: "host_us_codegen", "host_us_launch", "host_us_sync".
  *          The environment variable FMC_OPTIONS="key=value,..." is applied once at fmc_init. */
 int fmc_set_option(const char* key, double value);

@@ -19,7 +19,9 @@ def ref(fc):
     from oracle import ref_kernels
     if not ref_kernels.available():
         pytest.skip("oracle/_ref cubin or cuda-python not available")
-    return ref_kernels.ReferenceKernels(0)
+    dev = ctypes.c_double()
+    fc._capi.check(fc._capi.load().fmc_get_option(b"device_index", ctypes.byref(dev)))     # the runtime's device (-1 = last by default)
+    return ref_kernels.ReferenceKernels(int(dev.value))
 
 
 def dev_ptr(fc, rv) -> int:
