@@ -255,7 +255,11 @@ public:
 private:
     HostWorkers() {
         unsigned hc = std::thread::hardware_concurrency();
-        int want = (int)std::min<unsigned>(hc ? std::max(hc / 2, 1u) : 4u, 8u) - 1;   // measured on the 16-vCPU B200 box: 8 beats 16+;   // FMC_HOST_THREADS overrides
+        // measured on the 16-vCPU single-B200 box: 8 threads beat 16+ (the loop is bound by host memory bandwidth);
+        // one process per GPU shares the host: divide by the number of local ranks (torchrun's LOCAL_WORLD_SIZE)
+        unsigned local_ranks = 1;
+        if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) local_ranks = (unsigned)std::max(1, std::atoi(e));
+        int want = (int)std::min<unsigned>(std::max<unsigned>((hc ? hc : 8u) / (2u * local_ranks), 2u), 8u) - 1;   // FMC_HOST_THREADS overrides
         if (const char* e = std::getenv("FMC_HOST_THREADS")) want = std::max(0, std::atoi(e) - 1);
         for (int i = 0; i < want; i++) threads_.emplace_back([this] { loop(); });
         for (auto& t : threads_) t.detach();
