@@ -59,30 +59,42 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Started BEFORE the warm-up (nvidia-smi needs a few hundred ms to come up); begin()/end() bracket the timed region."""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def begin(self): self.t0 = time.perf_counter()
+    def end(self): self.t1 = time.perf_counter()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)                      # let the sample that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        inside = [ln for (t, ln) in self.lines if self.t0 is not None and self.t0 <= t <= self.t1 + 0.06]
+        note = None
+        if not inside and self.lines:         # region shorter than the sampling interval: the samples closest to it
+            mid = 0.5 * ((self.t0 or 0.0) + (self.t1 or 0.0))
+            inside = [ln for (_, ln) in sorted(self.lines, key=lambda tl: abs(tl[0] - mid))[:2]]
+            note = "timed region shorter than the 50 ms sampling interval: nearest samples"
         sm, smax, reasons = [], None, set()
-        for ln in self.lines:
+        for ln in inside:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 9:
                 continue
@@ -93,7 +105,10 @@ class ClockSampler:
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def run_reference(args) -> None:
@@ -182,14 +197,15 @@ def run_ours(args) -> None:
 
     # ---- device-resident arm ----
     values = None
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         values = model.step()
     capi.check(capi.load().fmc_reset_stats())
     capi.set_option("profile", 1)
     capi.profile_read()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.begin()
     capi.timer_start()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -197,6 +213,7 @@ def run_ours(args) -> None:
     dev_ms = capi.timer_stop()
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
+    sampler.end()
     clocks = sampler.stop()
     touched = ctypes.c_double()
     capi.check(capi.load().fmc_get_option(b"profile_touched_bytes", ctypes.byref(touched)))
@@ -285,7 +302,7 @@ def run_ours(args) -> None:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--paths", type=int, default=1 << 20, help="paths per GPU (north-star: 1M-path runs)")
