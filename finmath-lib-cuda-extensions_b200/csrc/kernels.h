@@ -9,7 +9,8 @@ namespace fmc {
 
 // tape_kernel.cu
 cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t stream);   // n_warps per CTA: 2 or 4
-cudaError_t tape_kernel_setup(size_t* max_smem_per_cta);   // opts the kernel in to the device's full shared memory
+cudaError_t tape_kernel_setup(size_t* max_smem_per_cta);   // opts the kernels in to the device's full shared memory, allocates the tape ring
+void tape_kernel_teardown();
 size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots, int n_sets, int n_warps);   // dynamic shared memory of one CTA
 int tape_max_blocks_per_sm(size_t smem_bytes, int reduce_mode, int n_warps);
 

@@ -97,9 +97,10 @@ inline TapeInstr enc_imm(uint32_t op, uint32_t slot, float imm) {
 }
 inline TapeInstr enc_idx(uint32_t op, uint32_t slot, uint32_t idx) { return TapeInstr{ op | (slot << TAPE_SLOT_SHIFT), idx }; }
 
-struct TapeParams {
+// Everything a launch needs except the two tables.
+struct TapeHeader {
     long long n;              // elements per vector
-    int n_instr;              // instructions including the final T_END (one more padding word follows)
+    int n_instr;              // instructions including the final T_END (two more padding words follow)
     int n_prologue;           // leading T_LOADs, closed by a T_END: run once per slot set before the warp's first chunks;
                               // the body starts at instr[n_prologue + 1]
     int n_sets;               // slot sets per warp (cross-chunk prefetch depth), see tape_kernel.cu
@@ -114,8 +115,21 @@ struct TapeParams {
     double* host_result;      // [4] the same result through mapped pinned host memory ([3] = ticket), or nullptr
     double ticket;            // written to host_result[3] last: the host spins on it instead of a copy + stream sync
     Exchange xchg;            // peer tables of a path-sharded run (reduce_common.cuh)
+};
+
+// Host-side description of one launch (code generator -> launch_tape).
+struct TapeParams : TapeHeader {
     float* ptrs[TAPE_MAX_PTRS];
     TapeInstr instr[TAPE_MAX_INSTR + 3];   // + closing T_END + two padding words (the interpreter prefetches two ahead)
 };
+
+// Kernel arguments. Kernel parameters beyond 4 KB cost ~10 us per launch on the device and ~2 us on the host (measured:
+// a trivial fused reduction took 32 us with the 20 KB TapeParams by value, 22 us below 4 KB), so a tape that fits travels
+// inline in a 4 KB argument block and a longer one through a ring of device buffers filled by cudaMemcpyAsync.
+constexpr int TAPE_INLINE_PTRS = 64;
+constexpr int TAPE_INLINE_INSTR = 428;     // words including the closing T_END and the two padding words
+struct TapeArgsInline { TapeHeader h; float* ptrs[TAPE_INLINE_PTRS]; TapeInstr instr[TAPE_INLINE_INSTR]; };
+struct TapeArgsDev { TapeHeader h; float* const* ptrs; const TapeInstr* instr; };
+static_assert(sizeof(TapeArgsInline) <= 4096, "the inline argument block must stay within the 4 KB fast path");
 
 }  // namespace fmc

@@ -349,6 +349,7 @@ cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t
         return cudaErrorLaunchFailure;
     }
 }
+void tape_kernel_teardown() {}
 cudaError_t tape_kernel_setup(size_t* m) { if (m) *m = 232448 - 1024; return cudaSuccess; }
 size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots, int n_sets, int n_warps) {
     size_t s = (size_t)n_warps * (size_t)n_sets * TAPE_MAX_RING * 8;
