@@ -182,6 +182,10 @@ def run_ours(args) -> None:
     p0, p1 = rank * paths_per_gpu, (rank + 1) * paths_per_gpu
     lib = DriverLib()
     model = lib.lmm(total_paths, N_PERIODS, DELTA, 1, SEED, 0, (p0, p1))
+    if args.valuation_threads != 1:
+        if world > 1:
+            raise SystemExit("--valuation-threads > 1 is a single-rank option: sharded ranks must issue their reductions in one order")
+        model.set_valuation_threads(args.valuation_threads)
 
     def barrier():
         if dist is not None:
@@ -283,7 +287,7 @@ def run_ours(args) -> None:
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "LIBORMarketModelCalibrationATMTest inner loop: LMM Euler simulation 80x80, 1 factor + 144 ATM swaptions",
                    "paths_per_gpu": paths_per_gpu, "paths_total": total_paths, "time_steps": N_PERIODS, "seed": SEED,
-                   "parallelism": f"path-sharded x{world}", "l2": "inputs larger than L2 (simulation state >> 126 MB)",
+                   "parallelism": f"path-sharded x{world}", "valuation_threads": args.valuation_threads, "l2": "inputs larger than L2 (simulation state >> 126 MB)",
                    "forward_curve": "synthetic", "wall_ms_per_step": wall_ms / args.steps},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": st2["h2d_bytes"] // args.steps,
                 "d2h_bytes_per_step": st2["d2h_bytes"] // args.steps, "host_input_bytes": host_bytes},
@@ -309,6 +313,8 @@ def main():
     ap.add_argument("--cpu-sample-paths", type=int, default=131072)
     ap.add_argument("--ref-paths-per-thread", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--valuation-threads", type=int, default=1,
+                    help="host threads valuing the calibration products (the reference test uses 1, LIBORMarketModelCalibrationATMTest.java:319)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

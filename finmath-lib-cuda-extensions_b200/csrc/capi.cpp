@@ -15,8 +15,17 @@ namespace {
 template <typename F>
 int guarded(F&& f) {
     Runtime& rt = Runtime::get();
-    std::lock_guard<std::mutex> lock(rt.mu);
+    RuntimeLock lock(rt.mu);
+    struct Held {                                    // lets Runtime::reduce drop the lock while it waits for its result
+        Runtime& rt;
+        Held(Runtime& r, RuntimeLock* l) : rt(r) { rt.held = l; }
+        ~Held() { rt.held = nullptr; }
+    } held(rt, &lock);
     try {
+        // any thread may call: CUDA's current device is per thread, the runtime's device is not necessarily device 0
+        static thread_local int bound_device = -1;
+        if (rt.initialized && bound_device != rt.device) { FMC_CUDA(cudaSetDevice(rt.device)); bound_device = rt.device; }
+        if (!rt.initialized) bound_device = -1;
         f(rt);
         return FMC_OK;
     } catch (const Fail& e) {
@@ -277,8 +286,8 @@ int fmc_op_choose(fmc_vec trigger, fmc_vec if_nonneg, double s_nonneg, fmc_vec i
 namespace {
 
 // merge (count, value, M2) triples of the ranks in rank order (deterministic)
-void merge_ranks(Runtime& rt, int mode, double part[3]) {
-    if (rt.comm_size <= 1 || rt.last_reduce_global) return;      // in-kernel exchange: already the result of all ranks
+void merge_ranks(Runtime& rt, int mode, double part[3], bool already_global) {
+    if (rt.comm_size <= 1 || already_global) return;             // in-kernel exchange: already the result of all ranks
     // Runtime::reduce left every rank's partial in h_result[4 * r + 0..2] (ncclAllGather behind the reduction kernel)
     const int R = rt.comm_size;
     (void)part;
@@ -314,18 +323,19 @@ int fmc_reduce(int kind, fmc_vec a, fmc_vec weights, double* out) {
         }
         ReduceSpec spec;
         double p[3];
+        auto run = [&](const ReduceSpec& sp, int merge_mode) { const bool global = rt.reduce(x, sp, p); merge_ranks(rt, merge_mode, p, global); };
         switch (kind) {
         case FMC_RED_SUM:
         case FMC_RED_AVERAGE:
             spec.mode = RM_SUM;
-            rt.reduce(x, spec, p); merge_ranks(rt, RM_SUM, p);
+            run(spec, RM_SUM);
             if (kind == FMC_RED_SUM) *out = (p[0] == 0.0) ? 0.0 : p[1];
             else *out = (p[0] == 0.0) ? NAN : p[1] / p[0];                       // RVF:318-320, 333
             break;
         case FMC_RED_VARIANCE:
         case FMC_RED_SAMPLE_VARIANCE:
             spec.mode = RM_MOMENTS;
-            rt.reduce(x, spec, p); merge_ranks(rt, RM_MOMENTS, p);
+            run(spec, RM_MOMENTS);
             if (p[0] == 0.0) *out = NAN;                                         // RVF:364-366
             else if (p[0] == 1.0) *out = 0.0;                                    // RVF:361-363
             else {
@@ -336,23 +346,23 @@ int fmc_reduce(int kind, fmc_vec a, fmc_vec weights, double* out) {
         case FMC_RED_MIN:
         case FMC_RED_MAX:
             spec.mode = (kind == FMC_RED_MIN) ? RM_MIN : RM_MAX;
-            rt.reduce(x, spec, p); merge_ranks(rt, spec.mode, p);
+            run(spec, spec.mode);
             if (p[0] == 0.0) *out = (kind == FMC_RED_MIN) ? 1.7976931348623157e308 : -1.7976931348623157e308;  // RVF:288, 303
             else *out = p[1];
             break;
         case FMC_RED_AVERAGE_W:
             spec.mode = RM_DOT; spec.weight = w;
-            rt.reduce(x, spec, p); merge_ranks(rt, RM_SUM, p);
+            run(spec, RM_SUM);
             *out = (p[0] == 0.0) ? NAN : p[1] / p[0];                            // RVF:356
             break;
         case FMC_RED_VARIANCE_W: {
             rt.materialize(x);                                                   // two passes over x: keep it
             spec.mode = RM_DOT; spec.weight = w;
-            rt.reduce(x, spec, p); merge_ranks(rt, RM_SUM, p);
+            run(spec, RM_SUM);
             if (p[0] == 0.0) { *out = NAN; break; }
             const double avg = p[1] / p[0];                                      // RVF:393
             ReduceSpec s2; s2.mode = RM_WSQ; s2.weight = w; s2.param = avg;
-            rt.reduce(x, s2, p); merge_ranks(rt, RM_SUM, p);
+            run(s2, RM_SUM);
             *out = p[1];                                                         // RVF:406 (not divided by n)
             break;
         }

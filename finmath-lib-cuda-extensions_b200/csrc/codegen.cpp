@@ -588,8 +588,9 @@ struct Gen {
         P.xchg.rank = 0; P.xchg.nranks = 1;
         if (reduce_mode != RM_NONE) {
             rt.fill_exchange(P.xchg, &P.ticket);                                          // sharded run: ticket = the exchange's own sequence
-            if (P.xchg.nranks > 1) P.host_result = rt.h_ticket_dev;
-            else if (rt.comm_size == 1 && rt.opt.zero_copy_reduce) { P.host_result = rt.h_ticket_dev; P.ticket = (rt.reduce_ticket += 1.0); }
+            double* slot = rt.reduce_slot >= 0 ? rt.h_ticket_dev + 4 * rt.reduce_slot : nullptr;
+            if (P.xchg.nranks > 1) P.host_result = slot;
+            else if (rt.comm_size == 1 && rt.opt.zero_copy_reduce && slot) { P.ticket = (rt.reduce_ticket += 1.0); P.host_result = slot; }
         }
         if (reduce_mode != RM_NONE) rt.last_tape_ticket = P.host_result ? P.ticket : 0.0;
         std::memcpy(P.ptrs, ptrs.data(), sizeof(float*) * ptrs.size());
@@ -800,14 +801,22 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
     }
 }
 
-void Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
+bool Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
     require_init();
     ReduceSpec spec = spec_in;
-    last_reduce_global = false;
     if (spec.weight >= 0) materialize(spec.weight);
     const bool empty = nodes[idx].n == 0;
-    if (empty && comm_size == 1) { out[0] = 0.0; out[1] = NAN; out[2] = NAN; return; }
+    if (empty && comm_size == 1) { out[0] = 0.0; out[1] = NAN; out[2] = NAN; return false; }
     const bool p2p = comm_size > 1 && p2p_ready;
+    // the result slot of this reduction (released when the result has been read, also on the error paths)
+    struct Slot {
+        Runtime& rt; int s = -1;
+        explicit Slot(Runtime& r) : rt(r) {
+            if (~rt.ticket_slots_busy) { s = __builtin_ctzll(~rt.ticket_slots_busy); rt.ticket_slots_busy |= 1ull << s; }
+            rt.reduce_slot = s;
+        }
+        ~Slot() { if (s >= 0) rt.ticket_slots_busy &= ~(1ull << s); }
+    } slot(*this);
     double ticket = 0.0;                      // what the host spins on (0: result comes by copy + stream synchronisation)
     if (empty || (nodes[idx].state == NS_MAT && opt.leaf_reduce_kernel)) {
         // nothing to interpret: plain streaming reduction (reduce_kernel.cu); an empty slice of a sharded vector
@@ -818,8 +827,9 @@ void Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
         P.partials = d_partials; P.counter = d_counter; P.result = d_result;
         P.host_result = nullptr; P.ticket = 0.0;
         fill_exchange(P.xchg, &P.ticket);
-        if (P.xchg.nranks > 1) P.host_result = h_ticket_dev;
-        else if (comm_size == 1 && opt.zero_copy_reduce) { P.host_result = h_ticket_dev; P.ticket = (reduce_ticket += 1.0); }
+        double* slot = reduce_slot >= 0 ? h_ticket_dev + 4 * reduce_slot : nullptr;
+        if (P.xchg.nranks > 1) P.host_result = slot;
+        else if (comm_size == 1 && opt.zero_copy_reduce && slot) { P.ticket = (reduce_ticket += 1.0); P.host_result = slot; }
         ticket = P.host_result ? P.ticket : 0.0;
         const int64_t tiles = (P.n + reduce_tile_elems() - 1) / reduce_tile_elems();
         int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)sm_count * 8));
@@ -840,21 +850,36 @@ void Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
     if (ticket != 0.0) {
         // the last block of the reduction wrote {count, value, M2} (after the in-kernel exchange: of ALL ranks) and then the
         // ticket into mapped pinned memory: spin on the ticket instead of a 32-byte copy plus a stream synchronisation
-        volatile double* h = h_ticket;
+        // Single-rank runs wait WITHOUT the runtime lock: other host threads keep recording and launching meanwhile (their
+        // reductions use other ticket slots), the way the reference's valuation threads share one device. Sharded runs keep
+        // the lock: every rank must issue its reductions in the same order.
+        volatile double* h = h_ticket + 4 * slot.s;
+        RuntimeLock* mine = (comm_size == 1) ? held : nullptr;
+        cudaStream_t s = stream;
+        if (mine) { held = nullptr; mine->unlock(); }
         unsigned spins = 0;
+        auto t_query = t_sync0;
+        const char* err = nullptr; int err_code = 0; cudaError_t cuda_err = cudaSuccess;
         while (h[3] != ticket) {
-            if (h[3] == -ticket) fail(FMC_ERR_COMM, "reduction exchange timed out: a peer rank did not deliver its partial");
+            if (h[3] == -ticket) { err = "reduction exchange timed out: a peer rank did not deliver its partial"; err_code = FMC_ERR_COMM; break; }
             if ((++spins & 0x3ffu) == 0u) {
-                const cudaError_t q = cudaStreamQuery(stream);
-                if (q == cudaSuccess) { if (h[3] == ticket) break; fail(FMC_ERR_CUDA, "reduction finished without publishing its result"); }
-                if (q != cudaErrorNotReady) FMC_CUDA(q);
+                // liveness check, at most every 200 us: the driver call contends with the threads that are launching
+                const auto now = std::chrono::steady_clock::now();
+                if (now - t_query < std::chrono::microseconds(200)) continue;
+                t_query = now;
+                const cudaError_t q = cudaStreamQuery(s);
+                if (q == cudaSuccess) { if (h[3] == ticket) break; err = "reduction finished without publishing its result"; err_code = FMC_ERR_CUDA; break; }
+                if (q != cudaErrorNotReady) { cuda_err = q; break; }
             }
         }
-        out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
-        last_reduce_global = p2p;
+        const double r0 = h[0], r1 = h[1], r2 = h[2];
+        if (mine) { mine->lock(); held = mine; }
+        if (err) fail(err_code, "%s", err);
+        FMC_CUDA(cuda_err);
+        out[0] = r0; out[1] = r1; out[2] = r2;
         hostprof.sync += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_sync0).count();
         stats.d2h += 32;
-        return;
+        return p2p;
     }
     if (comm_size > 1) {
         // NCCL exchange (peer tables unavailable): every rank's {count, value, M2} into one table, merged on the host in
@@ -865,13 +890,14 @@ void Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
         hostprof.sync += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_sync0).count();
         stats.d2h += 32 * (uint64_t)comm_size;
         out[0] = h_result[4 * comm_rank]; out[1] = h_result[4 * comm_rank + 1]; out[2] = h_result[4 * comm_rank + 2];
-        return;
+        return false;
     }
     FMC_CUDA(cudaMemcpyAsync(h_result, d_result, sizeof(double) * 4, cudaMemcpyDeviceToHost, stream));
     FMC_CUDA(cudaStreamSynchronize(stream));
     hostprof.sync += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_sync0).count();
     stats.d2h += 32;
     out[0] = h_result[0]; out[1] = h_result[1]; out[2] = h_result[2];
+    return false;
 }
 
 }  // namespace fmc

@@ -52,9 +52,10 @@ void Runtime::init(int device_index) {
     FMC_CUDA(cudaMemset(d_counter, 0, sizeof(unsigned int) * 4));
     FMC_CUDA(cudaMalloc(&d_result, sizeof(double) * 1024));
     FMC_CUDA(cudaMallocHost(&h_result, sizeof(double) * 1024));
-    FMC_CUDA(cudaHostAlloc(&h_ticket, sizeof(double) * 4, cudaHostAllocMapped));
+    FMC_CUDA(cudaHostAlloc(&h_ticket, sizeof(double) * 4 * TICKET_SLOTS, cudaHostAllocMapped));
     FMC_CUDA(cudaHostGetDevicePointer(&h_ticket_dev, h_ticket, 0));
-    h_ticket[3] = 0.0; reduce_ticket = 0.0;
+    for (int i = 0; i < 4 * TICKET_SLOTS; i++) h_ticket[i] = 0.0;
+    reduce_ticket = 0.0; ticket_slots_busy = 0; reduce_slot = -1;
     nodes.reserve(1 << 16);
     initialized = true;
 }

@@ -5,8 +5,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -123,10 +125,29 @@ struct ReduceSpec {
     int32_t weight = -1;         // node index of the weight vector (RM_DOT / RM_WSQ)
 };
 
+// The runtime lock. Critical sections are ~100 ns (one recorded op), so waiters spin: test-and-test-and-set (a waiter only
+// reads the flag until it sees it free, so the holder's unlock does not fight for the cache line), yielding the core when the
+// holder is in a long operation (an upload, a Brownian generation).
+class RuntimeMutex {
+    std::atomic<int> state_{0};
+public:
+    bool try_lock() { return state_.load(std::memory_order_relaxed) == 0 && state_.exchange(1, std::memory_order_acquire) == 0; }
+    void lock() {
+        for (unsigned n = 0; !try_lock(); ) {
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+            if (++n > (1u << 14)) { std::this_thread::yield(); n = 1u << 13; }
+        }
+    }
+    void unlock() { state_.store(0, std::memory_order_release); }
+};
+using RuntimeLock = std::unique_lock<RuntimeMutex>;
+
 class Runtime {
 public:
     static Runtime& get();
-    std::mutex mu;
+    RuntimeMutex mu;
 
     // lifecycle
     bool initialized = false;
@@ -150,9 +171,16 @@ public:
     double* d_result = nullptr;         // [1024] doubles: [0,4) reduction, [8,40) rank gather, [64,160) regression, [200] path count,
                                         //   [256,356) histogram points, [512,768) order-statistics scratch
     double* h_result = nullptr;         // pinned mirror
-    double* h_ticket = nullptr;         // mapped pinned [4]: {count, value, M2, ticket} written by the reduction's last block
+    // mapped pinned [TICKET_SLOTS][4]: {count, value, M2, ticket} written by the reduction's last block. Every reduction in
+    // flight owns one slot, so several host threads can each wait for their own result (the runtime lock is released while
+    // waiting, see Runtime::reduce); with no slot free the reduction falls back to a copy + stream synchronisation.
+    static constexpr int TICKET_SLOTS = 64;
+    double* h_ticket = nullptr;
     double* h_ticket_dev = nullptr;     // device-side address of h_ticket
+    uint64_t ticket_slots_busy = 0;     // bit s: slot s belongs to a waiting reduction
+    int reduce_slot = -1;               // slot of the reduction being launched (-1: none)
     double reduce_ticket = 0.0;
+    RuntimeLock* held = nullptr;   // the C-ABI call's lock on `mu` (capi.cpp: guarded)
     double last_tape_ticket = 0.0;      // ticket of the last fused chain -> reduce launch (0: none published)
     int max_grid = 0;
 
@@ -193,7 +221,8 @@ public:
     void run_cone(const std::vector<int32_t>& targets, const ReduceSpec* red);   // core scheduler
     // {count, value, M2} of the LOCAL slice; with several ranks the partials of ALL ranks are left in h_result[4 * r + 0..2]
     // (one ncclAllGather behind the reduction kernel, one copy, one synchronisation)
-    void reduce(int32_t idx, const ReduceSpec& spec, double out[3]);
+    // returns true when `out` already is the merged result of all ranks (in-kernel exchange)
+    bool reduce(int32_t idx, const ReduceSpec& spec, double out[3]);
     void auto_flush();
 
     // host copies
@@ -210,7 +239,6 @@ public:
     double* peer_tables[XMAX_RANKS] = {nullptr};
     bool p2p_ready = false;
     double xticket = 0.0;                                 // same sequence on every rank: reset by comm_init
-    bool last_reduce_global = false;                      // the last reduce() already returned the merged result of all ranks
     void fill_exchange(Exchange& x, double* ticket);      // parameters of the next reduction kernel
     void allreduce_sum(double* dev, int count);           // in place on the compute stream
     void allgather(const double* dev_send, double* dev_recv, int count_per_rank);

@@ -9,6 +9,9 @@
 #include <cmath>
 #include <functional>
 #include <map>
+#include <mutex>
+#include <thread>
+#include <exception>
 #include <memory>
 #include <vector>
 
@@ -130,7 +133,9 @@ public:
     RV getLIBOR(int timeIndex, int liborIndex) const { return process_[(size_t)timeIndex][(size_t)liborIndex]; }
 
     // LIBORMarketModelFromCovarianceModel.getNumeraire, SPOT measure: N(T_k) = N(T_{k-1}).accrue(L_{k-1}(T_{k-1}), delta)
+    // (cached per model like the library's ConcurrentHashMap of numeraires: valuation threads share it)
     RV getNumeraire(int liborIndex) {
+        std::lock_guard<std::recursive_mutex> lock(numeraire_mu_);
         auto it = numeraire_.find(liborIndex);
         if (it != numeraire_.end()) return it->second;
         RV n;
@@ -180,6 +185,7 @@ private:
     TimeDiscretization td_;
     std::vector<std::vector<RV>> process_;
     std::map<int, RV> numeraire_;
+    std::recursive_mutex numeraire_mu_;
 };
 
 // analytic curve quantities from the initial forward rates (ForwardCurve / DiscountCurveFromForwardCurve, T-ATM:353-355)
@@ -261,10 +267,25 @@ inline std::vector<double> synthetic_forward_rates(int n, double delta) {
 }
 
 // one pass of the calibration inner loop: simulate the model, value every calibration product.
-inline std::vector<double> lmm_value_products(LIBORMarketModel& model, const std::vector<SwaptionSpec>& products) {
+// threads > 1: the products are valued by that many host threads (product k by thread k mod threads), the way the
+// library's calibration does with numberOfThreads > 1; the reference test runs with ONE thread (T-ATM:319), the default.
+inline std::vector<double> lmm_value_products(LIBORMarketModel& model, const std::vector<SwaptionSpec>& products, int threads = 1) {
     model.simulate();
     std::vector<double> values(products.size());
-    for (size_t k = 0; k < products.size(); k++) values[k] = swaption_values(model, products[k])->getAverage();
+    if (threads <= 1) {
+        for (size_t k = 0; k < products.size(); k++) values[k] = swaption_values(model, products[k])->getAverage();
+        return values;
+    }
+    std::vector<std::thread> pool;
+    std::vector<std::exception_ptr> errors((size_t)threads);
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&, t] {
+            try {
+                for (size_t k = (size_t)t; k < products.size(); k += (size_t)threads) values[k] = swaption_values(model, products[k])->getAverage();
+            } catch (...) { errors[(size_t)t] = std::current_exception(); }
+        });
+    for (auto& th : pool) th.join();
+    for (auto& e : errors) if (e) std::rethrow_exception(e);
     return values;
 }
 

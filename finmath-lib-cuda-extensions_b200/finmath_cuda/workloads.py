@@ -42,6 +42,7 @@ class DriverLib:
         L.fmd_lmm_implied_vols.argtypes = [vp, vp, vp]
         L.fmd_lmm_bermudan.argtypes = [vp, i32, i32, i32, i32, dbl, dp]
         L.fmd_lmm_simulate.argtypes = [vp]
+        L.fmd_lmm_set_valuation_threads.argtypes = [vp, i32]
         self.L = L
 
     def check(self, rc: int) -> None:
@@ -115,6 +116,10 @@ class Lmm:
 
     def simulate(self) -> None:
         self.lib.check(self.lib.L.fmd_lmm_simulate(self.h))
+
+    def set_valuation_threads(self, threads: int) -> None:
+        """Host threads that value the calibration products of step() (the reference test uses one, T-ATM:319)."""
+        self.lib.check(self.lib.L.fmd_lmm_set_valuation_threads(self.h, int(threads)))
 
     def libor(self, time_index: int, libor_index: int) -> np.ndarray:
         out = np.empty(self.local_paths)

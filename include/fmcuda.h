@@ -17,7 +17,9 @@
  *   - operations are RECORDED, not executed: they append to an op-tape (a DAG of pending nodes). The tape is
  *     executed by one fused interpreter kernel when a value is demanded (reduction, host read, device-pointer
  *     export, explicit fmc_flush) or when the number of pending nodes exceeds the "flush_threshold" option.
- *   - all entry points are thread safe (one runtime lock); host buffers are only read/written during the call.
+ *   - all entry points are thread safe and callable from any thread (one runtime lock; the calling thread is bound to
+ *     the runtime's device); a reduction waits for its result WITHOUT the lock in single-rank runs, so other threads
+ *     keep recording and launching meanwhile. Host buffers are only read/written during the call.
  *   - arithmetic contract: IEEE binary32 round-to-nearest, NO fused multiply-add (the reference compiles with
  *     `-fmad false`, JCudaUtils.java:65-75, to match Java float arithmetic); exp/log/pow/sin/cos are evaluated in
  *     double and rounded to float as RandomVariableFromFloatArray.java:849,890,905,920,935,950 does.

@@ -438,3 +438,42 @@ def test_pool_recycles_and_purges(fc):
     del y
     fc.RandomVariableCuda.purge()
     assert fc.stats()["bytes_cached"] <= s2["bytes_cached"]
+
+
+def test_host_threads_share_the_runtime(fc, O):
+    """RandomVariableCuda objects are immutable and usable from any thread (RandomVariableCuda.java:64-65; the library's
+    calibration values its products from a thread pool). Four threads record, reduce and read back concurrently; every
+    thread's results must be the single-threaded ones. A waiting reduction does not hold the runtime lock."""
+    import threading
+    n = 50_000
+    rng = np.random.default_rng(99)
+    inputs = [(rng.uniform(0.5, 2.0, n), rng.uniform(-1.0, 1.0, n)) for _ in range(4)]
+
+    def work(x, y, rounds):
+        out = []
+        X, Y = fc.RandomVariableCuda(0.0, x), fc.RandomVariableCuda(0.0, y)
+        for r in range(rounds):
+            v = X.mult(1.0 + 0.125 * r).add(Y).discount(X, 0.5).floor(0.0)
+            out.append((v.getAverage(), v.squared().getMax(), X.getAverage(), float(v.getRealizationsFloat()[r])))
+        return out
+
+    want = [work(x, y, 12) for x, y in inputs]
+    got = [None] * 4
+    errors = []
+
+    def run(k):
+        try:
+            got[k] = work(*inputs[k], 12)
+        except Exception as e:      # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=run, args=(k,)) for k in range(4)]
+    for t in threads: t.start()
+    for t in threads: t.join()
+    assert not errors, errors
+    assert got == want
+    # and against the oracle for one of them
+    x, y = inputs[0]
+    xf, yf = O.from_f64(x), O.from_f64(y)
+    v = O.op_vs(O.FLOOR, O.op_vvs(O.DISCOUNT, O.op_vv(O.ADD, O.op_vs(O.MULT, xf, 1.0), yf), xf, 0.5), 0.0)
+    assert abs(want[0][0][0] - O.average(v)) <= 1e-9 * abs(O.average(v))

@@ -43,10 +43,15 @@ def test_lmm_simulation_and_swaptions_match_oracle(libs, paths):
     assert np.allclose(vg, vc, rtol=1e-9, atol=1e-15)
     # modified volatility parameters (what the optimiser does between simulations)
     p = mg.parameters() * np.linspace(0.8, 1.3, mg.n_parameters)
-    assert np.allclose(mg.step(p), mc.step(p), rtol=1e-9, atol=1e-15)
+    vg_p = mg.step(p)
+    assert np.allclose(vg_p, mc.step(p), rtol=1e-9, atol=1e-15)
     # host-array (end-to-end) arm gives the same numbers as the device-resident arm
     mg.prepare_host_brownian()
     assert np.array_equal(mg.step(p, from_host=True), mg.step(p))
+    # products valued by three host threads (the library's numberOfThreads > 1): the same numbers
+    mg.set_valuation_threads(3)
+    assert np.array_equal(mg.step(p), vg_p)
+    mg.set_valuation_threads(1)
     # model reproduces its own flat 0.5% volatility to MC accuracy
     iv = mg.implied_vols(mg.step(mg.parameters() * 0 + 0.005))
     assert np.all(np.abs(iv - 0.005) < 0.0015)
