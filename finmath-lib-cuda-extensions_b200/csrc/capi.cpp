@@ -377,7 +377,13 @@ int fmc_sync(void) {
     return guarded([&](Runtime& rt) { rt.require_init(); rt.flush_all(); FMC_CUDA(cudaStreamSynchronize(rt.stream)); });
 }
 static void set_option_locked(Runtime& rt, const char* key, double value) {
+    // everything that steers the code generator invalidates the cached tapes
+    static const char* const keeps_cache[] = {"flush_threshold", "profile", "p2p_reduce", "zero_copy_reduce", "leaf_reduce_kernel"};
+    bool keep = false;
+    for (const char* k : keeps_cache) keep = keep || !std::strcmp(key, k);
+    if (!keep) tape_cache_clear();
     if (!std::strcmp(key, "flush_threshold")) rt.opt.flush_threshold = (int64_t)value;
+    else if (!std::strcmp(key, "tape_cache")) rt.opt.tape_cache = value != 0.0;
     else if (!std::strcmp(key, "fuse")) { rt.opt.fuse = value != 0.0; if (rt.initialized) rt.flush_all(); }
     else if (!std::strcmp(key, "profile")) rt.opt.profile = value != 0.0;
     else if (!std::strcmp(key, "ring_max")) rt.opt.ring_max = std::max(1, std::min((int)value, (int)TAPE_MAX_RING));
@@ -414,7 +420,13 @@ int fmc_set_option(const char* key, double value) {
 }
 int fmc_get_option(const char* key, double* value) {
     return guarded([&](Runtime& rt) {
+        uint64_t c_hits = 0, c_misses = 0, c_entries = 0;
+        tape_cache_stats(&c_hits, &c_misses, &c_entries);
         if (!std::strcmp(key, "flush_threshold")) *value = (double)rt.opt.flush_threshold;
+        else if (!std::strcmp(key, "tape_cache")) *value = rt.opt.tape_cache ? 1.0 : 0.0;
+        else if (!std::strcmp(key, "tape_cache_hits")) *value = (double)c_hits;
+        else if (!std::strcmp(key, "tape_cache_misses")) *value = (double)c_misses;
+        else if (!std::strcmp(key, "tape_cache_entries")) *value = (double)c_entries;
         else if (!std::strcmp(key, "fuse")) *value = rt.opt.fuse ? 1.0 : 0.0;
         else if (!std::strcmp(key, "profile")) *value = rt.opt.profile ? 1.0 : 0.0;
         else if (!std::strcmp(key, "ring_max")) *value = rt.opt.ring_max;

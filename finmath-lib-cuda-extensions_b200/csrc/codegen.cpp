@@ -17,6 +17,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <unordered_map>
 
 #include "runtime.h"
 
@@ -62,7 +63,37 @@ struct AIns {
     uint8_t kind;
     int32_t arg;      // K_REG: register-file slot; K_LEAF: local id of the leaf
     uint32_t y;       // immediate bits / pointer-table slot
+    // where the immediates came from (tape cache: a replay patches them): 4 * cone position + operand index, -1 = not an
+    // immediate; neg: the word holds the negated value (SUB_I a == ADD_I -a). src2 belongs to the second immediate of the
+    // two-word forms, which travels in `arg`.
+    int32_t src = -1, src2 = -1;
+    uint8_t neg = 0;
 };
+AIns mk(uint16_t op, uint8_t kind, int32_t arg, uint32_t y, int32_t src = -1, uint8_t neg = 0, int32_t src2 = -1) {
+    AIns a; a.op = op; a.kind = kind; a.arg = arg; a.y = y; a.src = src; a.neg = neg; a.src2 = src2; return a;
+}
+
+// ---- tape cache: the launches of one cone, keyed by the cone's structure (see Runtime::run_cone) ----
+struct ImmPatch { int32_t word; int32_t src; uint8_t neg; };
+struct KernelPlan {
+    int n_instr = 0, n_prologue = 0, n_ring = 0, n_slots = 0, n_sets = 1, reduce_mode = RM_NONE, grid = 1, n_warps = TAPE_WARPS;
+    int n_leaf_slots = 0, n_result_stores = 0;
+    std::vector<TapeInstr> words;       // n_instr + 2
+    std::vector<int32_t> ptr_local;     // pointer table: the local whose buffer goes into each entry
+    std::vector<ImmPatch> patches;
+};
+struct ConePlan {
+    std::vector<uint32_t> key;
+    std::vector<KernelPlan> kernels;
+    std::vector<uint8_t> node_flags;    // per cone node: bit 0 gets a buffer (stored or spilled), bit 1 ephemeral
+};
+struct TapeCache {
+    std::unordered_map<uint64_t, std::vector<std::unique_ptr<ConePlan>>> map;
+    size_t entries = 0, words = 0;
+    uint64_t hits = 0, misses = 0;
+    void clear() { map.clear(); entries = 0; words = 0; }
+};
+TapeCache g_cache;
 
 uint32_t f2u(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 
@@ -139,7 +170,7 @@ struct Gen {
         if (!f.buf) f.buf = (float*)rt.pool.alloc(sizeof(float) * (size_t)std::max<int64_t>(n, 1));
     }
 
-    void emit(uint16_t op, uint8_t kind = K_NONE, int32_t arg = 0, uint32_t y = 0) { A.push_back(AIns{op, kind, arg, y}); }
+    void emit(uint16_t op, uint8_t kind = K_NONE, int32_t arg = 0, uint32_t y = 0, int32_t src = -1) { A.push_back(mk(op, kind, arg, y, src)); }
     void emit_src(uint16_t binop, int32_t L) {      // binary instruction whose operand is the value L (register file or leaf)
         const Info& f = info[L];
         if (f.reg >= 0) emit(A_BIN | binop, K_REG, f.reg);
@@ -227,11 +258,11 @@ struct Gen {
 
     void emit_binary(uint16_t op, int32_t A_, float immA, int32_t B_, float immB) {
         // choose the operand that sits in (or goes to) the accumulator
-        int32_t X, O; float immO; uint16_t xop;
-        if (A_ >= 0 && acc_owner == A_) { X = A_; O = B_; immO = immB; xop = op; }
-        else if (B_ >= 0 && acc_owner == B_) { X = B_; O = A_; immO = immA; xop = rev_op(op); }
-        else if (A_ >= 0) { X = A_; O = B_; immO = immB; xop = op; }
-        else { X = B_; O = A_; immO = immA; xop = rev_op(op); }
+        int32_t X, O; float immO; uint16_t xop; int kO;
+        if (A_ >= 0 && acc_owner == A_) { X = A_; O = B_; immO = immB; xop = op; kO = 1; }
+        else if (B_ >= 0 && acc_owner == B_) { X = B_; O = A_; immO = immA; xop = rev_op(op); kO = 0; }
+        else if (A_ >= 0) { X = A_; O = B_; immO = immB; xop = op; kO = 1; }
+        else { X = B_; O = A_; immO = immA; xop = rev_op(op); kO = 0; }
         set_pins(X, O);
         if (O == X) {
             // both operands are the same value
@@ -246,7 +277,7 @@ struct Gen {
         }
         take_acc(X, 1);
         if (O >= 0) emit_src(xop, O);
-        else emit(A_BIN | xop, K_IMM, 0, f2u(immO));
+        else emit(A_BIN | xop, K_IMM, 0, f2u(immO), 4 * pos + kO);
         consume(X);
         if (O >= 0) consume(O);
     }
@@ -267,7 +298,7 @@ struct Gen {
             const int32_t A_ = loc(0);
             set_pins(A_);
             take_acc(A_, 1);
-            emit(map[nd.op], K_NONE, 0, f2u(nd.imm[1]));
+            emit(map[nd.op], K_NONE, 0, f2u(nd.imm[1]), 4 * L + 1);
             consume(A_);
             break;
         }
@@ -289,14 +320,14 @@ struct Gen {
                 else if (B_ == A_ && info[A_].reg < 0 && !reloadable(A_)) put_acc_in_reg();
             } else {
                 save_acc();
-                emit(A_BIN | B_MOV, K_IMM, 0, f2u(nd.imm[1]));
+                emit(A_BIN | B_MOV, K_IMM, 0, f2u(nd.imm[1]), 4 * L + 1);
                 acc_owner = -1;
             }
             if (B_ >= 0) {
                 if (B_ == A_) { /* choose(x, a, a) == a */ }
                 else emit_src(B_SEL, B_);
             } else {
-                emit(A_BIN | B_SEL, K_IMM, 0, f2u(nd.imm[2]));
+                emit(A_BIN | B_SEL, K_IMM, 0, f2u(nd.imm[2]), 4 * L + 2);
             }
             if (A_ >= 0) consume(A_);
             if (B_ >= 0) consume(B_);
@@ -305,7 +336,7 @@ struct Gen {
         case N_CONST:
             set_pins(-1);
             save_acc();
-            emit(A_BIN | B_MOV, K_IMM, 0, f2u(nd.imm[0]));
+            emit(A_BIN | B_MOV, K_IMM, 0, f2u(nd.imm[0]), 4 * L + 0);
             break;
         default: fail(FMC_ERR_UNSUPPORTED, "internal: cannot emit node op %d", (int)nd.op);
         }
@@ -364,10 +395,11 @@ struct Gen {
                 && A[i + 3].op == (A_BIN | B_MUL) && A[i + 3].kind == K_IMM
                 && A[i + 4].op == (A_BIN | B_ADD) && A[i + 4].kind == K_REG && A[i + 4].arg == a.arg
                 && reg_dead_after(i + 5, a.arg)) {
-                const uint32_t first = A[i + 2].op == (A_BIN | B_SUB) ? (A[i + 2].y ^ 0x80000000u) : A[i + 2].y;
-                // y = first immediate, arg of the following pseudo-entry = second immediate (see schedule)
-                out.push_back(AIns{(uint16_t)T_ADDAFF_S, A[i + 1].kind, A[i + 1].arg, first});
-                out.push_back(AIns{A_EXT, K_NONE, 0, A[i + 3].y});
+                const bool sub = A[i + 2].op == (A_BIN | B_SUB);
+                const uint32_t first = sub ? (A[i + 2].y ^ 0x80000000u) : A[i + 2].y;
+                // y = first immediate, y of the following pseudo-entry = second immediate (see schedule)
+                out.push_back(mk((uint16_t)T_ADDAFF_S, A[i + 1].kind, A[i + 1].arg, first, A[i + 2].src, sub ? 1 : 0));
+                out.push_back(mk(A_EXT, K_NONE, 0, A[i + 3].y, A[i + 3].src));
                 if (A[i + 1].kind == K_LEAF) leaf_refs++;
                 i += 4;
                 continue;
@@ -378,7 +410,7 @@ struct Gen {
                 && A[i + 2].op == (A_BIN | B_MUL) && A[i + 2].kind == K_IMM
                 && A[i + 3].op == (A_BIN | B_ADD) && A[i + 3].kind == K_REG && A[i + 3].arg == a.arg
                 && reg_dead_after(i + 4, a.arg)) {
-                out.push_back(AIns{(uint16_t)(A_BIN | B_ADDPROD), A[i + 1].kind, A[i + 1].arg, A[i + 2].y});
+                out.push_back(mk((uint16_t)(A_BIN | B_ADDPROD), A[i + 1].kind, A[i + 1].arg, A[i + 2].y, A[i + 2].src));
                 if (A[i + 1].kind == K_LEAF) leaf_refs++;
                 i += 3;
                 continue;
@@ -392,26 +424,27 @@ struct Gen {
                 && !(a.kind == K_REG && a.arg == A[i + 3].arg) && reg_dead_after(i + 4, A[i + 3].arg)) {
                 const int t = A[i + 3].arg;
                 if (out.back().op == T_STR) out.pop_back();                                   // acc still holds the value
-                else out.back() = AIns{(uint16_t)(A_BIN | B_ADD), K_REG, t, 0u};              // ACCUM without the write-back
-                out.push_back(AIns{(uint16_t)(A_BIN | (A[i + 3].op == (A_BIN | B_VID) ? B_DISCOUNT : B_ACCRUE)), a.kind, a.arg, A[i + 1].y});
+                else out.back() = mk((uint16_t)(A_BIN | B_ADD), K_REG, t, 0u);              // ACCUM without the write-back
+                out.push_back(mk((uint16_t)(A_BIN | (A[i + 3].op == (A_BIN | B_VID) ? B_DISCOUNT : B_ACCRUE)), a.kind, a.arg, A[i + 1].y, A[i + 1].src));
                 if (a.kind == K_LEAF) leaf_refs++;
                 i += 3;
                 continue;
             }
             if (i + 1 < A.size() && a.op == (A_BIN | B_MUL) && a.kind == K_IMM && A[i + 1].op == (A_BIN | B_ADD) && A[i + 1].kind == K_IMM) {
-                out.push_back(AIns{(uint16_t)T_MULADD_II, K_IMM, (int32_t)A[i + 1].y, a.y});   // arg carries the second immediate's bits
+                out.push_back(mk((uint16_t)T_MULADD_II, K_IMM, (int32_t)A[i + 1].y, a.y, a.src, 0, A[i + 1].src));   // arg carries the second immediate's bits
                 i += 1;
                 continue;
             }
             if (i + 1 < A.size() && (a.op == (A_BIN | B_ADD) || a.op == (A_BIN | B_SUB)) && a.kind == K_IMM && A[i + 1].op == (A_BIN | B_MUL) && A[i + 1].kind == K_IMM) {
                 // x - a == x + (-a) bit for bit
-                const uint32_t first = a.op == (A_BIN | B_SUB) ? (a.y ^ 0x80000000u) : a.y;
-                out.push_back(AIns{(uint16_t)T_ADDMUL_II, K_IMM, (int32_t)A[i + 1].y, first});
+                const bool sub = a.op == (A_BIN | B_SUB);
+                const uint32_t first = sub ? (a.y ^ 0x80000000u) : a.y;
+                out.push_back(mk((uint16_t)T_ADDMUL_II, K_IMM, (int32_t)A[i + 1].y, first, a.src, sub ? 1 : 0, A[i + 1].src));
                 i += 1;
                 continue;
             }
             if (i + 1 < A.size() && a.op == (A_BIN | B_ADD) && a.kind == K_REG && A[i + 1].op == T_STR && A[i + 1].kind == K_REG && A[i + 1].arg == a.arg) {
-                out.push_back(AIns{(uint16_t)T_ACCUM_S, K_REG, a.arg, 0u});
+                out.push_back(mk((uint16_t)T_ACCUM_S, K_REG, a.arg, 0u));
                 i += 1;
                 continue;
             }
@@ -425,7 +458,10 @@ struct Gen {
     // ---- ring scheduling: abstract code -> tape (see tape_isa.h) ----
     struct Event { int32_t leaf; std::vector<int32_t> use; size_t k = 0; int slot = -1; bool waited = false; };
 
-    void schedule(int ring_max, bool pipeline, int horizon, std::vector<TapeInstr>& prologue, std::vector<TapeInstr>& body, int& n_ring) {
+    // patches: where the immediates of the abstract code ended up (indices into `body`)
+    void schedule(int ring_max, bool pipeline, int horizon, std::vector<TapeInstr>& prologue, std::vector<TapeInstr>& body, int& n_ring,
+                  std::vector<ImmPatch>& patches) {
+        auto note = [&](const AIns& a) { if (a.src >= 0) patches.push_back(ImmPatch{(int32_t)body.size() - 1, a.src, a.neg}); };
         // 1. residency intervals ("events") of every leaf: consecutive uses closer than `horizon` share one TMA copy
         std::vector<Event> ev;
         {
@@ -469,6 +505,7 @@ struct Gen {
             if (pipeline) pro_leaf[s] = ev[e].leaf;
         }
         // 3. walk the code
+        int refill_after_ext = -1;
         for (int32_t i = 0; i < (int32_t)A.size(); i++) {
             const AIns& a = A[i];
             if (a.kind == K_LEAF) {
@@ -508,17 +545,24 @@ struct Gen {
                 const uint32_t opc = (a.op == T_ADDAFF_S) ? (fl == 1u ? (uint32_t)T_ADDAFF_S : (uint32_t)T_ADDAFF_W)
                                                           : T_BIN0 + 3u * (uint32_t)(a.op & 0xff) + fl;
                 body.push_back(TapeInstr{ opc | ((uint32_t)E.slot << TAPE_SLOT_SHIFT), a.y });
+                note(a);
                 E.k++;
-                if (E.k >= E.use.size()) refill(E.slot);
+                // a two-word instruction keeps its extension word right behind it: the slot is refilled after that word
+                if (E.k >= E.use.size()) { if (a.op == T_ADDAFF_S) refill_after_ext = E.slot; else refill(E.slot); }
             } else if (a.op & A_BIN) {
                 const uint32_t bop = T_BIN0 + 3u * (uint32_t)(a.op & 0xff);
                 if (a.kind == K_IMM) body.push_back(TapeInstr{ bop, a.y });
                 else body.push_back(TapeInstr{ (bop + 1u) | ((R + (uint32_t)a.arg) << TAPE_SLOT_SHIFT), a.y });
+                note(a);
             } else if (a.op == A_EXT) {
                 body.push_back(TapeInstr{ T_END, a.y });                  // only its y is read
+                note(a);
+                if (refill_after_ext >= 0) { refill(refill_after_ext); refill_after_ext = -1; }
             } else if (a.op == T_MULADD_II || a.op == T_ADDMUL_II) {
                 body.push_back(TapeInstr{ (uint32_t)a.op, a.y });
+                note(a);
                 body.push_back(TapeInstr{ T_END, (uint32_t)a.arg });      // extension word: only its y is read
+                if (a.src2 >= 0) patches.push_back(ImmPatch{(int32_t)body.size() - 1, a.src2, 0});
             } else if (a.op == T_END) {
                 // re-arm whatever prologue slot has not been re-armed yet (only slots that were never freed: none in practice)
                 if (a.kind == K_REG) body.push_back(TapeInstr{ T_END | ((R + (uint32_t)a.arg) << TAPE_SLOT_SHIFT), 1u });
@@ -526,11 +570,15 @@ struct Gen {
             } else {
                 const uint32_t slot = (a.kind == K_REG) ? R + (uint32_t)a.arg : 0u;
                 body.push_back(TapeInstr{ (uint32_t)a.op | (slot << TAPE_SLOT_SHIFT), a.y });
+                if (a.op != T_STG && a.op != T_STGS) note(a);
             }
         }
         if (pipeline) for (uint32_t s = 0; s < R; s++)
             if (pro_leaf[s] >= 0 && !loadn_done[s]) fail(FMC_ERR_UNSUPPORTED, "internal: ring slot %u not re-armed", s);
     }
+
+    std::vector<KernelPlan> plans;      // the launches of this cone, in order (kept for the tape cache)
+    bool keep_plans = false;
 
     void launch(int reduce_mode, double reduce_param, int32_t weight_local) {
         if (reduce_mode == RM_DOT || reduce_mode == RM_WSQ) {
@@ -547,6 +595,7 @@ struct Gen {
         { PhaseTimer pt(3); if (rt.opt.fuse_ops) peephole(); }
 
         std::vector<TapeInstr> prologue, body;
+        KernelPlan kp;
         int n_ring = 0;
         // Shared-memory budget of one warp, in 1 KB slots, if target_ctas CTAs are to be resident per SM: short tapes
         // keep the occupancy high, long ones trade it for ring depth (never below ring_min slots).
@@ -566,39 +615,26 @@ struct Gen {
         const int slot_budget = (int)std::max<long>(1, budget_bytes / (n_warps * TAPE_SLOT_BYTES));
         int ring_max = std::max(1, std::min<int>(rt.opt.ring_max, TAPE_MAX_RING));
         ring_max = std::min(ring_max, std::max(rt.opt.ring_min, slot_budget - regs_used));
-        { PhaseTimer pt(4); schedule(ring_max, rt.opt.pipeline, rt.opt.horizon, prologue, body, n_ring); }
+        { PhaseTimer pt(4); schedule(ring_max, rt.opt.pipeline, rt.opt.horizon, prologue, body, n_ring, kp.patches); }
         PhaseTimer pt_prep(5);
         const size_t total = prologue.size() + 1 + body.size();
         if (total > (size_t)TAPE_MAX_INSTR + 1 || ptrs.size() > (size_t)TAPE_MAX_PTRS)
             fail(FMC_ERR_UNSUPPORTED, "internal: tape overflow (%zu instr, %zu ptrs)", total, ptrs.size());
-        TapeParams& P = *params;
-        P.n = n;
-        P.n_instr = (int)total;
-        P.n_prologue = (int)prologue.size();
-        P.n_ptrs = (int)ptrs.size();
-        P.n_ring = n_ring;
-        P.n_slots = n_ring + regs_used;
-        P.reduce_mode = reduce_mode;
-        P.reduce_param = reduce_param;
-        P.partials = rt.d_partials;
-        P.counter = rt.d_counter;
-        P.result = rt.d_result;
-        P.host_result = nullptr; P.ticket = 0.0;
-        for (int r = 0; r < XMAX_RANKS; r++) P.xchg.tables[r] = nullptr;
-        P.xchg.rank = 0; P.xchg.nranks = 1;
-        if (reduce_mode != RM_NONE) {
-            rt.fill_exchange(P.xchg, &P.ticket);                                          // sharded run: ticket = the exchange's own sequence
-            double* slot = rt.reduce_slot >= 0 ? rt.h_ticket_dev + 4 * rt.reduce_slot : nullptr;
-            if (P.xchg.nranks > 1) P.host_result = slot;
-            else if (rt.comm_size == 1 && rt.opt.zero_copy_reduce && slot) { P.ticket = (rt.reduce_ticket += 1.0); P.host_result = slot; }
-        }
-        if (reduce_mode != RM_NONE) rt.last_tape_ticket = P.host_result ? P.ticket : 0.0;
-        std::memcpy(P.ptrs, ptrs.data(), sizeof(float*) * ptrs.size());
-        if (!prologue.empty()) std::memcpy(P.instr, prologue.data(), sizeof(TapeInstr) * prologue.size());
-        P.instr[prologue.size()] = TapeInstr{ T_END, 0u };      // closes the prologue
-        std::memcpy(P.instr + prologue.size() + 1, body.data(), sizeof(TapeInstr) * body.size());
-        P.instr[total] = TapeInstr{ T_END, 0u };                // the interpreter prefetches two words ahead
-        P.instr[total + 1] = TapeInstr{ T_END, 0u };
+        kp.n_instr = (int)total;
+        kp.n_prologue = (int)prologue.size();
+        kp.n_ring = n_ring;
+        kp.n_slots = n_ring + regs_used;
+        kp.reduce_mode = reduce_mode;
+        kp.n_warps = n_warps;
+        kp.n_leaf_slots = n_leaf_slots; kp.n_result_stores = n_result_stores;
+        kp.words.reserve(total + 2);
+        kp.words.insert(kp.words.end(), prologue.begin(), prologue.end());
+        kp.words.push_back(TapeInstr{ T_END, 0u });             // closes the prologue
+        kp.words.insert(kp.words.end(), body.begin(), body.end());
+        kp.words.push_back(TapeInstr{ T_END, 0u });             // the interpreter prefetches two words ahead
+        kp.words.push_back(TapeInstr{ T_END, 0u });
+        for (ImmPatch& ip : kp.patches) ip.word += (int32_t)prologue.size() + 1;
+        kp.ptr_local = slotted;
         static OccCache occ;
         auto blocks_per_sm = [&](size_t smem_bytes) {
             const auto key = std::make_pair((smem_bytes + 1023) / 1024, reduce_mode * 8 + n_warps);
@@ -609,9 +645,9 @@ struct Gen {
         // slot sets: a tape that leaves most of the budget unused keeps several chunks per warp in flight
         int n_sets = 1, per_sm = 1, grid = 1;
         size_t smem = 0;
-        if (rt.opt.pipeline && n_ring > 0) n_sets = std::max(1, std::min(rt.opt.max_sets, slot_budget / std::max(1, P.n_slots)));
+        if (rt.opt.pipeline && n_ring > 0) n_sets = std::max(1, std::min(rt.opt.max_sets, slot_budget / std::max(1, kp.n_slots)));
         for (;;) {
-            smem = tape_smem_bytes(P.n_ptrs, P.n_instr, P.n_slots, n_sets, n_warps);
+            smem = tape_smem_bytes((int)ptrs.size(), kp.n_instr, kp.n_slots, n_sets, n_warps);
             if (smem > rt.smem_per_cta_max && n_sets > 1) { n_sets--; continue; }
             if (smem > rt.smem_per_cta_max) fail(FMC_ERR_UNSUPPORTED, "internal: tape needs %zu bytes of shared memory per CTA", smem);
             per_sm = blocks_per_sm(smem);
@@ -622,21 +658,61 @@ struct Gen {
             if (n_sets > 1 && n_sets > chunks_per_warp) { n_sets = (int)std::max<int64_t>(1, chunks_per_warp); continue; }
             break;
         }
-        P.n_sets = n_sets;
+        kp.n_sets = n_sets;
+        kp.grid = grid;
         static const bool log_tapes = std::getenv("FMC_LOG_TAPES") != nullptr;
         if (log_tapes)
             std::fprintf(stderr, "[fmc tape] n=%lld instr=%zu (abstract %zu, prologue %zu) ptrs=%zu leaves=%d stores=%d ring=%d regs=%d sets=%d warps=%d smem=%zu ctas/sm=%d grid=%d reduce=%d\n",
                          (long long)n, total, A.size(), prologue.size(), ptrs.size(), n_leaf_slots, n_result_stores, n_ring, regs_used, n_sets, n_warps, smem, per_sm, grid, reduce_mode);
+        submit(kp, reduce_param, false);
+        if (keep_plans) plans.push_back(std::move(kp));
+    }
+
+    // fill the launch parameters from a plan and the buffers / immediates of THIS cone, launch
+    void submit(const KernelPlan& kp, double reduce_param, bool patch) {
+        TapeParams& P = *params;
+        P.n = n;
+        P.n_instr = kp.n_instr;
+        P.n_prologue = kp.n_prologue;
+        P.n_ptrs = (int)kp.ptr_local.size();
+        P.n_ring = kp.n_ring;
+        P.n_slots = kp.n_slots;
+        P.n_sets = kp.n_sets;
+        P.reduce_mode = kp.reduce_mode;
+        P.reduce_param = reduce_param;
+        P.partials = rt.d_partials;
+        P.counter = rt.d_counter;
+        P.result = rt.d_result;
+        P.host_result = nullptr; P.ticket = 0.0;
+        for (int r = 0; r < XMAX_RANKS; r++) P.xchg.tables[r] = nullptr;
+        P.xchg.rank = 0; P.xchg.nranks = 1;
+        if (kp.reduce_mode != RM_NONE) {
+            rt.fill_exchange(P.xchg, &P.ticket);                                          // sharded run: ticket = the exchange's own sequence
+            double* slot = rt.reduce_slot >= 0 ? rt.h_ticket_dev + 4 * rt.reduce_slot : nullptr;
+            if (P.xchg.nranks > 1) P.host_result = slot;
+            else if (rt.comm_size == 1 && rt.opt.zero_copy_reduce && slot) { P.ticket = (rt.reduce_ticket += 1.0); P.host_result = slot; }
+            rt.last_tape_ticket = P.host_result ? P.ticket : 0.0;
+        }
+        for (size_t k = 0; k < kp.ptr_local.size(); k++) P.ptrs[k] = info[kp.ptr_local[k]].buf;
+        std::memcpy(P.instr, kp.words.data(), sizeof(TapeInstr) * kp.words.size());
+        if (patch)
+            for (const ImmPatch& ip : kp.patches) {
+                const uint32_t bits = f2u(rt.nodes[info[ip.src >> 2].node].imm[ip.src & 3]);
+                P.instr[ip.word].y = ip.neg ? (bits ^ 0x80000000u) : bits;
+            }
         if (rt.opt.profile) rt.profile_begin();
         const auto t_launch0 = std::chrono::steady_clock::now();
-        FMC_CUDA(launch_tape(P, grid, n_warps, rt.stream));
+        FMC_CUDA(launch_tape(P, kp.grid, kp.n_warps, rt.stream));
         rt.hostprof.launch += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_launch0).count();
-        if (rt.opt.profile) rt.profile_end(4ull * (uint64_t)n * (uint64_t)(n_leaf_slots + n_result_stores), 4ull * (uint64_t)n * (uint64_t)ptrs.size());
-        rt.stats.n_kernels++; rt.stats.n_tape_kernels++; rt.stats.n_tape_instr += total;
+        if (rt.opt.profile) rt.profile_end(4ull * (uint64_t)n * (uint64_t)(kp.n_leaf_slots + kp.n_result_stores), 4ull * (uint64_t)n * (uint64_t)kp.ptr_local.size());
+        rt.stats.n_kernels++; rt.stats.n_tape_kernels++; rt.stats.n_tape_instr += (uint64_t)kp.n_instr;
     }
 };
 
 }  // namespace
+
+void tape_cache_clear() { g_cache.clear(); }
+void tape_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* entries) { *hits = g_cache.hits; *misses = g_cache.misses; *entries = g_cache.entries; }
 
 void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* red) {
     require_init();
@@ -723,6 +799,61 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
         g.info[target_local].uses++;   // the reduction epilogue reads it from acc
     }
 
+    // ---- 1b. tape cache: a cone with the same structure was lowered before -> replay its launches with this cone's
+    // buffers and immediates. The key holds everything the code generator looks at except the immediates' values (and
+    // whether one equals 1.0f, which the ACCRUE / DISCOUNT fusion tests): per node the operation, where each operand
+    // comes from (scalar / cone position / number of the leaf in order of first use), whether the caller or a pending
+    // node outside the cone still refers to it, whether it is a target; the vector length, the reduction. Options that
+    // steer the generator empty the cache when they change (capi.cpp).
+    ConePlan* hit = nullptr;
+    std::unique_ptr<ConePlan> fresh;
+    uint64_t hash = 0;
+    if (opt.tape_cache && n_cone > 0) {
+        std::vector<uint32_t> key;
+        key.reserve((size_t)n_cone * 5 + 8);
+        key.push_back((uint32_t)n); key.push_back((uint32_t)((uint64_t)n >> 32));
+        key.push_back(red ? (uint32_t)red->mode : 0u);
+        key.push_back((uint32_t)target_local); key.push_back((uint32_t)weight_local);
+        key.push_back((uint32_t)n_cone);
+        for (int32_t t : targets) if (nodes[t].state == NS_LAZY) g.info[nodes[t].local].written_here = true;   // scratch: target mark
+        for (int32_t L = 0; L < n_cone; L++) {
+            const Info& f = g.info[L];
+            const Node& nd = nodes[f.node];
+            const int32_t cone_uses = f.uses - ((red && L == target_local) ? 1 : 0);
+            uint32_t w = (uint32_t)nd.op;
+            if (nd.ext_refs > 0) w |= 1u << 8;
+            if ((int64_t)nd.int_refs > (int64_t)cone_uses) w |= 1u << 9;
+            if (f.written_here) w |= 1u << 10;
+            for (int k = 0; k < 3; k++) if (nd.in[k] < 0 && nd.imm[k] == 1.0f) w |= 1u << (11 + k);
+            key.push_back(w);
+            for (int k = 0; k < 3; k++) key.push_back(nd.in[k] < 0 ? 0xffffffffu : (uint32_t)nodes[nd.in[k]].local);
+        }
+        for (int32_t t : targets) if (nodes[t].state == NS_LAZY) g.info[nodes[t].local].written_here = false;
+        hash = 1469598103934665603ull;
+        for (uint32_t w : key) { hash ^= w; hash *= 1099511628211ull; }
+        auto it = g_cache.map.find(hash);
+        if (it != g_cache.map.end())
+            for (auto& cp : it->second) if (cp->key == key) { hit = cp.get(); break; }
+        if (hit) g_cache.hits++;
+        else { g_cache.misses++; fresh.reset(new ConePlan); fresh->key.swap(key); g.keep_plans = true; }
+    }
+    if (hit) {
+        ph.reset(); ph.reset(new PhaseTimer(5));
+        // buffers of the nodes this cone stores (or spills), all up front
+        std::vector<float*> got;
+        try {
+            for (int32_t L = 0; L < n_cone; L++)
+                if (hit->node_flags[(size_t)L] & 1u) {
+                    g.info[L].buf = (float*)pool.alloc(sizeof(float) * (size_t)std::max<int64_t>(n, 1));
+                    got.push_back(g.info[L].buf);
+                }
+        } catch (...) {
+            for (float* b : got) pool.free(b);
+            throw;
+        }
+        for (int32_t L = 0; L < n_cone; L++) g.info[L].eph = (hit->node_flags[(size_t)L] & 2u) != 0;
+        for (const KernelPlan& kp : hit->kernels) g.submit(kp, red ? red->param : 0.0, true);
+    } else {
     ph.reset(); ph.reset(new PhaseTimer(1));
     // ---- 2. store / ephemeral classification (reverse topological order) ----
     for (int32_t L = n_cone - 1; L >= 0; L--) {
@@ -779,6 +910,18 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
     } else {
         g.launch(RM_NONE, 0.0, -1);
     }
+
+    if (fresh) {
+        fresh->kernels = std::move(g.plans);
+        fresh->node_flags.resize((size_t)n_cone);
+        size_t words = 0;
+        for (int32_t L = 0; L < n_cone; L++) fresh->node_flags[(size_t)L] = (uint8_t)((g.info[L].buf ? 1u : 0u) | (g.info[L].eph ? 2u : 0u));
+        for (const KernelPlan& kp : fresh->kernels) words += kp.words.size();
+        if (g_cache.entries >= 8192 || g_cache.words + words > (64u << 20) / sizeof(TapeInstr)) g_cache.clear();   // bounded: start over
+        g_cache.entries++; g_cache.words += words;
+        g_cache.map[hash].push_back(std::move(fresh));
+    }
+    }   // cache miss
 
     ph.reset(); ph.reset(new PhaseTimer(6));
     // ---- 4. bookkeeping: stored / spilled nodes become materialised and drop their operands ----

@@ -75,6 +75,7 @@ void Runtime::shutdown() {
     pool.purge();
     staging.release();
     tape_kernel_teardown();
+    tape_cache_clear();
     cudaFree(d_partials); cudaFree(d_counter); cudaFree(d_result); cudaFreeHost(h_result); cudaFreeHost(h_ticket);
     d_partials = nullptr; d_counter = nullptr; d_result = nullptr; h_result = nullptr; h_ticket = nullptr; h_ticket_dev = nullptr;
     for (auto& pe : prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }

@@ -107,6 +107,7 @@ struct Options {
     int cta_warps = 4;              // warps per interpreter CTA (2 or 4)
     bool fuse_ops = true;           // peephole fusion of the abstract code (MULADD_II, ACCUM_S, ADDPROD)
     int grid_limit = 0;             // > 0: cap the interpreter grid (tests: many chunks per warp at small sizes)
+    bool tape_cache = true;         // replay the launches of a cone whose structure was lowered before (codegen.cpp)
 };
 
 struct Stats {
@@ -244,6 +245,10 @@ public:
     void allgather(const double* dev_send, double* dev_recv, int count_per_rank);
     void allreduce_minmax(double* dev, int count, bool is_max);
 };
+
+// codegen.cpp
+void tape_cache_clear();
+void tape_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* entries);
 
 // comm.cpp
 void comm_get_unique_id(char* id);

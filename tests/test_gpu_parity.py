@@ -477,3 +477,111 @@ def test_host_threads_share_the_runtime(fc, O):
     xf, yf = O.from_f64(x), O.from_f64(y)
     v = O.op_vs(O.FLOOR, O.op_vvs(O.DISCOUNT, O.op_vv(O.ADD, O.op_vs(O.MULT, xf, 1.0), yf), xf, 0.5), 0.0)
     assert abs(want[0][0][0] - O.average(v)) <= 1e-9 * abs(O.average(v))
+
+
+def _random_program(fc, rng_struct, rng_val, leaves):
+    """One random expression DAG: the STRUCTURE comes from rng_struct, every scalar from rng_val."""
+    vals = list(leaves)
+    kept = []
+    for _ in range(int(rng_struct.integers(25, 70))):
+        a = vals[int(rng_struct.integers(max(0, len(vals) - 6), len(vals)))]
+        b = vals[int(rng_struct.integers(0, len(vals)))]
+        c = vals[int(rng_struct.integers(0, len(vals)))]
+        s1 = float(rng_val.uniform(0.25, 1.75)); s2 = float(rng_val.uniform(-0.5, 0.5))
+        if rng_struct.integers(0, 12) == 0: s1 = 1.0           # the ACCRUE / DISCOUNT fusion looks for x * p + 1
+        kind = int(rng_struct.integers(0, 18))
+        if kind == 0: r = a.add(s2)
+        elif kind == 1: r = a.sub(s2).mult(s1)
+        elif kind == 2: r = a.mult(s1).add(s2)
+        elif kind == 3: r = a.add(b)
+        elif kind == 4: r = a.sub(b)
+        elif kind == 5: r = a.mult(b)
+        elif kind == 6: r = a.div(b.abs().add(0.5))
+        elif kind == 7: r = a.accrue(b, s1)
+        elif kind == 8: r = a.discount(b.abs(), s1)
+        elif kind == 9: r = a.addProduct(b, s2)
+        elif kind == 10: r = a.addProduct(b, c)
+        elif kind == 11: r = a.sub(s2).choose(b, c)
+        elif kind == 12: r = a.floor(s2).cap(s1)
+        elif kind == 13: r = a.squared().add(1.0).vid(s1)
+        elif kind == 14: r = b.mult(s1).add(1.0).mult(a)      # accrue written out
+        elif kind == 15: r = b.abs().mult(s1).add(1.0).vid(a) # discount written out: a / (1 + |b| s1)
+        elif kind == 16: r = a.bus(s2).abs().sqrt()
+        else: r = a.add(b.sub(s2).mult(s1))
+        vals.append(r)
+        if rng_struct.integers(0, 5) == 0: kept.append(r)      # a handle the caller keeps: must be stored
+    out = [v.getRealizationsFloat().copy() for v in kept[-3:]] + [vals[-1].getRealizationsFloat().copy()]
+    red = (vals[-2].getAverage(), vals[-3].getVariance(), vals[-4].getMax())
+    return out, red
+
+
+class _OracleRV:
+    """The oracle behind the RandomVariable method names _random_program uses (stochastic values only)."""
+    def __init__(self, O, v): self.O, self.v = O, v
+    def _s(self, op, s): return _OracleRV(self.O, self.O.op_vs(op, self.v, s))
+    def _v(self, op, o): return _OracleRV(self.O, self.O.op_vv(op, self.v, o.v))
+    def _b(self, op, o): return self._v(op, o) if isinstance(o, _OracleRV) else self._s(op, o)
+    def add(self, o): return self._b(self.O.ADD, o)
+    def sub(self, o): return self._b(self.O.SUB, o)
+    def bus(self, o): return self._b(self.O.BUS, o)
+    def mult(self, o): return self._b(self.O.MULT, o)
+    def div(self, o): return self._b(self.O.DIV, o)
+    def vid(self, o): return self._b(self.O.VID, o)
+    def floor(self, o): return self._b(self.O.FLOOR, o)
+    def cap(self, o): return self._b(self.O.CAP, o)
+    def abs(self): return _OracleRV(self.O, self.O.op_v(self.O.ABS, self.v))
+    def sqrt(self): return _OracleRV(self.O, self.O.op_v(self.O.SQRT, self.v))
+    def squared(self): return _OracleRV(self.O, self.O.op_v(self.O.SQUARED, self.v))
+    def accrue(self, r, p): return _OracleRV(self.O, self.O.op_vvs(self.O.ACCRUE, self.v, r.v, p))
+    def discount(self, r, p): return _OracleRV(self.O, self.O.op_vvs(self.O.DISCOUNT, self.v, r.v, p))
+    def addProduct(self, a, b):
+        if isinstance(b, _OracleRV): return _OracleRV(self.O, self.O.op_vvv(self.O.ADDPRODUCT, self.v, a.v, b.v))
+        return _OracleRV(self.O, self.O.op_vvs(self.O.ADDPRODUCT, self.v, a.v, b))
+    def choose(self, a, b): return _OracleRV(self.O, self.O.op_vvv(self.O.CHOOSE, self.v, a.v, b.v))
+    def getRealizationsFloat(self): return self.v
+    def getAverage(self): return self.O.average(self.v)
+    def getVariance(self): return self.O.variance(self.v)
+    def getMax(self): return self.O.maximum(self.v)
+
+
+def test_random_programs_match_the_oracle(fc, O):
+    """Random expression DAGs (every fused form, kept intermediates, three reductions each) against the oracle."""
+    n = 3000
+    for prog in range(24):
+        rv = np.random.default_rng(5000 + prog)
+        xs = [rv.uniform(0.2, 2.0, n) for _ in range(4)]
+        got = _random_program(fc, np.random.default_rng(prog), np.random.default_rng(prog + 77), [fc.RandomVariableCuda(0.0, x) for x in xs])
+        want = _random_program(fc, np.random.default_rng(prog), np.random.default_rng(prog + 77), [_OracleRV(O, O.from_f64(x)) for x in xs])
+        assert all(bits_equal(g, w) for g, w in zip(got[0], want[0])), prog
+        for g, w in zip(got[1], want[1]):
+            assert (g != g and w != w) or abs(g - w) <= 1e-9 * abs(w) + 1e-300, (prog, got[1], want[1])
+
+
+def test_tape_cache_replays_are_bit_exact(fc):
+    """a cone whose structure was lowered before is replayed from the tape cache with the new buffers and
+    immediates patched in. Replays must be indistinguishable from fresh code generation: same structure, three sets of
+    scalars and inputs, cache off against cache on (miss, hit, hit)."""
+    import ctypes
+    from finmath_cuda import _capi as capi
+
+    def counter(key):
+        v = ctypes.c_double(); capi.check(capi.load().fmc_get_option(key.encode(), ctypes.byref(v))); return int(v.value)
+
+    n = 3000
+    try:
+        for prog in range(12):
+            results = {}
+            for cache in (0, 1):
+                fc.set_option("tape_cache", cache)
+                for vset in (0, 1, 2, 0):
+                    rv = np.random.default_rng(1000 * prog + vset)
+                    leaves = [fc.RandomVariableCuda(0.0, rv.uniform(0.2, 2.0, n)) for _ in range(4)]
+                    got = _random_program(fc, np.random.default_rng(prog), rv, leaves)
+                    if cache == 0: results[vset] = got
+                    else:
+                        want = results[vset]
+                        assert all(bits_equal(g, w) for g, w in zip(got[0], want[0])), (prog, vset)
+                        assert got[1] == want[1] or all(a == b or (a != a and b != b) for a, b in zip(got[1], want[1])), (prog, vset, got[1], want[1])
+        assert counter("tape_cache_hits") > 100
+    finally:
+        fc.set_option("tape_cache", 1)
