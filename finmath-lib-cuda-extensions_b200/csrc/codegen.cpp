@@ -451,7 +451,38 @@ struct Gen {
             if (a.kind == K_LEAF) leaf_refs++;
             out.push_back(a);
         }
-        A.swap(out);
+        // second pass, over the fused forms: whole LMM drift terms and swaption periods in one dispatch
+        //   MULADD_II a, b ; VID_I c ; MUL_I d          -> RATIO a, b, c, d        (c / (acc * a + b)) * d
+        //   MULADD_II a, b ; MUL_I c                    -> MULADDMUL a, b, c
+        //   ADDAFF x, a, b ; DISCOUNT x, p              -> ADDAFFDISC x, a, b, p   (same operand x)
+        A.clear();
+        for (size_t i = 0; i < out.size(); i++) {
+            const AIns& a = out[i];
+            if (a.op == T_MULADD_II && i + 2 < out.size() && out[i + 1].op == (A_BIN | B_VID) && out[i + 1].kind == K_IMM
+                && out[i + 2].op == (A_BIN | B_MUL) && out[i + 2].kind == K_IMM) {
+                A.push_back(mk((uint16_t)T_RATIO, K_IMM, a.arg, a.y, a.src, 0, a.src2));
+                A.push_back(mk(A_EXT, K_NONE, 0, out[i + 1].y, out[i + 1].src));
+                A.push_back(mk(A_EXT, K_NONE, 0, out[i + 2].y, out[i + 2].src));
+                i += 2;
+                continue;
+            }
+            if (a.op == T_MULADD_II && i + 1 < out.size() && out[i + 1].op == (A_BIN | B_MUL) && out[i + 1].kind == K_IMM) {
+                A.push_back(mk((uint16_t)T_MULADDMUL, K_IMM, a.arg, a.y, a.src, 0, a.src2));
+                A.push_back(mk(A_EXT, K_NONE, 0, out[i + 1].y, out[i + 1].src));
+                i += 1;
+                continue;
+            }
+            if (a.op == T_ADDAFF_S && i + 2 < out.size() && out[i + 1].op == A_EXT && out[i + 2].op == (A_BIN | B_DISCOUNT)
+                && out[i + 2].kind == a.kind && out[i + 2].arg == a.arg && (a.kind == K_REG || a.kind == K_LEAF)) {
+                A.push_back(mk((uint16_t)T_ADDAFFDISC_S, a.kind, a.arg, a.y, a.src, a.neg));
+                A.push_back(out[i + 1]);
+                A.push_back(mk(A_EXT, K_NONE, 0, out[i + 2].y, out[i + 2].src));
+                if (a.kind == K_LEAF) leaf_refs--;
+                i += 2;
+                continue;
+            }
+            A.push_back(a);
+        }
         n_leaf_refs = leaf_refs;
     }
 
@@ -505,7 +536,7 @@ struct Gen {
             if (pipeline) pro_leaf[s] = ev[e].leaf;
         }
         // 3. walk the code
-        int refill_after_ext = -1;
+        int refill_after_ext = -1, ext_left = 0;
         for (int32_t i = 0; i < (int32_t)A.size(); i++) {
             const AIns& a = A[i];
             if (a.kind == K_LEAF) {
@@ -543,12 +574,17 @@ struct Gen {
                 const uint32_t fl = E.waited ? 1u : 2u;        // _S / _W
                 E.waited = true;
                 const uint32_t opc = (a.op == T_ADDAFF_S) ? (fl == 1u ? (uint32_t)T_ADDAFF_S : (uint32_t)T_ADDAFF_W)
+                                   : (a.op == T_ADDAFFDISC_S) ? (fl == 1u ? (uint32_t)T_ADDAFFDISC_S : (uint32_t)T_ADDAFFDISC_W)
                                                           : T_BIN0 + 3u * (uint32_t)(a.op & 0xff) + fl;
                 body.push_back(TapeInstr{ opc | ((uint32_t)E.slot << TAPE_SLOT_SHIFT), a.y });
                 note(a);
                 E.k++;
                 // a two-word instruction keeps its extension word right behind it: the slot is refilled after that word
-                if (E.k >= E.use.size()) { if (a.op == T_ADDAFF_S) refill_after_ext = E.slot; else refill(E.slot); }
+                if (E.k >= E.use.size()) {
+                    if (a.op == T_ADDAFF_S) { refill_after_ext = E.slot; ext_left = 1; }
+                    else if (a.op == T_ADDAFFDISC_S) { refill_after_ext = E.slot; ext_left = 2; }
+                    else refill(E.slot);
+                }
             } else if (a.op & A_BIN) {
                 const uint32_t bop = T_BIN0 + 3u * (uint32_t)(a.op & 0xff);
                 if (a.kind == K_IMM) body.push_back(TapeInstr{ bop, a.y });
@@ -557,8 +593,8 @@ struct Gen {
             } else if (a.op == A_EXT) {
                 body.push_back(TapeInstr{ T_END, a.y });                  // only its y is read
                 note(a);
-                if (refill_after_ext >= 0) { refill(refill_after_ext); refill_after_ext = -1; }
-            } else if (a.op == T_MULADD_II || a.op == T_ADDMUL_II) {
+                if (refill_after_ext >= 0 && --ext_left == 0) { refill(refill_after_ext); refill_after_ext = -1; }
+            } else if (a.op == T_MULADD_II || a.op == T_ADDMUL_II || a.op == T_MULADDMUL || a.op == T_RATIO) {
                 body.push_back(TapeInstr{ (uint32_t)a.op, a.y });
                 note(a);
                 body.push_back(TapeInstr{ T_END, (uint32_t)a.arg });      // extension word: only its y is read

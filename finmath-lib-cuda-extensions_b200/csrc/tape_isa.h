@@ -19,7 +19,7 @@
 //                  slots [n_ring, S)         register file for intermediate values (T_STR writes, *_S reads)
 // Instruction word (8 bytes): x = op | slot_byte_offset (slot * TAPE_SLOT_BYTES, low 11 bits are the opcode);
 //                             y = float immediate bits | pointer-table index.
-// Two-word instructions (T_MULADD_II) take the y of the following word as a second immediate.
+// Multi-word instructions (T_MULADD_II, ..., T_RATIO) take the y of the following word(s) as further immediates.
 // Binary opcodes come in three flavours: _I (operand = immediate), _S (operand = slot), _W (operand = ring slot
 // whose TMA copy has not been waited for yet: wait on its mbarrier, then as _S).
 // Every primitive rounds once, exactly like the Java float code; the compound RandomVariable ops (accrue, discount,
@@ -64,6 +64,10 @@ enum TapeOp : uint32_t {
     T_ADDMUL_II,     // acc = (acc + imm) * imm2            (two words, two roundings; SUB_I a is ADD_I -a exactly)
     T_ADDAFF_S,      // acc = acc + (slot + imm) * imm2     (two words, three roundings: a payoff added to a running value)
     T_ADDAFF_W,      //   ... on a ring slot whose copy has not been waited for yet
+    T_MULADDMUL,     // acc = (acc * imm + imm2) * imm3                      (three words)
+    T_RATIO,         // acc = (imm3 / (acc * imm + imm2)) * imm4             (four words: p / (1 + L p) * sigma of an LMM drift term)
+    T_ADDAFFDISC_S,  // acc = (acc + (slot + imm) * imm2) / (1 + slot * imm3) (three words: one swap period of a swaption)
+    T_ADDAFFDISC_W,
     T_NUM_OPS
 };
 constexpr uint32_t T_BIN0 = 20;
@@ -72,7 +76,7 @@ constexpr uint32_t T_BIN0 = 20;
 //   MIN Math.min(acc, b)   MAX Math.max(acc, b)   (NaN propagating, -0 < +0)      SEL p ? acc : b
 //   ADDPROD  acc + b * s        ACCRUE  acc * (1 + b * s)        DISCOUNT  acc / (1 + b * s)     (_S/_W only)
 static_assert(T_MOV_I == T_BIN0, "binary opcode layout");
-static_assert(T_ADDMUL_II == T_BIN0 + 39 && T_ADDAFF_W == T_BIN0 + 41 && T_NUM_OPS == T_BIN0 + 42, "binary opcode layout");
+static_assert(T_ADDMUL_II == T_BIN0 + 39 && T_ADDAFF_W == T_BIN0 + 41 && T_ADDAFFDISC_W == T_BIN0 + 45 && T_NUM_OPS == T_BIN0 + 46, "binary opcode layout");
 
 enum ReduceMode : int {
     RM_NONE = 0,

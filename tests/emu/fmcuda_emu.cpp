@@ -179,6 +179,7 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
             }
             if (op == T_ADDAFF_S || op == T_ADDAFF_W) {
                 if (pc + 1 >= P.n_instr) bad("two-word instruction at the end of the tape");
+                if (P.instr[pc + 1].x != T_END) bad("the word behind two-word opcode %d is not its extension word", (int)op);
                 float imm2; std::memcpy(&imm2, &P.instr[pc + 1].y, 4);
                 if (op == T_ADDAFF_W) w.wait(slot);
                 const float* b = w.read(slot, chunk);
@@ -186,8 +187,33 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
                 pc++;
                 continue;
             }
+            if (op == T_MULADDMUL || op == T_RATIO || op == T_ADDAFFDISC_S || op == T_ADDAFFDISC_W) {
+                const int ext = (op == T_RATIO) ? 3 : 2;
+                if (pc + ext >= P.n_instr) bad("multi-word instruction at the end of the tape");
+                float im[4] = {imm, 0.f, 0.f, 0.f};
+                for (int k = 1; k <= ext; k++) {
+                    if ((P.instr[pc + k].x) != T_END) bad("extension word %d of opcode %d is not a plain T_END word", k, (int)op);
+                    std::memcpy(&im[k], &P.instr[pc + k].y, 4);
+                }
+                if (op == T_MULADDMUL) {
+                    for (int e = 0; e < C; e++) { float t = acc[e] * im[0]; t = t + im[1]; acc[e] = t * im[2]; }
+                } else if (op == T_RATIO) {
+                    for (int e = 0; e < C; e++) { float t = acc[e] * im[0]; t = t + im[1]; t = im[2] / t; acc[e] = t * im[3]; }
+                } else {
+                    if (op == T_ADDAFFDISC_W) w.wait(slot);
+                    const float* b = w.read(slot, chunk);
+                    for (int e = 0; e < C; e++) {
+                        float t = b[e] + im[0]; t = t * im[1]; const float num = acc[e] + t;
+                        float d = b[e] * im[2]; d = d + 1.0f;
+                        acc[e] = num / d;
+                    }
+                }
+                pc += ext;
+                continue;
+            }
             if (op == T_ADDMUL_II) {
                 if (pc + 1 >= P.n_instr) bad("two-word instruction at the end of the tape");
+                if (P.instr[pc + 1].x != T_END) bad("the word behind two-word opcode %d is not its extension word", (int)op);
                 float imm2; std::memcpy(&imm2, &P.instr[pc + 1].y, 4);
                 for (int e = 0; e < C; e++) { const float t = acc[e] + imm; acc[e] = t * imm2; }
                 pc++;
@@ -253,6 +279,7 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
             case T_POW: for (int e = 0; e < C; e++) acc[e] = jpow(acc[e], imm); break;
             case T_MULADD_II: {
                 if (pc + 1 >= P.n_instr) bad("two-word instruction at the end of the tape");
+                if (P.instr[pc + 1].x != T_END) bad("the word behind two-word opcode %d is not its extension word", (int)op);
                 float imm2; std::memcpy(&imm2, &P.instr[pc + 1].y, 4);
                 for (int e = 0; e < C; e++) { const float t = acc[e] * imm; acc[e] = t + imm2; }
                 pc++;                                   // the extension word is not an instruction
@@ -302,7 +329,10 @@ void dump_tape(const TapeParams& P, int grid) {
     for (int i = 0; i < P.n_instr; i++) {
         const uint32_t op = P.instr[i].x & ((1u << TAPE_SLOT_SHIFT) - 1u), slot = P.instr[i].x >> TAPE_SLOT_SHIFT;
         float imm; std::memcpy(&imm, &P.instr[i].y, 4);
-        if (op == T_ADDMUL_II) std::fprintf(stderr, "  %4d ADDMUL_II %g\n", i, imm);
+        if (op == T_MULADDMUL) std::fprintf(stderr, "  %4d MULADDMUL %g\n", i, imm);
+        else if (op == T_RATIO) std::fprintf(stderr, "  %4d RATIO %g\n", i, imm);
+        else if (op == T_ADDAFFDISC_S || op == T_ADDAFFDISC_W) std::fprintf(stderr, "  %4d ADDAFFDISC_%c s%u %g\n", i, op == T_ADDAFFDISC_S ? 'S' : 'W', slot, imm);
+        else if (op == T_ADDMUL_II) std::fprintf(stderr, "  %4d ADDMUL_II %g\n", i, imm);
         else if (op == T_ADDAFF_S || op == T_ADDAFF_W) std::fprintf(stderr, "  %4d ADDAFF_%c s%u %g\n", i, op == T_ADDAFF_S ? 'S' : 'W', slot, imm);
         else if (op >= T_BIN0) {
             const uint32_t k = (op - T_BIN0) / 3u, fl = (op - T_BIN0) % 3u;
