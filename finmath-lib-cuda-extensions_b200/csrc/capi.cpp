@@ -374,7 +374,7 @@ int fmc_reduce(int kind, fmc_vec a, fmc_vec weights, double* out) {
 // ---- execution control ----
 int fmc_flush(void) { return guarded([&](Runtime& rt) { rt.require_init(); rt.flush_all(); }); }
 int fmc_sync(void) {
-    return guarded([&](Runtime& rt) { rt.require_init(); rt.flush_all(); FMC_CUDA(cudaStreamSynchronize(rt.stream)); });
+    return guarded([&](Runtime& rt) { rt.require_init(); rt.flush_all(); rt.sync_stream(); });
 }
 static void set_option_locked(Runtime& rt, const char* key, double value) {
     // everything that steers the code generator invalidates the cached tapes
@@ -447,6 +447,8 @@ int fmc_get_option(const char* key, double* value) {
         else if (!std::strcmp(key, "host_us_codegen")) *value = rt.hostprof.codegen;
         else if (!std::strcmp(key, "host_us_launch")) *value = rt.hostprof.launch;
         else if (!std::strcmp(key, "host_us_sync")) *value = rt.hostprof.sync;
+        else if (!std::strcmp(key, "host_us_upload")) *value = rt.hostprof.upload;
+        else if (!std::strcmp(key, "host_us_upload_wait")) *value = rt.hostprof.upload_wait;
         else fail(FMC_ERR_INVALID, "unknown option '%s'", key);
     });
 }

@@ -1026,6 +1026,7 @@ bool Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
         ticket = last_tape_ticket;
     }
     const auto t_sync0 = std::chrono::steady_clock::now();
+    const uint64_t stamp_at_launch = pool.free_stamp;   // blocks freed so far were last used by work queued before this kernel
     if (ticket != 0.0) {
         // the last block of the reduction wrote {count, value, M2} (after the in-kernel exchange: of ALL ranks) and then the
         // ticket into mapped pinned memory: spin on the ticket instead of a 32-byte copy plus a stream synchronisation
@@ -1056,6 +1057,7 @@ bool Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
         if (err) fail(err_code, "%s", err);
         FMC_CUDA(cuda_err);
         out[0] = r0; out[1] = r1; out[2] = r2;
+        settled_stamp = std::max(settled_stamp, stamp_at_launch);
         hostprof.sync += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_sync0).count();
         stats.d2h += 32;
         return p2p;
@@ -1065,14 +1067,14 @@ bool Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
         // rank order (capi.cpp)
         allgather(d_result, d_result + 8, 4);
         FMC_CUDA(cudaMemcpyAsync(h_result, d_result + 8, sizeof(double) * 4 * (size_t)comm_size, cudaMemcpyDeviceToHost, stream));
-        FMC_CUDA(cudaStreamSynchronize(stream));
+        sync_stream();
         hostprof.sync += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_sync0).count();
         stats.d2h += 32 * (uint64_t)comm_size;
         out[0] = h_result[4 * comm_rank]; out[1] = h_result[4 * comm_rank + 1]; out[2] = h_result[4 * comm_rank + 2];
         return false;
     }
     FMC_CUDA(cudaMemcpyAsync(h_result, d_result, sizeof(double) * 4, cudaMemcpyDeviceToHost, stream));
-    FMC_CUDA(cudaStreamSynchronize(stream));
+    sync_stream();
     hostprof.sync += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_sync0).count();
     stats.d2h += 32;
     out[0] = h_result[0]; out[1] = h_result[1]; out[2] = h_result[2];

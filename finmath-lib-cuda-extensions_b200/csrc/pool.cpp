@@ -37,7 +37,7 @@ void* DevicePool::carve(size_t rounded) {
             void* p = sl.base + sl.used;
             sl.used += rounded;
             sl.live++;
-            blocks_[p] = Block{rounded, (int)s};
+            blocks_[p] = Block{rounded, (int)s, 0};
             return p;
         }
     }
@@ -61,7 +61,7 @@ void* DevicePool::carve(size_t rounded) {
     for (size_t i = 0; i < slabs_.size(); i++) if (!slabs_[i].base) { s = (int)i; break; }
     if (s < 0) { slabs_.push_back(Slab{}); s = (int)slabs_.size() - 1; }
     slabs_[s] = Slab{(char*)base, slab_size, rounded, 1, dedicated};
-    blocks_[base] = Block{rounded, s};
+    blocks_[base] = Block{rounded, s, 0};
     return base;
 }
 
@@ -84,10 +84,42 @@ void* DevicePool::alloc(size_t bytes) {
     return p;
 }
 
+void* DevicePool::alloc_settled(size_t bytes, uint64_t settled_stamp, bool* settled) {
+    const size_t rounded = round_size(bytes);
+    auto it = free_.find(rounded);
+    if (it != free_.end()) {
+        auto& v = it->second;                       // oldest frees sit at the front (free() appends, alloc() pops the back)
+        for (size_t i = 0; i < v.size() && i < 64; i++) {
+            void* p = v[i];
+            Block& b = blocks_[p];
+            if (b.stamp > settled_stamp) continue;
+            v.erase(v.begin() + (long)i);
+            n_alloc++; n_reused++;
+            bytes_cached -= rounded;
+            slabs_[b.slab].live++;
+            bytes_in_use += rounded;
+            high_water = std::max(high_water, bytes_in_use);
+            *settled = true;
+            return p;
+        }
+    }
+    if (it == free_.end() || it->second.empty()) {   // nothing cached of this size: fresh memory, or the usual OOM ladder
+        *settled = true;
+        n_alloc++;
+        void* p = carve(rounded);
+        bytes_in_use += rounded;
+        high_water = std::max(high_water, bytes_in_use);
+        return p;
+    }
+    *settled = false;                                // cached blocks exist but all were freed too recently
+    return alloc(bytes);
+}
+
 void DevicePool::free(void* p) {
     if (!p) return;
     auto it = blocks_.find(p);
     if (it == blocks_.end()) return;
+    it->second.stamp = ++free_stamp;
     const size_t rounded = it->second.size;
     slabs_[it->second.slab].live--;
     bytes_in_use -= rounded;

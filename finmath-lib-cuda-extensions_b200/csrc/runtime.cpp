@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <condition_variable>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <functional>
 #include <thread>
@@ -43,8 +44,10 @@ void Runtime::init(int device_index) {
     FMC_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     FMC_CUDA(cudaEventCreate(&ev_start));
     FMC_CUDA(cudaEventCreate(&ev_stop));
-    FMC_CUDA(cudaEventCreateWithFlags(&ev_copy[0], cudaEventDisableTiming));
-    FMC_CUDA(cudaEventCreateWithFlags(&ev_copy[1], cudaEventDisableTiming));
+    FMC_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < STAGING_SLOTS; i++) { FMC_CUDA(cudaEventCreateWithFlags(&ev_copy[i], cudaEventDisableTiming)); staging_busy[i] = false; }
+    FMC_CUDA(cudaEventCreateWithFlags(&ev_order, cudaEventDisableTiming));
+    settled_stamp = 0;
     FMC_CUDA(tape_kernel_setup(&smem_per_cta_max));
     max_grid = sm_count * 16;
     FMC_CUDA(cudaMalloc(&d_partials, sizeof(double) * 128 * (size_t)max_grid));
@@ -63,7 +66,8 @@ void Runtime::init(int device_index) {
 void Runtime::shutdown() {
     if (!initialized) return;
     cudaStreamSynchronize(stream);
-    staging_busy[0] = staging_busy[1] = false;
+    if (copy_stream) cudaStreamSynchronize(copy_stream);
+    for (int i = 0; i < STAGING_SLOTS; i++) staging_busy[i] = false;
     comm_destroy(*this);
     brownian_release_caches(*this);
     for (auto& nd : nodes) {
@@ -80,7 +84,9 @@ void Runtime::shutdown() {
     d_partials = nullptr; d_counter = nullptr; d_result = nullptr; h_result = nullptr; h_ticket = nullptr; h_ticket_dev = nullptr;
     for (auto& pe : prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
     prof_events.clear(); prof_used = 0;
-    cudaEventDestroy(ev_start); cudaEventDestroy(ev_stop); cudaEventDestroy(ev_copy[0]); cudaEventDestroy(ev_copy[1]);
+    cudaEventDestroy(ev_start); cudaEventDestroy(ev_stop); for (int i = 0; i < STAGING_SLOTS; i++) { cudaEventDestroy(ev_copy[i]); ev_copy[i] = nullptr; }
+    cudaEventDestroy(ev_order); ev_order = nullptr;
+    if (copy_stream) { cudaStreamDestroy(copy_stream); copy_stream = nullptr; }
     cudaStreamDestroy(stream);
     stream = nullptr;
     initialized = false;
@@ -327,30 +333,57 @@ inline void cast_to_staging(float* dst, const float* src, int64_t n) { std::memc
 
 }  // namespace
 
+constexpr size_t kUploadChunk = 1u << 20;  // 4 MiB of floats per staging chunk on the upload path (STAGING_SLOTS of them)
+
 template <typename T>
 static int32_t upload_impl(Runtime& rt, const T* h, int64_t n) {
     if (n > 0 && !h) fail(FMC_ERR_INVALID, "null host pointer");
-    const int32_t idx = rt.new_leaf(n);
-    float* dst = rt.nodes[idx].buf;
+    if (n < 0) fail(FMC_ERR_INVALID, "negative vector size %lld", (long long)n);
+    struct Timer {
+        double& acc; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        explicit Timer(double& a) : acc(a) {}
+        ~Timer() { acc += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); }
+    } timer(rt.hostprof.upload);
+    // The copy runs on the copy stream, concurrently with the kernels already queued on the compute stream. Its destination
+    // must therefore be memory no queued kernel still touches: a block freed before the last point the host saw the compute
+    // stream idle or a reduction finish, or fresh memory.
+    { const uint64_t stamp = rt.pool.free_stamp; if (cudaStreamQuery(rt.stream) == cudaSuccess) rt.settled_stamp = std::max(rt.settled_stamp, stamp); else cudaGetLastError(); }
+    bool settled = true;
+    float* dst = (float*)rt.pool.alloc_settled(sizeof(float) * (size_t)std::max<int64_t>(n, 1), rt.settled_stamp, &settled);
+    int32_t idx;
+    try {
+        idx = rt.new_node();
+    } catch (...) { rt.pool.free(dst); throw; }
+    {
+        Node& nd = rt.nodes[idx];
+        nd.op = N_LEAF; nd.state = NS_MAT; nd.n = n; nd.ext_refs = 1; nd.buf = dst;
+        rt.n_live_handles++;
+    }
+    static_assert(2 * kChunkElems >= Runtime::STAGING_SLOTS * kUploadChunk, "the staging buffer holds all upload chunks");
     rt.staging.ensure(2 * kChunkElems * sizeof(float));
-    float* stage[2] = {(float*)rt.staging.host, (float*)rt.staging.host + kChunkElems};
-    cudaEvent_t done[2] = {rt.ev_copy[0], rt.ev_copy[1]};
     int64_t off = 0;
     try {
+        if (!settled) {                            // recycled too recently: the copy must wait for what is queued
+            FMC_CUDA(cudaEventRecord(rt.ev_order, rt.stream));
+            FMC_CUDA(cudaStreamWaitEvent(rt.copy_stream, rt.ev_order, 0));
+        }
+        int last = -1;
         while (off < n) {
-            const int64_t m = std::min<int64_t>(kChunkElems, n - off);
-            const int which = rt.staging_next; rt.staging_next ^= 1;
-            if (rt.staging_busy[which]) { FMC_CUDA(cudaEventSynchronize(done[which])); rt.staging_busy[which] = false; }
-            float* s = stage[which];
+            const int64_t m = std::min<int64_t>(kUploadChunk, n - off);
+            const int which = rt.staging_next; rt.staging_next = (rt.staging_next + 1) % Runtime::STAGING_SLOTS;
+            if (rt.staging_busy[which]) { Timer tw(rt.hostprof.upload_wait); FMC_CUDA(cudaEventSynchronize(rt.ev_copy[which])); rt.staging_busy[which] = false; }
+            float* s = (float*)rt.staging.host + (size_t)which * kUploadChunk;
             const T* src = h + off;
             HostWorkers::get().parallel_for(m, [&](int64_t b, int64_t e) { cast_to_staging(s + b, src + b, e - b); });   // RVC:768-774
-            FMC_CUDA(cudaMemcpyAsync(dst + off, s, sizeof(float) * (size_t)m, cudaMemcpyHostToDevice, rt.stream));
-            FMC_CUDA(cudaEventRecord(done[which], rt.stream));
+            FMC_CUDA(cudaMemcpyAsync(dst + off, s, sizeof(float) * (size_t)m, cudaMemcpyHostToDevice, rt.copy_stream));
+            FMC_CUDA(cudaEventRecord(rt.ev_copy[which], rt.copy_stream));
             rt.staging_busy[which] = true;
+            last = which;
             off += m;
         }
-        // no wait here: the staging half stays marked busy until its copy's event is seen by the next user, so the
-        // conversion of the next vector overlaps this vector's transfer (the copy is stream-ordered before any kernel)
+        // no host wait: a staging chunk stays marked busy until its copy's event is seen by its next user. Whatever the
+        // compute stream is given from here on runs after the copy.
+        if (last >= 0) FMC_CUDA(cudaStreamWaitEvent(rt.stream, rt.ev_copy[last], 0));
     } catch (...) {
         rt.release_ext(idx);
         throw;
@@ -362,7 +395,13 @@ int32_t Runtime::upload_f64(const double* h, int64_t n) { return upload_impl(*th
 int32_t Runtime::upload_f32(const float* h, int64_t n) { return upload_impl(*this, h, n); }
 
 void Runtime::staging_quiesce() {
-    for (int w = 0; w < 2; w++) if (staging_busy[w]) { FMC_CUDA(cudaEventSynchronize(ev_copy[w])); staging_busy[w] = false; }
+    for (int w = 0; w < STAGING_SLOTS; w++) if (staging_busy[w]) { FMC_CUDA(cudaEventSynchronize(ev_copy[w])); staging_busy[w] = false; }
+}
+
+void Runtime::sync_stream() {
+    const uint64_t stamp = pool.free_stamp;          // everything freed so far was last used by work queued before this point
+    FMC_CUDA(cudaStreamSynchronize(stream));
+    settled_stamp = std::max(settled_stamp, stamp);
 }
 
 template <typename T>

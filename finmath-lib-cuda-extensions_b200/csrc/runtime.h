@@ -39,12 +39,18 @@ class DevicePool {
 public:
     void* alloc(size_t bytes);          // throws Fail{FMC_ERR_OOM}
     void  free(void* p);
+    // For a buffer that a SECOND stream will write (host uploads on the copy stream): a cached block is only handed out if
+    // it was freed at or before `settled_stamp` (every kernel that touched it is known to have finished), else fresh memory
+    // is carved. *settled = false when neither was possible and an ordinary cached block is returned: the caller must then
+    // order the second stream behind the compute stream.
+    void* alloc_settled(size_t bytes, uint64_t settled_stamp, bool* settled);
+    uint64_t free_stamp = 0;            // every free() gets the next stamp
     void  trim();                       // return slabs without live blocks to the driver
     void  purge();                      // trim, must be called with no live blocks to release everything
     uint64_t bytes_in_use = 0, bytes_cached = 0, bytes_reserved = 0, high_water = 0, n_alloc = 0, n_reused = 0;
 private:
     struct Slab { char* base; size_t size, used; int live; bool dedicated; };
-    struct Block { size_t size; int slab; };
+    struct Block { size_t size; int slab; uint64_t stamp; };
     std::vector<Slab> slabs_;
     std::unordered_map<void*, Block> blocks_;                  // live + cached blocks by address
     std::unordered_map<size_t, std::vector<void*>> free_;      // rounded size -> cached blocks
@@ -116,7 +122,7 @@ struct Stats {
 };
 
 // host-side time spent per phase (microseconds since the last reset); read with fmc_get_option("host_us_*")
-struct HostProfile { double codegen = 0, launch = 0, sync = 0; };
+struct HostProfile { double codegen = 0, launch = 0, sync = 0, upload = 0, upload_wait = 0; };   // upload: whole host->device calls; upload_wait: of that, waiting for a free staging chunk
 
 struct Operand { int32_t node; float imm; };   // node < 0 => scalar
 
@@ -156,7 +162,13 @@ public:
     size_t smem_per_sm = 0, smem_per_cta_max = 0;
     cudaDeviceProp prop{};
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_copy[2] = {nullptr, nullptr};
+    // host -> device uploads run on their own stream so that they overlap the kernels already queued (the compute stream
+    // waits for the copy's event before it goes on); STAGING_SLOTS pinned chunks let the host run ahead of the copies
+    static constexpr int STAGING_SLOTS = 8;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_copy[STAGING_SLOTS] = {nullptr}, ev_order = nullptr;
+    uint64_t settled_stamp = 0;         // pool blocks freed up to this stamp are no longer touched by any queued kernel
+    void sync_stream();                 // cudaStreamSynchronize(stream) + settled_stamp update
     void init(int device_index);
     void shutdown();
     void require_init() const;
@@ -164,7 +176,7 @@ public:
     // memory
     DevicePool pool;
     Staging staging;
-    bool staging_busy[2] = {false, false};   // a host->device copy out of that staging half may still be in flight
+    bool staging_busy[STAGING_SLOTS] = {false};   // a host->device copy out of that staging chunk may still be in flight
     int staging_next = 0;
     void staging_quiesce();                  // wait for those copies (before the staging buffer is reused for something else)
     double* d_partials = nullptr;       // reduction scratch

@@ -56,6 +56,7 @@ cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)0x1; return cuda
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)0x1; return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned int) { return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }

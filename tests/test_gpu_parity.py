@@ -585,3 +585,32 @@ def test_tape_cache_replays_are_bit_exact(fc):
         assert counter("tape_cache_hits") > 100
     finally:
         fc.set_option("tape_cache", 1)
+
+
+def test_uploads_on_the_copy_stream_do_not_overtake_queued_kernels(fc, O):
+    """Host uploads run on their own stream, concurrently with kernels already queued. A block freed while a queued
+    kernel may still read it must not be overwritten by the next upload: upload a, queue a long chain on it without
+    waiting, drop a, upload b (which would recycle a's block), repeat; every chain result must come from ITS input."""
+    from finmath_cuda import _capi as capi
+    n = 6_000_000
+    rng = np.random.default_rng(5)
+    inputs = [rng.uniform(0.5, 1.5, n) for _ in range(3)]
+    want = []
+    for a in inputs:
+        v = O.from_f64(a)
+        for _ in range(6):
+            v = O.op_v(O.SQRT, O.op_vs(O.ADD, O.op_vs(O.MULT, v, 1.25), 0.5))
+        want.append(v)
+    for round_ in range(3):
+        results = []
+        for a in inputs:
+            x = fc.RandomVariableCuda(0.0, a)
+            y = x
+            for _ in range(6):
+                y = y.mult(1.25).add(0.5).sqrt()
+            z = y.add(0.0)                       # force y to be stored by a launch that is only QUEUED here
+            capi.check(capi.load().fmc_flush())
+            del x, y                             # frees the input (and intermediate) blocks while the kernel may still run
+            results.append(z)
+        for z, w in zip(results, want):
+            assert bits_equal(z.getRealizationsFloat(), O.op_vs(O.ADD, w, 0.0)), round_
