@@ -131,8 +131,11 @@ int fmc_sync(void);                     /* flush + wait for the device (cuCtxSyn
  *          interpreter scheduling knobs (tuning / tests; defaults in csrc/runtime.h): "ring_max", "ring_min", "target_ctas",
  *          "horizon", "pipeline", "max_sets", "grid_limit", "fuse_ops", "cta_warps", "zero_copy_reduce", "leaf_reduce_kernel",
  *          "p2p_reduce" (1 default: sharded runs exchange reduction partials inside the kernel over NVLink peer memory; 0: NCCL);
- *          read-only: "p2p_ready", "device_index";
- *          read-only host-side timers in microseconds since fmc_reset_stats: "host_us_codegen", "host_us_launch", "host_us_sync".
+ *          "tape_cache" (1 default: a cone of pending nodes whose structure was lowered before is replayed with the new
+ *          buffers and immediates patched in instead of being code-generated again);
+ *          read-only: "p2p_ready", "device_index", "tape_cache_hits", "tape_cache_misses", "tape_cache_entries";
+ *          read-only host-side timers in microseconds since fmc_reset_stats: "host_us_codegen", "host_us_launch", "host_us_sync",
+ *          "host_us_upload" (host->device calls; of that "host_us_upload_wait" waiting for a free pinned staging chunk).
  *          The environment variable FMC_OPTIONS="key=value,..." is applied once at fmc_init. */
 int fmc_set_option(const char* key, double value);
 int fmc_get_option(const char* key, double* value);
