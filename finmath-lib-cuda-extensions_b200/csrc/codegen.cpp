@@ -175,7 +175,8 @@ struct Gen {
         const Info& f = info[L];
         if (f.reg >= 0) emit(A_BIN | binop, K_REG, f.reg);
         else if (reloadable(L)) { slot_for(L); emit(A_BIN | binop, K_LEAF, L); n_leaf_refs++; }
-        else fail(FMC_ERR_UNSUPPORTED, "internal: operand has no location");
+        else fail(FMC_ERR_UNSUPPORTED, "internal: operand %d has no location (at %d: lazy %d computed %d store %d buffer %d written here %d, uses left %d)",
+                  (int)L, (int)pos, (int)f.lazy, (int)f.computed, (int)f.store, (int)(f.buf != nullptr), (int)f.written_here, (int)rem(L));
     }
 
     // write local L (currently in acc or in a register) to its HBM buffer
@@ -231,6 +232,9 @@ struct Gen {
         if (L < 0) return;
         if (rem(L) > 0 && info[L].reg < 0) {
             if (!has_buf(L)) put_acc_in_reg();
+            // an operand of the instruction being built that cannot come back through the ring (its buffer is written by
+            // this kernel) must stay on chip, whatever it costs
+            else if ((L == pins[0] || L == pins[1] || L == pins[2]) && !reloadable(L)) put_acc_in_reg();
             // the value is already in HBM: a register copy pays only for a use that is near
             else if (next_use(L) - pos < 192 && free_reg_exists()) put_acc_in_reg();
         }

@@ -309,8 +309,8 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
                 switch (P.reduce_mode) {
                 case RM_SUM: part.s += x; break;
                 case RM_MOMENTS: values.push_back(x); break;
-                case RM_MIN: part.mn = part.c == 0 ? x : std::fmin(part.mn, x); if (x != x) part.mn = x; break;
-                case RM_MAX: part.mx = part.c == 0 ? x : std::fmax(part.mx, x); if (x != x) part.mx = x; break;
+                case RM_MIN: part.mn = part.c == 0 ? x : (double)jminf((float)part.mn, (float)x); break;      // NaN sticks, -0 < +0
+                case RM_MAX: part.mx = part.c == 0 ? x : (double)jmaxf((float)part.mx, (float)x); break;
                 case RM_DOT: if (!endb) bad("RM_DOT without a slot operand on T_END"); part.s += (double)endb[e] * x; break;
                 case RM_WSQ: { if (!endb) bad("RM_WSQ without a slot operand on T_END"); const double d = (double)endb[e] - P.reduce_param; part.s += d * d * x; break; }
                 default: bad("reduce mode %d unknown", P.reduce_mode);
@@ -438,8 +438,8 @@ cudaError_t launch_reduce(const ReduceParams& P, int, cudaStream_t) {
         switch (P.mode) {
         case RM_SUM: s += x; break;
         case RM_MOMENTS: vals.push_back(x); break;
-        case RM_MIN: mn = c == 0 ? x : std::fmin(mn, x); if (x != x) mn = x; break;
-        case RM_MAX: mx = c == 0 ? x : std::fmax(mx, x); if (x != x) mx = x; break;
+        case RM_MIN: mn = c == 0 ? x : (double)jminf((float)mn, (float)x); break;
+        case RM_MAX: mx = c == 0 ? x : (double)jmaxf((float)mx, (float)x); break;
         case RM_DOT: s += x * w; break;
         case RM_WSQ: s += (x - P.param) * (x - P.param) * w; break;
         default: return cudaErrorInvalidValue;
