@@ -154,8 +154,8 @@ def run_reference(args) -> None:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (an LMM Euler-step launch of tape_kernel<0> at
-# 1 Mi paths, 158 pointers), one `ncu --set full` capture: profiles/prof_micro_r1h.txt (337.2 MB read + 284.0 MB written)
-NCU_TRAFFIC_PER_LAUNCH = 621.2e6
+# 1 Mi paths, 158 pointers), one `ncu --set full` capture: profiles/prof_micro_r1k.txt (338.0 MB read + 285.0 MB written)
+NCU_TRAFFIC_PER_LAUNCH = 623.0e6
 
 
 def run_ours(args) -> None:
