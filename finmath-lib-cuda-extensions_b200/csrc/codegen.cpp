@@ -770,8 +770,9 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
     // Post-order (operands first, each value as late as its first consumer allows) keeps few intermediates alive at a
     // time: e.g. an Euler step whose caller computed all 80 drifts before applying any of them is emitted component
     // by component, so the register file holds a handful of values instead of 80.
-    std::vector<int32_t> cone;
-    std::vector<std::pair<int32_t, int>> stack;
+    // One pass over the nodes does everything that needs them: when a node is finished (all operands numbered) it gets
+    // its cone position, its operands' use counts go up, materialised operands are numbered in order of first use, and
+    // the node's words of the tape-cache key are written (see 1b).
     int64_t n = -1;
     for (int32_t t : targets) {
         const Node& nd = nodes[t];
@@ -785,6 +786,41 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
             return;
         }
     }
+    Gen g(*this, n);
+    constexpr int32_t LEAF_BASE = 0x40000000;            // Node::local of a leaf until the cone size is known: LEAF_BASE + ordinal
+    static thread_local std::vector<std::pair<int32_t, int>> stack;
+    static thread_local std::vector<int32_t> leaf_nodes, leaf_uses;
+    static thread_local std::vector<uint32_t> key;
+    static thread_local std::vector<uint32_t> int_refs;  // per cone position
+    stack.clear(); leaf_nodes.clear(); leaf_uses.clear(); key.clear(); int_refs.clear();
+    key.resize(6);
+    auto leaf_ordinal = [&](int32_t u) -> int32_t {
+        Node& nd = nodes[u];
+        if (nd.epoch != epoch) {
+            nd.epoch = epoch;
+            nd.local = LEAF_BASE + (int32_t)leaf_nodes.size();
+            leaf_nodes.push_back(u); leaf_uses.push_back(0);
+        }
+        return nd.local - LEAF_BASE;
+    };
+    auto finish = [&](int32_t v) {
+        Node& nd = nodes[v];
+        const int32_t L = (int32_t)g.info.size();
+        nd.local = L;
+        Info f; f.node = v; f.lazy = true;
+        g.info.push_back(f);
+        int_refs.push_back(nd.int_refs);
+        uint32_t w = (uint32_t)nd.op;
+        if (nd.ext_refs > 0) w |= 1u << 8;
+        uint32_t o[3];
+        for (int k = 0; k < 3; k++) {
+            const int32_t u = nd.in[k];
+            if (u < 0) { o[k] = 0xffffffffu; if (nd.imm[k] == 1.0f) w |= 1u << (11 + k); continue; }
+            if (nodes[u].state == NS_LAZY) { const int32_t lu = nodes[u].local; g.info[lu].uses++; o[k] = (uint32_t)lu; }
+            else { const int32_t j = leaf_ordinal(u); leaf_uses[(size_t)j]++; o[k] = 0x80000000u | (uint32_t)j; }
+        }
+        key.push_back(w); key.push_back(o[0]); key.push_back(o[1]); key.push_back(o[2]);
+    };
     for (int32_t t : targets) {
         if (nodes[t].state != NS_LAZY || nodes[t].epoch == epoch) continue;
         nodes[t].epoch = epoch;
@@ -797,46 +833,23 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
                 if (u >= 0 && nodes[u].state == NS_LAZY && nodes[u].epoch != epoch) { nodes[u].epoch = epoch; stack.emplace_back(u, 0); }
             } else {
                 stack.pop_back();
-                cone.push_back(v);
+                finish(v);
             }
         }
     }
-
-    Gen g(*this, n);
-    g.info.reserve(cone.size() * 2 + 4);
-    for (int32_t v : cone) {
-        nodes[v].local = (int32_t)g.info.size();
-        Info f; f.node = v; f.lazy = true;
-        g.info.push_back(f);
-    }
-    const int32_t n_cone = (int32_t)cone.size();
-    auto leaf_local = [&](int32_t u) -> int32_t {
-        Node& nd = nodes[u];
-        if (nd.epoch != epoch || nd.local < 0 || nd.local >= (int32_t)g.info.size() || g.info[nd.local].node != u) {
-            nd.epoch = epoch;
-            nd.local = (int32_t)g.info.size();
-            Info f; f.node = u; f.lazy = false; f.buf = nd.buf;
-            g.info.push_back(f);
-        }
-        return nd.local;
-    };
-    // uses
-    for (int32_t L = 0; L < n_cone; L++) {
-        const Node& nd = nodes[cone[L]];
-        for (int k = 0; k < 3; k++) {
-            const int32_t u = nd.in[k];
-            if (u < 0) continue;
-            const int32_t lu = (nodes[u].state == NS_LAZY) ? nodes[u].local : leaf_local(u);
-            g.info[lu].uses++;
-        }
-    }
+    const int32_t n_cone = (int32_t)g.info.size();
     const int32_t T = red ? targets[0] : -1;
-    int32_t weight_local = -1;
-    if (red && red->weight >= 0) { weight_local = leaf_local(red->weight); g.info[weight_local].uses++; }
-    int32_t target_local = -1;
+    int32_t weight_local = -1, target_local = -1;
+    if (red && red->weight >= 0) { const int32_t j = leaf_ordinal(red->weight); leaf_uses[(size_t)j]++; weight_local = n_cone + j; }
     if (red) {
-        target_local = (nodes[T].state == NS_LAZY) ? nodes[T].local : leaf_local(T);
-        g.info[target_local].uses++;   // the reduction epilogue reads it from acc
+        if (nodes[T].state == NS_LAZY) { target_local = nodes[T].local; g.info[target_local].uses++; }   // the reduction epilogue reads it from acc
+        else { const int32_t j = leaf_ordinal(T); leaf_uses[(size_t)j]++; target_local = n_cone + j; }
+    }
+    for (size_t j = 0; j < leaf_nodes.size(); j++) {
+        Node& nd = nodes[leaf_nodes[j]];
+        nd.local = n_cone + (int32_t)j;
+        Info f; f.node = leaf_nodes[j]; f.lazy = false; f.buf = nd.buf; f.uses = leaf_uses[j];
+        g.info.push_back(f);
     }
 
     // ---- 1b. tape cache: a cone with the same structure was lowered before -> replay its launches with this cone's
@@ -849,33 +862,22 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
     std::unique_ptr<ConePlan> fresh;
     uint64_t hash = 0;
     if (opt.tape_cache && n_cone > 0) {
-        std::vector<uint32_t> key;
-        key.reserve((size_t)n_cone * 5 + 8);
-        key.push_back((uint32_t)n); key.push_back((uint32_t)((uint64_t)n >> 32));
-        key.push_back(red ? (uint32_t)red->mode : 0u);
-        key.push_back((uint32_t)target_local); key.push_back((uint32_t)weight_local);
-        key.push_back((uint32_t)n_cone);
-        for (int32_t t : targets) if (nodes[t].state == NS_LAZY) g.info[nodes[t].local].written_here = true;   // scratch: target mark
+        key[0] = (uint32_t)n; key[1] = (uint32_t)((uint64_t)n >> 32);
+        key[2] = red ? (uint32_t)red->mode : 0u;
+        key[3] = (uint32_t)target_local; key[4] = (uint32_t)weight_local;
+        key[5] = (uint32_t)n_cone;
         for (int32_t L = 0; L < n_cone; L++) {
-            const Info& f = g.info[L];
-            const Node& nd = nodes[f.node];
-            const int32_t cone_uses = f.uses - ((red && L == target_local) ? 1 : 0);
-            uint32_t w = (uint32_t)nd.op;
-            if (nd.ext_refs > 0) w |= 1u << 8;
-            if ((int64_t)nd.int_refs > (int64_t)cone_uses) w |= 1u << 9;
-            if (f.written_here) w |= 1u << 10;
-            for (int k = 0; k < 3; k++) if (nd.in[k] < 0 && nd.imm[k] == 1.0f) w |= 1u << (11 + k);
-            key.push_back(w);
-            for (int k = 0; k < 3; k++) key.push_back(nd.in[k] < 0 ? 0xffffffffu : (uint32_t)nodes[nd.in[k]].local);
+            const int32_t cone_uses = g.info[L].uses - ((red && L == target_local) ? 1 : 0);
+            if ((int64_t)int_refs[(size_t)L] > (int64_t)cone_uses) key[6 + 4 * (size_t)L] |= 1u << 9;
         }
-        for (int32_t t : targets) if (nodes[t].state == NS_LAZY) g.info[nodes[t].local].written_here = false;
+        for (int32_t t : targets) if (nodes[t].state == NS_LAZY) key[6 + 4 * (size_t)nodes[t].local] |= 1u << 10;
         hash = 1469598103934665603ull;
         for (uint32_t w : key) { hash ^= w; hash *= 1099511628211ull; }
         auto it = g_cache.map.find(hash);
         if (it != g_cache.map.end())
             for (auto& cp : it->second) if (cp->key == key) { hit = cp.get(); break; }
         if (hit) g_cache.hits++;
-        else { g_cache.misses++; fresh.reset(new ConePlan); fresh->key.swap(key); g.keep_plans = true; }
+        else { g_cache.misses++; fresh.reset(new ConePlan); fresh->key = key; g.keep_plans = true; }
     }
     if (hit) {
         ph.reset(); ph.reset(new PhaseTimer(5));
@@ -924,7 +926,7 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
         g.use_list.assign((size_t)off, 0);
         auto add_use = [&](int32_t lu, int32_t at) { Info& f = g.info[lu]; g.use_list[(size_t)f.uend++] = at; };
         for (int32_t L = 0; L < n_cone; L++) {
-            const Node& nd = nodes[cone[L]];
+            const Node& nd = nodes[g.info[L].node];
             for (int k = 0; k < 3; k++) if (nd.in[k] >= 0) add_use(nodes[nd.in[k]].local, L);
         }
         if (weight_local >= 0) add_use(weight_local, n_cone);

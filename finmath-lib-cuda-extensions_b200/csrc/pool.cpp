@@ -37,7 +37,7 @@ void* DevicePool::carve(size_t rounded) {
             void* p = sl.base + sl.used;
             sl.used += rounded;
             sl.live++;
-            blocks_[p] = Block{rounded, (int)s, 0};
+            blocks_[p] = Block{rounded, (int)s};
             return p;
         }
     }
@@ -61,7 +61,7 @@ void* DevicePool::carve(size_t rounded) {
     for (size_t i = 0; i < slabs_.size(); i++) if (!slabs_[i].base) { s = (int)i; break; }
     if (s < 0) { slabs_.push_back(Slab{}); s = (int)slabs_.size() - 1; }
     slabs_[s] = Slab{(char*)base, slab_size, rounded, 1, dedicated};
-    blocks_[base] = Block{rounded, s, 0};
+    blocks_[base] = Block{rounded, s};
     return base;
 }
 
@@ -69,12 +69,13 @@ void* DevicePool::alloc(size_t bytes) {
     const size_t rounded = round_size(bytes);
     n_alloc++;
     void* p = nullptr;
-    auto it = free_.find(rounded);
-    if (it != free_.end() && !it->second.empty()) {
-        p = it->second.back();
-        it->second.pop_back();
+    std::vector<Cached>& v = list_for(rounded);
+    if (!v.empty()) {
+        const Cached c = v.back();
+        v.pop_back();
+        p = c.p;
         bytes_cached -= rounded;
-        slabs_[blocks_[p].slab].live++;
+        slabs_[c.slab].live++;
         n_reused++;
     } else {
         p = carve(rounded);
@@ -86,24 +87,20 @@ void* DevicePool::alloc(size_t bytes) {
 
 void* DevicePool::alloc_settled(size_t bytes, uint64_t settled_stamp, bool* settled) {
     const size_t rounded = round_size(bytes);
-    auto it = free_.find(rounded);
-    if (it != free_.end()) {
-        auto& v = it->second;                       // oldest frees sit at the front (free() appends, alloc() pops the back)
-        for (size_t i = 0; i < v.size() && i < 64; i++) {
-            void* p = v[i];
-            Block& b = blocks_[p];
-            if (b.stamp > settled_stamp) continue;
-            v.erase(v.begin() + (long)i);
-            n_alloc++; n_reused++;
-            bytes_cached -= rounded;
-            slabs_[b.slab].live++;
-            bytes_in_use += rounded;
-            high_water = std::max(high_water, bytes_in_use);
-            *settled = true;
-            return p;
-        }
+    std::vector<Cached>& v = list_for(rounded);     // oldest frees sit at the front (free() appends, alloc() pops the back)
+    for (size_t i = 0; i < v.size() && i < 64; i++) {
+        if (v[i].stamp > settled_stamp) continue;
+        const Cached c = v[i];
+        v.erase(v.begin() + (long)i);
+        n_alloc++; n_reused++;
+        bytes_cached -= rounded;
+        slabs_[c.slab].live++;
+        bytes_in_use += rounded;
+        high_water = std::max(high_water, bytes_in_use);
+        *settled = true;
+        return c.p;
     }
-    if (it == free_.end() || it->second.empty()) {   // nothing cached of this size: fresh memory, or the usual OOM ladder
+    if (v.empty()) {                                 // nothing cached of this size: fresh memory, or the usual OOM ladder
         *settled = true;
         n_alloc++;
         void* p = carve(rounded);
@@ -119,12 +116,11 @@ void DevicePool::free(void* p) {
     if (!p) return;
     auto it = blocks_.find(p);
     if (it == blocks_.end()) return;
-    it->second.stamp = ++free_stamp;
     const size_t rounded = it->second.size;
     slabs_[it->second.slab].live--;
     bytes_in_use -= rounded;
     bytes_cached += rounded;
-    free_[rounded].push_back(p);
+    list_for(rounded).push_back(Cached{p, it->second.slab, ++free_stamp});
 }
 
 void DevicePool::trim() {
@@ -135,11 +131,10 @@ void DevicePool::trim() {
         for (auto& kv : free_) {
             auto& v = kv.second;
             for (size_t i = 0; i < v.size();) {
-                auto b = blocks_.find(v[i]);
-                if (b != blocks_.end() && b->second.slab == (int)s) {
-                    bytes_cached -= b->second.size;
-                    blocks_.erase(b);
-                    v[i] = v.back(); v.pop_back();
+                if (v[i].slab == (int)s) {
+                    bytes_cached -= kv.first;
+                    blocks_.erase(v[i].p);
+                    v.erase(v.begin() + (long)i);            // keeps the oldest-first order
                 } else i++;
             }
         }

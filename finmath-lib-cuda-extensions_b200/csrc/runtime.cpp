@@ -113,7 +113,6 @@ int32_t Runtime::new_node() {
     const uint32_t gen = nd.gen;
     nd = Node{};
     nd.gen = gen;
-    nd.seq = next_seq++;
     return idx;
 }
 

@@ -50,10 +50,17 @@ public:
     uint64_t bytes_in_use = 0, bytes_cached = 0, bytes_reserved = 0, high_water = 0, n_alloc = 0, n_reused = 0;
 private:
     struct Slab { char* base; size_t size, used; int live; bool dedicated; };
-    struct Block { size_t size; int slab; uint64_t stamp; };
+    struct Block { size_t size; int slab; };
     std::vector<Slab> slabs_;
     std::unordered_map<void*, Block> blocks_;                  // live + cached blocks by address
-    std::unordered_map<size_t, std::vector<void*>> free_;      // rounded size -> cached blocks
+    struct Cached { void* p; int slab; uint64_t stamp; };     // what alloc() needs, so that reuse costs no map lookup
+    std::unordered_map<size_t, std::vector<Cached>> free_;     // rounded size -> cached blocks (oldest first)
+    size_t last_size_ = 0; std::vector<Cached>* last_list_ = nullptr;   // Monte-Carlo vectors all have one size
+    std::vector<Cached>& list_for(size_t rounded) {
+        if (last_list_ && last_size_ == rounded) return *last_list_;
+        last_list_ = &free_[rounded]; last_size_ = rounded;    // references into an unordered_map stay valid across rehashes
+        return *last_list_;
+    }
     static size_t round_size(size_t b);
     void* carve(size_t rounded);
 };
@@ -81,20 +88,20 @@ enum NodeOp : uint8_t {
 };
 enum NodeState : uint8_t { NS_FREE = 0, NS_LAZY = 1, NS_MAT = 2 };
 
-struct Node {
+struct alignas(64) Node {        // exactly one cache line: the cone walk of every flush touches each pending node
     uint8_t op = N_LEAF, state = NS_FREE;
     int32_t in[3] = {-1, -1, -1};
     float imm[3] = {0.f, 0.f, 0.f};
-    int64_t n = 0;
     uint32_t ext_refs = 0;      // handles held by the caller
     uint32_t int_refs = 0;      // operand slots of pending (lazy) nodes that reference this node
     uint32_t gen = 1;
-    uint64_t seq = 0;           // creation order == a topological order
-    float* buf = nullptr;       // device vector when NS_MAT
     // scratch used during one flush
     uint32_t epoch = 0;
     int32_t local = -1;
+    int64_t n = 0;
+    float* buf = nullptr;       // device vector when NS_MAT
 };
+static_assert(sizeof(Node) == 64, "Node is one cache line");
 
 struct Options {
     int64_t flush_threshold = 4096;
@@ -201,7 +208,6 @@ public:
     std::vector<Node> nodes;
     std::vector<int32_t> free_nodes;
     std::vector<int32_t> pending;       // lazy nodes in creation order (may contain stale entries)
-    uint64_t next_seq = 1;
     uint32_t epoch = 0;
     int64_t n_lazy = 0, n_live_handles = 0;
     Options opt;

@@ -77,19 +77,19 @@ struct PiecewiseConstantVolatility {
                 if (simGrid[s] + ttmGrid[m] <= maxMaturity) index[s][m] = k++;
         param.assign((size_t)k, value);
     }
-    static int bucket(const std::vector<double>& grid, double x) {
+    TimeDiscretization simDisc{simGrid}, ttmDisc{ttmGrid};    // the model's two TimeDiscretization members
+    static int bucket(const TimeDiscretization& td, double x) {
         // TimeDiscretization.getTimeIndex with the "-idx-1-1" fix-up of LIBORVolatilityModelPiecewiseConstant.getVolatility
-        TimeDiscretization td(grid);
         int i = td.getTimeIndex(x);
         if (i < 0) i = -i - 1 - 1;
         if (i < 0) i = 0;
-        if (i >= (int)grid.size()) i = (int)grid.size() - 1;
+        if (i >= td.getNumberOfTimes()) i = td.getNumberOfTimes() - 1;
         return i;
     }
     double volatility(double time, double maturity) const {
         const double ttm = maturity - time;
         if (ttm <= 0) return 0.0;
-        int s = bucket(simGrid, time), m = bucket(ttmGrid, ttm);
+        int s = bucket(simDisc, time), m = bucket(ttmDisc, ttm);
         while (m > 0 && index[(size_t)s][(size_t)m] < 0) m--;
         return param[(size_t)index[(size_t)s][(size_t)m]];
     }

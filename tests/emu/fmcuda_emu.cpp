@@ -347,6 +347,14 @@ void dump_tape(const TapeParams& P, int grid) {
 
 cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t) {
     if (std::getenv("FMC_EMU_DUMP")) dump_tape(P, grid);
+    static const bool noexec = std::getenv("FMC_EMU_NOEXEC") != nullptr;    // host-side profiling: launches cost nothing
+    if (noexec) {
+        if (P.reduce_mode != RM_NONE) {
+            P.result[0] = (double)P.n; P.result[1] = 0.0; P.result[2] = 0.0;
+            if (P.host_result) { P.host_result[0] = (double)P.n; P.host_result[1] = 0.0; P.host_result[2] = 0.0; P.host_result[3] = P.ticket; }
+        }
+        return cudaSuccess;
+    }
     try {
         if (P.n_ring < 0 || P.n_ring > TAPE_MAX_RING || P.n_slots < P.n_ring) bad("bad slot counts: ring %d slots %d", P.n_ring, P.n_slots);
         if (P.n_instr < 1 || P.n_instr > TAPE_MAX_INSTR + 1) bad("bad instruction count %d", P.n_instr);
