@@ -310,7 +310,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--paths", type=int, default=1 << 20, help="paths per GPU (north-star: 1M-path runs)")
-    ap.add_argument("--cpu-sample-paths", type=int, default=131072)
+    ap.add_argument("--cpu-sample-paths", type=int, default=393216)
     ap.add_argument("--ref-paths-per-thread", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--valuation-threads", type=int, default=1,
