@@ -384,6 +384,7 @@ static void set_option_locked(Runtime& rt, const char* key, double value) {
     if (!keep) tape_cache_clear();
     if (!std::strcmp(key, "flush_threshold")) rt.opt.flush_threshold = (int64_t)value;
     else if (!std::strcmp(key, "tape_cache")) rt.opt.tape_cache = value != 0.0;
+    else if (!std::strcmp(key, "max_regs")) rt.opt.max_regs = std::max(4, std::min((int)value, (int)TAPE_REGS));
     else if (!std::strcmp(key, "fuse")) { rt.opt.fuse = value != 0.0; if (rt.initialized) rt.flush_all(); }
     else if (!std::strcmp(key, "profile")) rt.opt.profile = value != 0.0;
     else if (!std::strcmp(key, "ring_max")) rt.opt.ring_max = std::max(1, std::min((int)value, (int)TAPE_MAX_RING));
@@ -424,6 +425,7 @@ int fmc_get_option(const char* key, double* value) {
         tape_cache_stats(&c_hits, &c_misses, &c_entries);
         if (!std::strcmp(key, "flush_threshold")) *value = (double)rt.opt.flush_threshold;
         else if (!std::strcmp(key, "tape_cache")) *value = rt.opt.tape_cache ? 1.0 : 0.0;
+        else if (!std::strcmp(key, "max_regs")) *value = rt.opt.max_regs;
         else if (!std::strcmp(key, "tape_cache_hits")) *value = (double)c_hits;
         else if (!std::strcmp(key, "tape_cache_misses")) *value = (double)c_misses;
         else if (!std::strcmp(key, "tape_cache_entries")) *value = (double)c_entries;

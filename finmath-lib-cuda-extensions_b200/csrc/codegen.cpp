@@ -200,10 +200,11 @@ struct Gen {
     // has an HBM copy is simply dropped, any other is stored first. Either way it cannot be read back through the TMA
     // ring inside this kernel (its buffer is written here), so its next use ends the kernel (see emit loop).
     int alloc_reg() {
-        for (int j = 0; j < TAPE_REGS; j++) if (reg_owner[j] < 0) { regs_used = std::max(regs_used, j + 1); return j; }
+        const int n_regs = std::max(4, std::min(rt.opt.max_regs, TAPE_REGS));
+        for (int j = 0; j < n_regs; j++) if (reg_owner[j] < 0) { regs_used = std::max(regs_used, j + 1); return j; }
         int victim = -1, victim_buf = -1;
         int32_t far = -1, far_buf = -1;
-        for (int j = 0; j < TAPE_REGS; j++) {
+        for (int j = 0; j < n_regs; j++) {
             const int32_t L = reg_owner[j];
             if (L == pins[0] || L == pins[1] || L == pins[2]) continue;
             const int32_t nu = next_use(L);
@@ -224,7 +225,11 @@ struct Gen {
         emit(T_STR, K_REG, j);
         reg_owner[j] = L; info[L].reg = (int8_t)j;
     }
-    bool free_reg_exists() const { for (int j = 0; j < TAPE_REGS; j++) if (reg_owner[j] < 0) return true; return false; }
+    bool free_reg_exists() const {
+        const int n_regs = std::max(4, std::min(rt.opt.max_regs, TAPE_REGS));
+        for (int j = 0; j < n_regs; j++) if (reg_owner[j] < 0) return true;
+        return false;
+    }
 
     // the accumulator is about to be overwritten: keep its value if somebody still needs it
     void save_acc() {

@@ -120,6 +120,8 @@ struct Options {
     int cta_warps = 4;              // warps per interpreter CTA (2 or 4)
     bool fuse_ops = true;           // peephole fusion of the abstract code (MULADD_II, ACCUM_S, ADDPROD)
     int grid_limit = 0;             // > 0: cap the interpreter grid (tests: many chunks per warp at small sizes)
+    int max_regs = 8;               // register-file slots the code generator may use, <= TAPE_REGS. Measured on the LMM step: 16 slots
+                                    // let a few kernels drop to one CTA per SM (8.36 ms simulation); 8: 8.14 ms, 4: 8.00 ms but more spills
     bool tape_cache = true;         // replay the launches of a cone whose structure was lowered before (codegen.cpp)
 };
 

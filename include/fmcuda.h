@@ -129,7 +129,7 @@ int fmc_sync(void);                     /* flush + wait for the device (cuCtxSyn
  *          "fuse" (1 default; 0 = execute every op as its own kernel, the reference's execution model),
  *          "profile" (0 default; see fmc_profile_read);
  *          interpreter scheduling knobs (tuning / tests; defaults in csrc/runtime.h): "ring_max", "ring_min", "target_ctas",
- *          "horizon", "pipeline", "max_sets", "grid_limit", "fuse_ops", "cta_warps", "zero_copy_reduce", "leaf_reduce_kernel",
+ *          "horizon", "pipeline", "max_sets", "max_regs", "grid_limit", "fuse_ops", "cta_warps", "zero_copy_reduce", "leaf_reduce_kernel",
  *          "p2p_reduce" (1 default: sharded runs exchange reduction partials inside the kernel over NVLink peer memory; 0: NCCL);
  *          "tape_cache" (1 default: a cone of pending nodes whose structure was lowered before is replayed with the new
  *          buffers and immediates patched in instead of being code-generated again);

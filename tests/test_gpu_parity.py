@@ -283,7 +283,7 @@ def test_long_tape_register_pressure_and_cuts(fc, O, data):
     assert bits_equal(c.getRealizationsFloat(), co)
 
 
-SCHED_DEFAULTS = {"ring_max": 16, "ring_min": 2, "target_ctas": 4, "horizon": 96, "pipeline": 1, "max_sets": 1, "grid_limit": 0}
+SCHED_DEFAULTS = {"ring_max": 16, "ring_min": 2, "target_ctas": 4, "horizon": 96, "pipeline": 1, "max_sets": 1, "grid_limit": 0, "max_regs": 8}
 
 
 @pytest.mark.parametrize("opts", [
@@ -577,7 +577,8 @@ def test_fuzzed_programs_match_the_oracle(fc, O):
     (tests/test_codegen_emulator.py) they are in."""
     import os
     emulated = bool(os.environ.get("FMC_TEST_TAPE_EMULATOR"))
-    knobs = [{}, {"ring_max": 2, "ring_min": 1}, {"grid_limit": 1}, {"grid_limit": 2, "max_sets": 2}, {"pipeline": 0}, {"horizon": 4}, {"target_ctas": 1}]
+    knobs = [{}, {"ring_max": 2, "ring_min": 1}, {"grid_limit": 1}, {"grid_limit": 2, "max_sets": 2}, {"pipeline": 0}, {"horizon": 4}, {"target_ctas": 1},
+             {"max_regs": 4}, {"max_regs": 16}]
     try:
         for opts in knobs:
             for k_, v_ in SCHED_DEFAULTS.items(): fc.set_option(k_, v_)
