@@ -50,6 +50,19 @@ checks = {
         min(max(int(math.floor((n + 1) * 0.1 - 0.5)), 0), n - 1):min(max(int(math.floor((n + 1) * 0.9 - 0.5)), 0), n - 1) + 1].mean())),
     "histogram[2]": (float(X.getHistogram(np.array([-1.0, 0.0, 1.0]))[2]), float(((x > 0.0) & (x <= 1.0)).sum()) / n),
 }
+# conditional-expectation regression on the sharded vectors: normal equations all-reduced, coefficients solved on every rank
+from finmath_cuda.conditional_expectation import MonteCarloConditionalExpectationRegression, normal_equations  # noqa: E402
+one = fc.RandomVariableCuda(0.0, 1.0)
+basis = [one, X, X.squared(), Y]
+XtX, XtY = normal_equations(basis, Z)
+xd, yd, zd = x.astype(np.float64), y.astype(np.float64), z.astype(np.float64)
+B = np.stack([np.ones(n), xd, (x * x).astype(np.float64), yd])
+checks["regression XtX[1][2]"] = (float(XtX[1, 2]), float((B[1] * B[2]).mean()))
+checks["regression XtX[3][3]"] = (float(XtX[3, 3]), float((B[3] * B[3]).mean()))
+checks["regression XtY[3]"] = (float(XtY[3]), float((B[3] * zd).mean()))
+coef = MonteCarloConditionalExpectationRegression(basis).getLinearRegressionParameters(Z)
+want_coef = np.linalg.lstsq((B @ B.T) / n, (B @ zd) / n, rcond=1e-10)[0]
+checks["regression coefficient[3]"] = (float(coef[3]), float(want_coef[3]))
 ok = True
 for name, (got, want) in checks.items():
     good = abs(got - want) <= 1e-5 * max(abs(want), 1e-12)

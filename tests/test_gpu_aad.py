@@ -102,3 +102,55 @@ def test_black_scholes_delta_and_vega_by_aad_on_the_gpu(fc):
     assert abs(delta - (price_plain(S0 + h, sigma) - price_plain(S0 - h, sigma)) / (2 * h)) < 2e-3
     assert abs(vega - (price_plain(S0, sigma + h) - price_plain(S0, sigma - h)) / (2 * h)) < 3e-3
     assert kernels < 40, f"primal + adjoint sweep should fuse into a few launches, used {kernels}"
+
+
+def test_lmm_swaption_vega_by_aad_on_the_gpu(fc):
+    """BASELINE config 4, LMM half: a small LIBOR market model (spot measure, normal state space, one factor, as
+    drivers/workloads.hpp) simulated on RandomVariableDifferentiableAAD over the GPU type; the derivative of a swaption
+    value with respect to the (flat) volatility parameter by one reverse sweep must equal bump-and-revalue on the same
+    Brownian paths, and the sweep must stay a handful of fused launches."""
+    n, NP, delta = 60_000, 8, 0.5
+    L0, strike, sigma0 = 0.02, 0.02, 0.006
+    td = fc.TimeDiscretization(0.0, NP, delta)
+    bm = fc.BrownianMotionCuda(td, 1, n, 31415)
+    plain = fc.RandomVariableCudaFactory()
+
+    def swaption_value(sig):
+        libor = [plain.createRandomVariable(0.0, L0) for _ in range(NP)]
+        numeraire = [plain.createRandomVariable(0.0, 1.0)]
+        exercise = NP // 2
+        at_exercise = None
+        for t in range(NP):
+            if t == exercise: at_exercise = list(libor)
+            numeraire.append(numeraire[-1].accrue(libor[t], delta))                    # N(T_{t+1}) = N(T_t) (1 + L_t(T_t) delta)
+            dW = bm.getBrownianIncrement(t, 0)
+            factor_sum = None
+            new = list(libor)
+            for i in range(t + 1, NP):
+                transform = sig.mult(libor[i].mult(delta).add(1.0).invert().mult(delta))   # sigma * delta / (1 + delta L_i)
+                factor_sum = transform if factor_sum is None else factor_sum.add(transform)
+                drift = factor_sum.mult(sig)
+                new[i] = libor[i].add(drift.mult(delta)).add(sig.mult(dW))
+            libor = new
+        value = None
+        for i in range(NP - 1, exercise - 1, -1):                                      # Swaption.getValue backward recursion
+            payoff = at_exercise[i].sub(strike).mult(delta)
+            value = payoff if value is None else value.add(payoff)
+            value = value.discount(at_exercise[i], delta)
+        return value.floor(0.0).div(numeraire[exercise]).average()
+
+    fac = fc.RandomVariableDifferentiableAADFactory(plain)
+    sig = fac.createRandomVariable(0.0, sigma0)
+    k0 = fc.stats()["n_tape_kernels"]
+    V = swaption_value(sig)
+    vega = V.getGradient()[sig.getID()].getAverage()
+    kernels = fc.stats()["n_tape_kernels"] - k0
+    h = 1e-5
+    up = swaption_value(fc.RandomVariableDifferentiableAAD(plain.createRandomVariable(0.0, sigma0 + h))).doubleValue()
+    dn = swaption_value(fc.RandomVariableDifferentiableAAD(plain.createRandomVariable(0.0, sigma0 - h))).doubleValue()
+    fd = (up - dn) / (2 * h)
+    assert V.doubleValue() > 0 and vega > 0
+    assert abs(vega - fd) <= 2e-3 * abs(fd), (vega, fd)
+    # Bachelier: value = annuity * sigma * sqrt(T / 2 pi) for the ATM option -> vega ~ value / sigma
+    assert abs(vega - V.doubleValue() / sigma0) <= 0.15 * vega
+    assert kernels < 60, f"primal + adjoint sweep should fuse into few launches, used {kernels}"
