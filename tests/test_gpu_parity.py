@@ -657,3 +657,54 @@ def test_uploads_on_the_copy_stream_do_not_overtake_queued_kernels(fc, O):
             results.append(z)
         for z, w in zip(results, want):
             assert bits_equal(z.getRealizationsFloat(), O.op_vs(O.ADD, w, 0.0)), round_
+
+
+def test_fuzzed_statistics_regression_and_brownian(fc, O):
+    """Randomised sizes and parameters for the kernels next to the interpreter: radix-select order statistics (ties,
+    signed zeros, infinities), histogram, the fused regression normal equations (k = 1..12 with deterministic columns)
+    and Brownian path slices with random (T, F, n, p0, p1, seed)."""
+    from finmath_cuda.conditional_expectation import normal_equations
+    rng = np.random.default_rng(2024)
+    for case in range(40):
+        n = int(rng.choice([1, 2, 31, 255, 256, 257, 1023, 4097, 65537, 300_001]))
+        kind = case % 4
+        if kind == 0: x = rng.standard_normal(n)
+        elif kind == 1: x = np.round(rng.standard_normal(n) * 2.0) / 2.0              # ties
+        elif kind == 2: x = np.where(rng.random(n) < 0.3, 0.0, rng.standard_normal(n)) * np.where(rng.random(n) < 0.5, -1.0, 1.0)   # +-0
+        else: x = np.concatenate([rng.standard_normal(max(n - 2, 0)), [np.inf, -np.inf][: min(n, 2)]])[:n]
+        x = x.astype(np.float32)
+        X = fc.RandomVariableCuda(0.0, x)
+        for q in list(rng.random(3)) + [0.0, 1.0]:
+            got, want = X.getQuantile(float(q)), O.quantile(x, float(q))
+            assert got == want, (case, n, q, got, want)
+        q0, q1 = sorted(rng.random(2))
+        got, want = X.getQuantileExpectation(float(q0), float(q1)), O.quantile_expectation(x, float(q0), float(q1))
+        assert (got != got and want != want) or got == want or abs(got - want) <= 1e-12 * max(1.0, abs(want)), (case, n, q0, q1, got, want)
+        pts = np.sort(rng.standard_normal(int(rng.integers(1, 9))))
+        assert np.array_equal(X.getHistogram(pts), O.histogram(x, pts)), (case, n)
+    for case in range(12):
+        n = int(rng.choice([7, 513, 5000, 100_003]))
+        k = int(rng.integers(1, 13))
+        cols = [rng.uniform(-1.0, 1.0, n).astype(np.float32) for _ in range(k)]
+        det = [bool(rng.random() < 0.2) for _ in range(k)]
+        y = rng.uniform(-1.0, 1.0, n).astype(np.float32)
+        basis = [fc.RandomVariableCuda(0.0, float(c[0])) if d else fc.RandomVariableCuda(0.0, c.astype(np.float64)) for c, d in zip(cols, det)]
+        basis_o = [float(np.float64(c[0])) if d else c for c, d in zip(cols, det)]
+        XtX, XtY = normal_equations(basis, fc.RandomVariableCuda(0.0, y.astype(np.float64)))
+        XtX_o, XtY_o = O.regression_normal_eq(basis_o, y)
+        assert np.allclose(XtX, XtX_o, rtol=1e-9, atol=1e-13), (case, n, k, det)
+        assert np.allclose(XtY, XtY_o, rtol=1e-9, atol=1e-13), (case, n, k, det)
+    for case in range(10):
+        T, F = int(rng.integers(1, 30)), int(rng.integers(1, 5))
+        n = int(rng.choice([1, 33, 1000, 20_011]))
+        p0 = int(rng.integers(0, n)); p1 = int(rng.integers(p0, n + 1))
+        seed, mode = int(rng.integers(1, 2**31 - 1)), int(rng.integers(0, 2))
+        dt = float(rng.choice([0.1, 0.25, 1.0]))
+        td = fc.TimeDiscretization(0.0, T, dt)
+        sqrt_dt = np.array([math.sqrt(td.getTimeStep(t)) for t in range(T)])
+        bm = fc.BrownianMotionCuda(td, F, n, seed, seedMode=mode, pathRange=(p0, p1))
+        want = O.brownian(seed, T, F, n, sqrt_dt, mode, p0, p1)
+        for t in {0, T // 2, T - 1}:
+            for f in range(F):
+                got = bm.getBrownianIncrement(t, f).getRealizationsFloat() if p1 > p0 else np.empty(0, dtype=np.float32)
+                assert bits_equal(got, want[t * F + f]), (case, T, F, n, p0, p1, seed, mode, t, f)
