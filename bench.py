@@ -154,7 +154,7 @@ def run_reference(args) -> None:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (an LMM Euler-step launch of tape_kernel<0> at
-# 1 Mi paths, 158 pointers), one `ncu --set full` capture: profiles/prof_micro_r1k.txt (338.0 MB read + 285.0 MB written)
+# 1 Mi paths, 158 pointers), one `ncu --set full` capture: profiles/prof_micro_r1m.txt (338.0 MB read + 285.1 MB written)
 NCU_TRAFFIC_PER_LAUNCH = 623.0e6
 
 
