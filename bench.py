@@ -138,6 +138,14 @@ def run_reference(args) -> None:
         step()
     dt = time.perf_counter() - t0
     value = total * N_PERIODS * args.steps / dt
+    # the same sample on finmath-lib's default CPU type, RandomVariableFromDoubleArray (north star: "DoubleArray/FloatArray path")
+    from oracle.workloads_oracle import driver_f64
+    lib64 = driver_f64()
+    models64 = [lib64.lmm(total, N_PERIODS, DELTA, 1, SEED, 0, (i * paths_per_thread, (i + 1) * paths_per_thread)) for i in range(cores)]
+    list(pool.map(lambda m: m.step(), models64))
+    t0 = time.perf_counter()
+    list(pool.map(lambda m: m.step(), models64))
+    value64 = total * N_PERIODS / (time.perf_counter() - t0)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -147,6 +155,8 @@ def run_reference(args) -> None:
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{total} paths ({paths_per_thread} per thread x {cores} threads), {args.steps} steps; C++ restatement of "
                                    "RandomVariableFromFloatArray (no JVM in this environment)"},
+        "cpu_double_array": {"value": value64, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{total} paths, 1 step; C++ restatement of finmath-lib's RandomVariableFromDoubleArray (not part of the ratio)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

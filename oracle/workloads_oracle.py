@@ -13,5 +13,14 @@ from finmath_cuda.workloads import DriverLib  # noqa: E402  (generic ctypes bind
 ORACLE_DRIVER_LIB = os.path.join(_HERE, "libfmdrivers_oracle.so")
 
 
+ORACLE_F64_DRIVER_LIB = os.path.join(_HERE, "libfmdrivers_oracle_f64.so")
+
+
 def driver() -> DriverLib:
+    """Drivers on the RandomVariableFromFloatArray twin (the parity oracle)."""
     return DriverLib(ORACLE_DRIVER_LIB)
+
+
+def driver_f64() -> DriverLib:
+    """Drivers on the RandomVariableFromDoubleArray twin (finmath-lib's default CPU type; timing baseline only)."""
+    return DriverLib(ORACLE_F64_DRIVER_LIB)

@@ -154,3 +154,18 @@ def test_workload_drivers_on_oracle_backend():
     iv = m.implied_vols(vals)
     assert np.all(np.isfinite(vals)) and np.all(vals > 0) and np.all(np.abs(iv - 0.005) < 0.002)
     assert m.bermudan(10, 30, 2, 40, 0.02) > 0
+
+
+def test_double_array_twin_agrees_with_the_float_twin():
+    """oracle/RandomVariableFromDoubleArray.hpp (finmath-lib's default CPU type, CPU timing baseline only) runs the same
+    drivers; with every intermediate in double it must agree with the float twin to float accuracy."""
+    from oracle.workloads_oracle import driver, driver_f64
+    f32, f64 = driver(), driver_f64()
+    (v32, a32), (v64, a64) = f32.bs_call(100_000), f64.bs_call(100_000)
+    assert a32 == a64 and abs(v32 - v64) < 1e-6 * abs(v64)
+    m32, m64 = f32.lmm(2000), f64.lmm(2000)
+    s32, s64 = m32.step(), m64.step()
+    assert np.allclose(s32, s64, rtol=2e-4, atol=1e-9)
+    m32.simulate(); m64.simulate()
+    b32, b64 = m32.bermudan(10, 30, 2, 40, 0.02), m64.bermudan(10, 30, 2, 40, 0.02)
+    assert abs(b32 - b64) < 5e-3 * abs(b64)         # exercise decisions of a few paths flip between float and double
