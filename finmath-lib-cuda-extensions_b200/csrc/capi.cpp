@@ -94,6 +94,11 @@ int fmc_device_info(char* name, size_t name_len, int* sm_count, uint64_t* total_
 int fmc_vec_from_f64(const double* host, int64_t n, fmc_vec* out) {
     return guarded([&](Runtime& rt) { rt.require_init(); *out = rt.handle_of(rt.upload_f64(host, n)); });
 }
+int fmc_host_alloc(size_t bytes, void** out) { return guarded([&](Runtime& rt) { rt.require_init(); *out = rt.host_alloc(bytes); }); }
+int fmc_host_free(void* p) { return guarded([&](Runtime& rt) { rt.require_init(); rt.host_free(p); }); }
+int fmc_vec_from_f64_pinned(const double* pinned_host, int64_t n, fmc_vec* out) {
+    return guarded([&](Runtime& rt) { rt.require_init(); *out = rt.handle_of(rt.upload_f64_pinned(pinned_host, n)); });
+}
 int fmc_vec_from_f32(const float* host, int64_t n, fmc_vec* out) {
     return guarded([&](Runtime& rt) { rt.require_init(); *out = rt.handle_of(rt.upload_f32(host, n)); });
 }

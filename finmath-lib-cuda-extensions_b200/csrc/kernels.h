@@ -29,6 +29,8 @@ struct ReduceParams {
     Exchange xchg;            // peer tables of a path-sharded run (reduce_common.cuh)
 };
 cudaError_t launch_reduce(const ReduceParams& P, int grid, cudaStream_t stream);
+// dst[i] = (float)src[i]; both device pointers, 8-byte aligned (dst offsets of the upload path are multiples of the chunk size)
+cudaError_t launch_cast_f64_f32(const double* src, float* dst, long long n, int sm_count, cudaStream_t stream);
 int reduce_tile_elems();
 
 // order_kernel.cu — radix select / range statistics / histogram (order statistics without a sort)

@@ -10,6 +10,7 @@
 //
 // Bound: HBM. Algorithmic bytes: 4 per element (8 for the weighted modes).
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <math.h>
 
 #include "kernels.h"
@@ -146,5 +147,28 @@ cudaError_t launch_reduce(const ReduceParams& P, int grid, cudaStream_t stream) 
     return cudaGetLastError();
 }
 int reduce_tile_elems() { return RTILE; }
+
+// ---- (float) cast of an uploaded double chunk (asynchronous pinned upload path, runtime.cpp: upload_pinned) ----
+// cvt.rn.f32.f64 rounds to nearest even like Java's (float) cast (RandomVariableCuda.java:768-774).
+namespace {
+__global__ void __launch_bounds__(256) cast_f64_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, long long n)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x * 2;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += stride) {
+        if (i + 1 < n) {
+            const double2 v = *reinterpret_cast<const double2*>(src + i);
+            *reinterpret_cast<float2*>(dst + i) = make_float2(__double2float_rn(v.x), __double2float_rn(v.y));
+        } else dst[i] = __double2float_rn(src[i]);
+    }
+}
+}  // namespace
+
+cudaError_t launch_cast_f64_f32(const double* src, float* dst, long long n, int sm_count, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const long long blocks = (n / 2 + 255) / 256;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(blocks, (long long)sm_count * 8));
+    cast_f64_f32_kernel<<<grid, 256, 0, stream>>>(src, dst, n);
+    return cudaGetLastError();
+}
 
 }  // namespace fmc

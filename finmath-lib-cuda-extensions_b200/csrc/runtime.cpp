@@ -80,6 +80,9 @@ void Runtime::shutdown() {
     staging.release();
     tape_kernel_teardown();
     tape_cache_clear();
+    if (d_upload) { cudaFree(d_upload); d_upload = nullptr; }
+    for (auto& kv : pinned_) cudaFreeHost((void*)kv.first);
+    pinned_.clear();
     cudaFree(d_partials); cudaFree(d_counter); cudaFree(d_result); cudaFreeHost(h_result); cudaFreeHost(h_ticket);
     d_partials = nullptr; d_counter = nullptr; d_result = nullptr; h_result = nullptr; h_ticket = nullptr; h_ticket_dev = nullptr;
     for (auto& pe : prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
@@ -392,6 +395,72 @@ static int32_t upload_impl(Runtime& rt, const T* h, int64_t n) {
     return idx;
 }
 int32_t Runtime::upload_f64(const double* h, int64_t n) { return upload_impl(*this, h, n); }
+
+void* Runtime::host_alloc(size_t bytes) {
+    void* p = nullptr;
+    FMC_CUDA(cudaMallocHost(&p, std::max<size_t>(bytes, 1)));
+    pinned_[(const char*)p] = bytes;
+    return p;
+}
+void Runtime::host_free(void* p) {
+    auto it = pinned_.find((const char*)p);
+    if (it == pinned_.end()) fail(FMC_ERR_INVALID, "fmc_host_free: not an fmc_host_alloc pointer");
+    FMC_CUDA(cudaStreamSynchronize(copy_stream));        // a DMA out of it may still be in flight
+    pinned_.erase(it);
+    FMC_CUDA(cudaFreeHost(p));
+}
+bool Runtime::is_pinned(const void* p, size_t bytes) const {
+    auto it = pinned_.upper_bound((const char*)p);
+    if (it == pinned_.begin()) return false;
+    --it;
+    return (const char*)p >= it->first && (const char*)p + bytes <= it->first + it->second;
+}
+
+int32_t Runtime::upload_f64_pinned(const double* h, int64_t n) {
+    if (n < 0) fail(FMC_ERR_INVALID, "negative vector size %lld", (long long)n);
+    if (n > 0 && !is_pinned(h, sizeof(double) * (size_t)n)) fail(FMC_ERR_INVALID, "fmc_vec_from_f64_pinned: the buffer does not come from fmc_host_alloc");
+    struct Timer {
+        double& acc; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        explicit Timer(double& a) : acc(a) {}
+        ~Timer() { acc += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); }
+    } timer(hostprof.upload);
+    if (!d_upload) FMC_CUDA(cudaMalloc(&d_upload, sizeof(double) * kUploadChunk * STAGING_SLOTS));
+    { const uint64_t stamp = pool.free_stamp; if (cudaStreamQuery(stream) == cudaSuccess) settled_stamp = std::max(settled_stamp, stamp); else cudaGetLastError(); }
+    bool settled = true;
+    float* dst = (float*)pool.alloc_settled(sizeof(float) * (size_t)std::max<int64_t>(n, 1), settled_stamp, &settled);
+    int32_t idx;
+    try { idx = new_node(); } catch (...) { pool.free(dst); throw; }
+    {
+        Node& nd = nodes[idx];
+        nd.op = N_LEAF; nd.state = NS_MAT; nd.n = n; nd.ext_refs = 1; nd.buf = dst;
+        n_live_handles++;
+    }
+    try {
+        if (!settled) {
+            FMC_CUDA(cudaEventRecord(ev_order, stream));
+            FMC_CUDA(cudaStreamWaitEvent(copy_stream, ev_order, 0));
+        }
+        int last = -1;
+        for (int64_t off = 0; off < n; off += (int64_t)kUploadChunk) {
+            const int64_t m = std::min<int64_t>(kUploadChunk, n - off);
+            const int which = staging_next; staging_next = (staging_next + 1) % STAGING_SLOTS;
+            if (staging_busy[which]) { Timer tw(hostprof.upload_wait); FMC_CUDA(cudaEventSynchronize(ev_copy[which])); staging_busy[which] = false; }
+            double* chunk = d_upload + (size_t)which * kUploadChunk;
+            FMC_CUDA(cudaMemcpyAsync(chunk, h + off, sizeof(double) * (size_t)m, cudaMemcpyHostToDevice, copy_stream));
+            FMC_CUDA(launch_cast_f64_f32(chunk, dst + off, m, sm_count, copy_stream));
+            FMC_CUDA(cudaEventRecord(ev_copy[which], copy_stream));
+            staging_busy[which] = true;
+            last = which;
+        }
+        if (last >= 0) FMC_CUDA(cudaStreamWaitEvent(stream, ev_copy[last], 0));
+    } catch (...) {
+        release_ext(idx);
+        throw;
+    }
+    stats.h2d += sizeof(double) * (uint64_t)n;
+    stats.n_kernels++;
+    return idx;
+}
 int32_t Runtime::upload_f32(const float* h, int64_t n) { return upload_impl(*this, h, n); }
 
 void Runtime::staging_quiesce() {

@@ -249,6 +249,14 @@ public:
     // host copies
     int32_t upload_f64(const double* h, int64_t n);
     int32_t upload_f32(const float* h, int64_t n);
+    // asynchronous upload from pinned host memory (fmc_host_alloc): DMA of the doubles on the copy stream into a ring of device
+    // chunks, (float) cast on the device. The host buffer is read AFTER the call returns.
+    int32_t upload_f64_pinned(const double* h, int64_t n);
+    void* host_alloc(size_t bytes);
+    void host_free(void* p);
+    bool is_pinned(const void* p, size_t bytes) const;
+    std::map<const char*, size_t> pinned_;               // base -> size of the fmc_host_alloc allocations
+    double* d_upload = nullptr;                           // STAGING_SLOTS chunks of doubles on the device
     void download_f32(int32_t idx, float* h, int64_t n);
     void download_f64(int32_t idx, double* h, int64_t n);
 

@@ -71,12 +71,36 @@ public:
                 local_n_ = (int64_t)host_[(size_t)t * factors_ + f].size();
             }
         inc_.resize(host_.size());
+#if defined(FMD_BACKEND_CUDA)
+        // a second copy of the same doubles in pinned memory, for the asynchronous upload (fmc_vec_from_f64_pinned)
+        const size_t bytes = sizeof(double) * (size_t)local_n_ * host_.size();
+        void* p = nullptr;
+        fmc_check(fmc_host_alloc(bytes, &p));
+        pinned_ = static_cast<double*>(p);
+        for (size_t k = 0; k < host_.size(); k++) std::memcpy(pinned_ + k * (size_t)local_n_, host_[k].data(), sizeof(double) * (size_t)local_n_);
+#endif
+    }
+    ~HostArrayBrownianMotion() override {
+#if defined(FMD_BACKEND_CUDA)
+        inc_.clear();
+        if (pinned_) fmc_host_free(pinned_);
+#endif
     }
     void reset() { for (auto& r : inc_) r.reset(); }
+    void use_pinned(bool on) { use_pinned_ = on; }
     uint64_t host_bytes() const { return (uint64_t)host_.size() * (uint64_t)local_n_ * sizeof(double); }
     RV getBrownianIncrement(int t, int f) override {
         RV& r = inc_[(size_t)t * factors_ + f];
-        if (!r) r = factory_->createRandomVariable(td_.getTime(t + 1), host_[(size_t)t * factors_ + f].data(), local_n_);
+        if (!r) {
+#if defined(FMD_BACKEND_CUDA)
+            if (use_pinned_) {
+                r = static_cast<const RandomVariableCudaFactory&>(*factory_).createRandomVariableFromPinned(
+                        td_.getTime(t + 1), pinned_ + ((size_t)t * factors_ + f) * (size_t)local_n_, local_n_);
+                return r;
+            }
+#endif
+            r = factory_->createRandomVariable(td_.getTime(t + 1), host_[(size_t)t * factors_ + f].data(), local_n_);
+        }
         return r;
     }
     const TimeDiscretization& getTimeDiscretization() const override { return td_; }
@@ -89,6 +113,8 @@ private:
     FactoryPtr factory_;
     std::vector<std::vector<double>> host_;
     std::vector<RV> inc_;
+    double* pinned_ = nullptr;
+    bool use_pinned_ = false;
 };
 
 struct LmmHandle {
@@ -186,6 +212,7 @@ int fmd_lmm_step(void* handle, const double* vol_params, int from_host, double* 
             if (!h->host_brownian) throw std::runtime_error("call fmd_lmm_prepare_host_brownian first");
             h->last_model.reset();                 // drop the previous simulation before its inputs
             h->host_brownian->reset();
+            h->host_brownian->use_pinned(from_host == 2);   // 1: pageable double[] (the reference API); 2: pinned, asynchronous
             bm = h->host_brownian;
         }
         h->last_model.reset(new LIBORMarketModel(h->factory, bm, h->L0, h->vol));

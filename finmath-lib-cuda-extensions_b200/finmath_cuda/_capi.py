@@ -48,6 +48,9 @@ PROTOTYPES = {
     "fmc_device_info": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "fmc_vec_from_f64": (C.c_int, [C.c_void_p, C.c_int64, _vecp]),
     "fmc_vec_from_f32": (C.c_int, [C.c_void_p, C.c_int64, _vecp]),
+    "fmc_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "fmc_host_free": (C.c_int, [C.c_void_p]),
+    "fmc_vec_from_f64_pinned": (C.c_int, [C.c_void_p, C.c_int64, _vecp]),
     "fmc_vec_fill": (C.c_int, [C.c_double, C.c_int64, _vecp]),
     "fmc_vec_alloc": (C.c_int, [C.c_int64, _vecp]),
     "fmc_vec_retain": (C.c_int, [_vec]),

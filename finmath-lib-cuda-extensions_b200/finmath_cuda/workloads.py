@@ -104,14 +104,16 @@ class Lmm:
         self.lib.check(self.lib.L.fmd_lmm_prepare_host_brownian(self.h, C.byref(b)))
         return b.value
 
-    def step(self, vol_params=None, from_host: bool = False) -> np.ndarray:
-        """One simulation (n_periods Euler steps) + valuation of all calibration swaptions. Returns their values."""
+    def step(self, vol_params=None, from_host=False) -> np.ndarray:
+        """One simulation (n_periods Euler steps) + valuation of all calibration swaptions. Returns their values.
+        from_host: False / 0 device-resident increments; True / 1 uploaded from pageable host doubles; 2 from pinned host
+        doubles, asynchronously (fmc_vec_from_f64_pinned)."""
         out = np.empty(self.n_products)
         p = None
         if vol_params is not None:
             vp_ = np.ascontiguousarray(vol_params, dtype=np.float64)
             p = vp_.ctypes.data
-        self.lib.check(self.lib.L.fmd_lmm_step(self.h, p, 1 if from_host else 0, out.ctypes.data))
+        self.lib.check(self.lib.L.fmd_lmm_step(self.h, p, int(from_host), out.ctypes.data))
         return out
 
     def simulate(self) -> None:

@@ -53,6 +53,13 @@ using RandomVariableCuda = RandomVariableImpl<CudaBackend>;
 class RandomVariableCudaFactory : public RandomVariableFactory {
 public:
     using RandomVariableFactory::createRandomVariable;
+    // Extension for callers that keep their doubles in pinned memory (fmc_host_alloc): asynchronous DMA + cast on the device.
+    // The array is read after the call returns; see fmc_vec_from_f64_pinned.
+    RV createRandomVariableFromPinned(double time, const double* pinnedValues, int64_t n) const {
+        fmc_vec h = 0;
+        fmc_check(fmc_vec_from_f64_pinned(pinnedValues, n, &h));
+        return RandomVariableCuda::of(time, CudaBackend::Vec(h), n);
+    }
     RV createRandomVariable(double time, double value) const override { return RandomVariableCuda::of(time, value); }                       // RVCF:26-29
     RV createRandomVariable(double time, const double* values, int64_t n) const override { return RandomVariableCuda::of(time, values, n); }   // RVCF:31-34
 };

@@ -80,6 +80,14 @@ int fmc_device_info(char* name, size_t name_len, int* sm_count, uint64_t* total_
 
 /* ---- vectors (replaces RVC:618-734 constructors, RVC:457-481 H2D/D2H, RVC:737-749 getDevicePointer) ---- */
 int fmc_vec_from_f64(const double* host, int64_t n, fmc_vec* out);   /* (float) cast RVC:768-774, H2D via pinned staging */
+/* Pinned host memory and the asynchronous upload from it. fmc_vec_from_f64 reads the caller's (pageable) array during the call:
+ * the (float) cast of RVC:768-774 runs on host threads into pinned staging, which bounds an upload-heavy run by host memory
+ * bandwidth. A caller that keeps its doubles in memory from fmc_host_alloc can use fmc_vec_from_f64_pinned instead: the doubles
+ * are copied by DMA on the copy stream and cast on the device, overlapping the kernels already queued. THE BUFFER IS READ AFTER
+ * THE CALL RETURNS: keep it unchanged until a reduction / host read that depends on the vector has returned, or fmc_sync(). */
+int fmc_host_alloc(size_t bytes, void** out);
+int fmc_host_free(void* p);
+int fmc_vec_from_f64_pinned(const double* pinned_host, int64_t n, fmc_vec* out);
 int fmc_vec_from_f32(const float* host, int64_t n, fmc_vec* out);
 int fmc_vec_fill(double value, int64_t n, fmc_vec* out);             /* RVF:139-146 (numberOfPath, value) constructor */
 int fmc_vec_alloc(int64_t n, fmc_vec* out);                          /* RVC:737-739 getDevicePointer(size): uninitialised */

@@ -389,6 +389,10 @@ cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t
     }
 }
 void tape_kernel_teardown() {}
+cudaError_t launch_cast_f64_f32(const double* src, float* dst, long long n, int, cudaStream_t) {
+    for (long long i = 0; i < n; i++) dst[i] = (float)src[i];
+    return cudaSuccess;
+}
 cudaError_t tape_kernel_setup(size_t* m) { if (m) *m = 232448 - 1024; return cudaSuccess; }
 size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots, int n_sets, int n_warps) {
     size_t s = (size_t)n_warps * (size_t)n_sets * TAPE_MAX_RING * 8;

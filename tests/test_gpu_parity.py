@@ -708,3 +708,32 @@ def test_fuzzed_statistics_regression_and_brownian(fc, O):
             for f in range(F):
                 got = bm.getBrownianIncrement(t, f).getRealizationsFloat() if p1 > p0 else np.empty(0, dtype=np.float32)
                 assert bits_equal(got, want[t * F + f]), (case, T, F, n, p0, p1, seed, mode, t, f)
+
+
+def test_pinned_asynchronous_upload(fc, O):
+    """fmc_host_alloc + fmc_vec_from_f64_pinned: DMA of the doubles on the copy stream and (float) cast on the device must
+    give exactly the vector the synchronous upload gives (Java's (float) cast, RVC:768-774), for sizes around the 1 Mi
+    element chunk, while kernels are queued; buffers that are not pinned are refused."""
+    import ctypes as C
+    from finmath_cuda import _capi as capi
+    L = capi.load()
+    rng = np.random.default_rng(11)
+    for n in (1, 7, 4097, (1 << 20) - 1, (1 << 20) + 3, 3 * (1 << 20) + 17):
+        p = C.c_void_p()
+        capi.check(L.fmc_host_alloc(8 * n, C.byref(p)))
+        host = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n,))
+        host[:] = rng.standard_normal(n) * np.where(rng.random(n) < 0.01, 1e-40, 1.0)      # some values denormal as floats
+        busy = fc.RandomVariableCuda(0.0, rng.random(2_000_000))
+        for _ in range(8): busy = busy.mult(1.0001).add(0.5).sqrt()
+        keep = busy.add(0.0); capi.check(L.fmc_flush())                                     # kernels in flight during the upload
+        h = C.c_uint64()
+        capi.check(L.fmc_vec_from_f64_pinned(p, n, C.byref(h)))
+        out = np.empty(n, dtype=np.float32)
+        capi.check(L.fmc_vec_to_f32(h.value, out.ctypes.data, n))
+        assert bits_equal(out, O.from_f64(host)), n
+        capi.check(L.fmc_vec_release(h.value))
+        del keep, busy
+        capi.check(L.fmc_host_free(p))
+    x = rng.random(100)
+    h = C.c_uint64()
+    assert L.fmc_vec_from_f64_pinned(x.ctypes.data, 100, C.byref(h)) == capi.FMC_ERR_INVALID

@@ -48,6 +48,8 @@ def test_lmm_simulation_and_swaptions_match_oracle(libs, paths):
     # host-array (end-to-end) arm gives the same numbers as the device-resident arm
     mg.prepare_host_brownian()
     assert np.array_equal(mg.step(p, from_host=True), mg.step(p))
+    # ... and so does the asynchronous upload from pinned host doubles (fmc_vec_from_f64_pinned, cast on the device)
+    assert np.array_equal(mg.step(p, from_host=2), mg.step(p))
     # products valued by three host threads (the library's numberOfThreads > 1): the same numbers
     mg.set_valuation_threads(3)
     assert np.array_equal(mg.step(p), vg_p)
