@@ -1053,6 +1053,9 @@ bool Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
         const char* err = nullptr; int err_code = 0; cudaError_t cuda_err = cudaSuccess;
         while (h[3] != ticket) {
             if (h[3] == -ticket) { err = "reduction exchange timed out: a peer rank did not deliver its partial"; err_code = FMC_ERR_COMM; break; }
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();                  // be polite to the sibling hyper-thread (another valuation thread may be recording)
+#endif
             if ((++spins & 0x3ffu) == 0u) {
                 // liveness check, at most every 200 us: the driver call contends with the threads that are launching
                 const auto now = std::chrono::steady_clock::now();
