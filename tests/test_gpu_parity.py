@@ -583,7 +583,7 @@ def test_fuzzed_programs_match_the_oracle(fc, O):
         for opts in knobs:
             for k_, v_ in SCHED_DEFAULTS.items(): fc.set_option(k_, v_)
             for k_, v_ in opts.items(): fc.set_option(k_, v_)
-            for seed in range(24):
+            for seed in range(int(os.environ.get("FMC_FUZZ_SEEDS", "24"))):      # more seeds for an occasional long run
                 rs0 = np.random.default_rng(1000 * len(opts) + seed)
                 n = int(rs0.choice([1, 5, 100, 511, 512, 513, 700, 1500, 3000, 5000]))
                 nops = int(rs0.choice([10, 40, 120, 400, 1200]))
