@@ -163,9 +163,19 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (an LMM Euler-step launch of tape_kernel<0> at
-# 1 Mi paths, 158 pointers), one `ncu --set full` capture: profiles/prof_micro_r1m.txt (338.0 MB read + 285.1 MB written)
-NCU_TRAFFIC_PER_LAUNCH = 623.0e6
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (an LMM Euler-step launch of the tape
+# interpreter at 1 Mi paths) from one `ncu --set full` capture; NOT measured in this run, NOT comparable with the per-step
+# algorithmic bytes: reported under its own name with the capture it came from (None until this round's capture exists).
+NCU_DRAM_BYTES_DOMINANT_LAUNCH = None
+NCU_CAPTURE_FILE = None
+
+PARITY_REL_TOL = 1e-4       # north star: "Monte-Carlo prices ... match within 1e-4 relative on identical seeds"
+
+
+def rel_diff(got, want):
+    import numpy as np
+    got = np.asarray(got, dtype=np.float64); want = np.asarray(want, dtype=np.float64)
+    return float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-12)))
 
 
 def run_ours(args) -> None:
@@ -274,11 +284,24 @@ def run_ours(args) -> None:
     st3 = fc.stats()
     pinned_ms = max_over_ranks(1e3 * pinned_s) / args.steps
 
+    # ---- the workload at the parity sample's size, on every rank's slice of the SAME global paths (compared with the oracle below) ----
+    sample_values = None
+    if not args.no_cpu_baseline:
+        sp = args.cpu_sample_paths if world == 1 else args.multi_gpu_check_paths
+        per = (sp + world - 1) // world
+        per = (per + 3) // 4 * 4                                  # slice boundaries on multiples of 4 elements
+        s0, s1 = min(sp, rank * per), min(sp, (rank + 1) * per)
+        sm = lib.lmm(sp, N_PERIODS, DELTA, 1, SEED, 0, (s0, s1))
+        sample_values = sm.step()
+        sm.close()
+        barrier()
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
+    import numpy as np
     peaks, peak_src = measured_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = prof["tape_algorithmic_bytes"] / (prof["tape_ms"] * 1e-3) / 1e9 if prof["tape_ms"] > 0 else 0.0
@@ -292,21 +315,32 @@ def run_ours(args) -> None:
                 "touched_bytes_per_step": touched.value / args.steps,
                 "achieved_touched": touched.value / (prof["tape_ms"] * 1e-3) / 1e9 if prof["tape_ms"] > 0 else 0.0,
                 "frac_touched": (touched.value / (prof["tape_ms"] * 1e-3) / 1e9) / peak if prof["tape_ms"] > 0 else 0.0}
-    roofline["traffic"] = NCU_TRAFFIC_PER_LAUNCH
+    roofline["ncu_dram_bytes_dominant_launch"] = NCU_DRAM_BYTES_DOMINANT_LAUNCH
+    roofline["ncu_capture"] = NCU_CAPTURE_FILE
 
+    # ---- parity of what was timed: the CPU oracle on a bounded sample, the GPU on exactly the same paths ----
     cpu_baseline = None
     if not args.no_cpu_baseline:
         from oracle.workloads_oracle import driver
         olib = driver()
-        sample_paths = args.cpu_sample_paths
+        sample_paths = args.cpu_sample_paths if world == 1 else args.multi_gpu_check_paths
         om = olib.lmm(sample_paths, N_PERIODS, DELTA, 1, SEED, 0)
         t0 = time.perf_counter()
         ovalues = om.step()
         dt = time.perf_counter() - t0
-        cpu_baseline = {"value": sample_paths * N_PERIODS / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                        "sample": f"1 step at {sample_paths} paths, single thread ({dt:.1f} s); C++ restatement of RandomVariableFromFloatArray",
-                        "max_abs_price_diff_vs_gpu_sample": None}
         del om
+        d = rel_diff(sample_values, ovalues)
+        parity = {"paths": sample_paths, "products": int(len(ovalues)), "max_rel_diff": d, "tol": PARITY_REL_TOL, "ok": bool(d <= PARITY_REL_TOL),
+                  "what": "all swaption values of one step, CUDA path vs CPU oracle (RandomVariableFromFloatArray restated) on the same paths and seed"}
+        if world == 1:
+            cpu_baseline = {"value": sample_paths * N_PERIODS / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                            "sample": f"1 step at {sample_paths} paths, single thread ({dt:.1f} s); C++ restatement of RandomVariableFromFloatArray",
+                            "max_abs_price_diff_vs_gpu_sample": float(np.max(np.abs(np.asarray(sample_values) - np.asarray(ovalues)))),
+                            "max_rel_price_diff_vs_gpu_sample": d}
+        else:
+            parity["what"] += f"; the GPU run is sharded over {world} ranks (global Brownian stream by jump-ahead, reductions exchanged between the GPUs)"
+    else:
+        parity = None
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -326,12 +360,15 @@ def run_ours(args) -> None:
         "ops_recorded_per_step": st["n_ops_recorded"] / args.steps,
         "nodes_stored_per_step": st["n_nodes_stored"] / args.steps, "nodes_fused_per_step": st["n_nodes_fused"] / args.steps,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "host_profile": host_prof,
+        ("parity" if world == 1 else "multi_gpu_parity"): parity,
         "price_check": {"first_values": [float(v) for v in values[:3]], "e2e_equal": bool((values == values_e2e).all()),
                         "e2e_pinned_equal": bool((values == values_pinned).all())},
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit(f"bench.py: parity check failed: max relative difference {parity['max_rel_diff']:.3g} > {PARITY_REL_TOL}")
 
 
 def main():
@@ -342,6 +379,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--paths", type=int, default=1 << 20, help="paths per GPU (north-star: 1M-path runs)")
     ap.add_argument("--cpu-sample-paths", type=int, default=393216)
+    ap.add_argument("--multi-gpu-check-paths", type=int, default=98304,
+                    help="N > 1: total paths of the sharded run that rank 0 compares with the CPU oracle (untimed)")
     ap.add_argument("--ref-paths-per-thread", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--valuation-threads", type=int, default=1,

@@ -52,10 +52,20 @@ def report(ws, hs, wf, hf):
 
 for prof in (0, 1):
     capi.set_option("profile", prof)
-    ws, hs = timed(m.simulate)
-    wf, hf = timed(m.step)
     capi.profile_read()
+    ws, hs = timed(m.simulate)
+    ps = capi.profile_read()
+    wf, hf = timed(m.step)
+    pf = capi.profile_read()
     print(f"-- per-launch event timing {'on' if prof else 'off'}")
     report(ws, hs, wf, hf)
+    if prof:
+        reps = 7      # 2 warm-up + 5 timed calls of each
+        ks, kf = ps["tape_ms"] / reps, pf["tape_ms"] / reps
+        bs, bf = ps["tape_algorithmic_bytes"] / reps, pf["tape_algorithmic_bytes"] / reps
+        print(f"paths={paths}  kernels: simulation {ks:6.3f} ms ({ps['tape_launches'] / reps:.0f} launches, {bs / 1e9:6.2f} GB algorithmic, {bs / ks / 1e6:7.1f} GB/s)")
+        print(f"paths={paths}  kernels: swaptions  {kf - ks:6.3f} ms ({(pf['tape_launches'] - ps['tape_launches']) / reps:.0f} launches, {(bf - bs) / 1e9:6.2f} GB algorithmic, "
+              f"{(bf - bs) / max(kf - ks, 1e-9) / 1e6:7.1f} GB/s)")
+        print(f"paths={paths}  kernels: whole step {kf:6.3f} ms, {bf / 1e9:6.2f} GB algorithmic, {bf / kf / 1e6:7.1f} GB/s")
 
 

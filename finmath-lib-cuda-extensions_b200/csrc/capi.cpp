@@ -394,7 +394,9 @@ static void set_option_locked(Runtime& rt, const char* key, double value) {
     else if (!std::strcmp(key, "profile")) rt.opt.profile = value != 0.0;
     else if (!std::strcmp(key, "ring_max")) rt.opt.ring_max = std::max(1, std::min((int)value, (int)TAPE_MAX_RING));
     else if (!std::strcmp(key, "ring_min")) rt.opt.ring_min = std::max(1, std::min((int)value, (int)TAPE_MAX_RING));
-    else if (!std::strcmp(key, "target_ctas")) rt.opt.target_ctas = std::max(1, (int)value);
+    else if (!std::strcmp(key, "target_ctas")) rt.opt.target_ctas = std::max(0, (int)value);
+    else if (!std::strcmp(key, "tape_elems")) { const int e = (int)value; if (e != 0 && !tape_valid_elems(e)) fail(FMC_ERR_INVALID, "tape_elems must be 0 (auto), 4, 8 or 16"); rt.opt.tape_elems = e; }
+    else if (!std::strcmp(key, "min_warps")) rt.opt.min_warps = std::max(1, (int)value);
     else if (!std::strcmp(key, "horizon")) rt.opt.horizon = std::max(0, (int)value);
     else if (!std::strcmp(key, "pipeline")) rt.opt.pipeline = value != 0.0;
     else if (!std::strcmp(key, "max_sets")) rt.opt.max_sets = std::max(1, std::min((int)value, 4));
@@ -403,7 +405,7 @@ static void set_option_locked(Runtime& rt, const char* key, double value) {
     else if (!std::strcmp(key, "p2p_reduce")) rt.opt.p2p_reduce = value != 0.0;
     else if (!std::strcmp(key, "zero_copy_reduce")) rt.opt.zero_copy_reduce = value != 0.0;
     else if (!std::strcmp(key, "leaf_reduce_kernel")) rt.opt.leaf_reduce_kernel = value != 0.0;
-    else if (!std::strcmp(key, "cta_warps")) rt.opt.cta_warps = (int)value == 2 ? 2 : 4;
+    else if (!std::strcmp(key, "cta_warps")) rt.opt.cta_warps = std::max(1, std::min((int)value, (int)TAPE_MAX_WARPS));
     else fail(FMC_ERR_INVALID, "unknown option '%s'", key);
 }
 // FMC_OPTIONS="key=value,key=value": applied once at fmc_init (tuning experiments without touching the caller)
@@ -439,6 +441,8 @@ int fmc_get_option(const char* key, double* value) {
         else if (!std::strcmp(key, "ring_max")) *value = rt.opt.ring_max;
         else if (!std::strcmp(key, "ring_min")) *value = rt.opt.ring_min;
         else if (!std::strcmp(key, "target_ctas")) *value = rt.opt.target_ctas;
+        else if (!std::strcmp(key, "tape_elems")) *value = rt.opt.tape_elems;
+        else if (!std::strcmp(key, "min_warps")) *value = rt.opt.min_warps;
         else if (!std::strcmp(key, "horizon")) *value = rt.opt.horizon;
         else if (!std::strcmp(key, "pipeline")) *value = rt.opt.pipeline ? 1.0 : 0.0;
         else if (!std::strcmp(key, "max_sets")) *value = rt.opt.max_sets;

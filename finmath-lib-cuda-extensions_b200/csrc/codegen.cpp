@@ -77,6 +77,7 @@ AIns mk(uint16_t op, uint8_t kind, int32_t arg, uint32_t y, int32_t src = -1, ui
 struct ImmPatch { int32_t word; int32_t src; uint8_t neg; };
 struct KernelPlan {
     int n_instr = 0, n_prologue = 0, n_ring = 0, n_slots = 0, n_sets = 1, reduce_mode = RM_NONE, grid = 1, n_warps = TAPE_WARPS;
+    int elems = TAPE_E_MAX;             // chunk geometry (elements per lane) the words are encoded for
     int n_leaf_slots = 0, n_result_stores = 0;
     std::vector<TapeInstr> words;       // n_instr + 2
     std::vector<int32_t> ptr_local;     // pointer table: the local whose buffer goes into each entry
@@ -499,7 +500,7 @@ struct Gen {
     struct Event { int32_t leaf; std::vector<int32_t> use; size_t k = 0; int slot = -1; bool waited = false; };
 
     // patches: where the immediates of the abstract code ended up (indices into `body`)
-    void schedule(int ring_max, bool pipeline, int horizon, std::vector<TapeInstr>& prologue, std::vector<TapeInstr>& body, int& n_ring,
+    void schedule(int ring_max, bool pipeline, int horizon, int shift, std::vector<TapeInstr>& prologue, std::vector<TapeInstr>& body, int& n_ring,
                   std::vector<ImmPatch>& patches) {
         auto note = [&](const AIns& a) { if (a.src >= 0) patches.push_back(ImmPatch{(int32_t)body.size() - 1, a.src, a.neg}); };
         // 1. residency intervals ("events") of every leaf: consecutive uses closer than `horizon` share one TMA copy
@@ -528,13 +529,13 @@ struct Gen {
 
         auto issue = [&](std::vector<TapeInstr>& out, int e, int s) {
             ev[e].slot = s; ev[e].waited = false; slot_ev[s] = e;
-            out.push_back(enc_idx(T_LOAD, (uint32_t)s, (uint32_t)info[ev[e].leaf].slot));
+            out.push_back(enc_idx(T_LOAD, (uint32_t)s, (uint32_t)info[ev[e].leaf].slot, shift));
         };
         auto refill = [&](int s) {
             slot_ev[s] = -1;
             if (q < order.size()) issue(body, order[q++], s);
             else if (pipeline && pro_leaf[s] >= 0 && !loadn_done[s]) {
-                body.push_back(enc_idx(T_LOADN, (uint32_t)s, (uint32_t)info[pro_leaf[s]].slot));
+                body.push_back(enc_idx(T_LOADN, (uint32_t)s, (uint32_t)info[pro_leaf[s]].slot, shift));
                 loadn_done[s] = 1;
             }
         };
@@ -563,7 +564,7 @@ struct Gen {
                     if (vs < 0) fail(FMC_ERR_UNSUPPORTED, "internal: no ring slot to evict");
                     const int o = slot_ev[vs];
                     {
-                        if (!ev[o].waited) body.push_back(enc_idx(T_WAIT, (uint32_t)vs, 0));
+                        if (!ev[o].waited) body.push_back(enc_idx(T_WAIT, (uint32_t)vs, 0, shift));
                         // the evicted occupant's remaining uses become a new event, queued by its next use
                         Event rest; rest.leaf = ev[o].leaf;
                         rest.use.assign(ev[o].use.begin() + (long)ev[o].k, ev[o].use.end());
@@ -585,7 +586,7 @@ struct Gen {
                 const uint32_t opc = (a.op == T_ADDAFF_S) ? (fl == 1u ? (uint32_t)T_ADDAFF_S : (uint32_t)T_ADDAFF_W)
                                    : (a.op == T_ADDAFFDISC_S) ? (fl == 1u ? (uint32_t)T_ADDAFFDISC_S : (uint32_t)T_ADDAFFDISC_W)
                                                           : T_BIN0 + 3u * (uint32_t)(a.op & 0xff) + fl;
-                body.push_back(TapeInstr{ opc | ((uint32_t)E.slot << TAPE_SLOT_SHIFT), a.y });
+                body.push_back(TapeInstr{ opc | ((uint32_t)E.slot << shift), a.y });
                 note(a);
                 E.k++;
                 // a two-word instruction keeps its extension word right behind it: the slot is refilled after that word
@@ -597,7 +598,7 @@ struct Gen {
             } else if (a.op & A_BIN) {
                 const uint32_t bop = T_BIN0 + 3u * (uint32_t)(a.op & 0xff);
                 if (a.kind == K_IMM) body.push_back(TapeInstr{ bop, a.y });
-                else body.push_back(TapeInstr{ (bop + 1u) | ((R + (uint32_t)a.arg) << TAPE_SLOT_SHIFT), a.y });
+                else body.push_back(TapeInstr{ (bop + 1u) | ((R + (uint32_t)a.arg) << shift), a.y });
                 note(a);
             } else if (a.op == A_EXT) {
                 body.push_back(TapeInstr{ T_END, a.y });                  // only its y is read
@@ -610,11 +611,11 @@ struct Gen {
                 if (a.src2 >= 0) patches.push_back(ImmPatch{(int32_t)body.size() - 1, a.src2, 0});
             } else if (a.op == T_END) {
                 // re-arm whatever prologue slot has not been re-armed yet (only slots that were never freed: none in practice)
-                if (a.kind == K_REG) body.push_back(TapeInstr{ T_END | ((R + (uint32_t)a.arg) << TAPE_SLOT_SHIFT), 1u });
+                if (a.kind == K_REG) body.push_back(TapeInstr{ T_END | ((R + (uint32_t)a.arg) << shift), 1u });
                 else body.push_back(TapeInstr{ T_END, 0u });
             } else {
                 const uint32_t slot = (a.kind == K_REG) ? R + (uint32_t)a.arg : 0u;
-                body.push_back(TapeInstr{ (uint32_t)a.op | (slot << TAPE_SLOT_SHIFT), a.y });
+                body.push_back(TapeInstr{ (uint32_t)a.op | (slot << shift), a.y });
                 if (a.op != T_STG && a.op != T_STGS) note(a);
             }
         }
@@ -642,25 +643,41 @@ struct Gen {
         std::vector<TapeInstr> prologue, body;
         KernelPlan kp;
         int n_ring = 0;
-        // Shared-memory budget of one warp, in 1 KB slots, if target_ctas CTAs are to be resident per SM: short tapes
-        // keep the occupancy high, long ones trade it for ring depth (never below ring_min slots).
-        const int64_t chunks = (n + TAPE_CHUNK - 1) / TAPE_CHUNK;
-        const int n_warps = rt.opt.cta_warps == 2 ? 2 : TAPE_WARPS;
-        const size_t est_tables = 8 * (A.size() + 2 * (size_t)n_leaf_refs + 2 * TAPE_MAX_RING + 6) + 8 * ptrs.size() + 256;
-        // CTAs per SM to aim for: the configured target, raised when that lets the whole vector be resident at once
-        // (at ~1 chunk per warp a grid that needs a second round of CTAs runs it at a fraction of the occupancy)
-        int target = std::max(1, rt.opt.target_ctas) * (TAPE_WARPS / n_warps);
-        {
-            const int64_t need = (chunks + (int64_t)n_warps * rt.sm_count - 1) / ((int64_t)n_warps * rt.sm_count);
-            const int hw_max = (reduce_mode != RM_NONE ? 6 : 8) * (TAPE_WARPS / n_warps);
-            if (need > target && need <= hw_max) target = (int)need;
+        const int n_warps = std::max(1, std::min(rt.opt.cta_warps, TAPE_MAX_WARPS));
+        // Chunk geometry (elements per lane, tape_interp.cuh). A warp interprets one chunk of 32 E paths at a time, so a vector
+        // of n paths is n / (32 E) warps' worth of work per pass: the largest E that still gives every SM `min_warps` warps
+        // (16-element chunks amortise the dispatch best; below that the GPU's warp slots stay empty and the interpreter runs
+        // at the latency of a lone warp, so more, shorter warps win).
+        int elems = rt.opt.tape_elems;
+        if (!tape_valid_elems(elems)) {
+            elems = 4;
+            for (int e = TAPE_E_MAX; e > 4; e >>= 1)
+                if (n >= (int64_t)rt.opt.min_warps * rt.sm_count * tape_chunk(e)) { elems = e; break; }
         }
+        const int slot_bytes = tape_slot_bytes(elems);
+        const int64_t chunks = (n + tape_chunk(elems) - 1) / tape_chunk(elems);
+        // Shared-memory budget of one warp, in slots, if `target` CTAs are to be resident per SM: as many as the vector needs
+        // to be resident at once (at ~1 chunk per warp a grid that needs a second round of CTAs runs it at a fraction of the
+        // occupancy), at most what the registers of this geometry allow; short tapes keep the occupancy high, long ones
+        // trade it for ring depth (never below ring_min slots).
+        const size_t est_tables = 8 * (A.size() + 2 * (size_t)n_leaf_refs + 2 * TAPE_MAX_RING + 6) + 8 * ptrs.size() + 256;
+        static OccCache occ;
+        auto blocks_per_sm = [&](size_t smem_bytes) {
+            const auto key = std::make_pair((smem_bytes + 1023) / 1024, (reduce_mode * 16 + n_warps) * 32 + elems);
+            auto it = occ.blocks.find(key);
+            if (it == occ.blocks.end()) it = occ.blocks.emplace(key, tape_max_blocks_per_sm(key.first * 1024, reduce_mode, n_warps, elems)).first;
+            return it->second;
+        };
+        const int hw_max = blocks_per_sm(1024);
+        const int64_t need = (chunks + (int64_t)n_warps * rt.sm_count - 1) / ((int64_t)n_warps * rt.sm_count);
+        int target = (int)std::max<int64_t>(1, std::min<int64_t>(need, hw_max));
+        if (rt.opt.target_ctas > 0) target = std::min(rt.opt.target_ctas, hw_max);          // tests / tuning: forced
         const size_t cta_share = rt.smem_per_sm / (size_t)target;
         const long budget_bytes = (long)std::min(cta_share, rt.smem_per_cta_max) - 1024 - (long)est_tables;
-        const int slot_budget = (int)std::max<long>(1, budget_bytes / (n_warps * TAPE_SLOT_BYTES));
+        const int slot_budget = (int)std::max<long>(1, budget_bytes / (n_warps * slot_bytes));
         int ring_max = std::max(1, std::min<int>(rt.opt.ring_max, TAPE_MAX_RING));
         ring_max = std::min(ring_max, std::max(rt.opt.ring_min, slot_budget - regs_used));
-        { PhaseTimer pt(4); schedule(ring_max, rt.opt.pipeline, rt.opt.horizon, prologue, body, n_ring, kp.patches); }
+        { PhaseTimer pt(4); schedule(ring_max, rt.opt.pipeline, rt.opt.horizon, tape_slot_shift(elems), prologue, body, n_ring, kp.patches); }
         PhaseTimer pt_prep(5);
         const size_t total = prologue.size() + 1 + body.size();
         if (total > (size_t)TAPE_MAX_INSTR + 1 || ptrs.size() > (size_t)TAPE_MAX_PTRS)
@@ -671,6 +688,7 @@ struct Gen {
         kp.n_slots = n_ring + regs_used;
         kp.reduce_mode = reduce_mode;
         kp.n_warps = n_warps;
+        kp.elems = elems;
         kp.n_leaf_slots = n_leaf_slots; kp.n_result_stores = n_result_stores;
         kp.words.reserve(total + 2);
         kp.words.insert(kp.words.end(), prologue.begin(), prologue.end());
@@ -680,19 +698,12 @@ struct Gen {
         kp.words.push_back(TapeInstr{ T_END, 0u });
         for (ImmPatch& ip : kp.patches) ip.word += (int32_t)prologue.size() + 1;
         kp.ptr_local = slotted;
-        static OccCache occ;
-        auto blocks_per_sm = [&](size_t smem_bytes) {
-            const auto key = std::make_pair((smem_bytes + 1023) / 1024, reduce_mode * 8 + n_warps);
-            auto it = occ.blocks.find(key);
-            if (it == occ.blocks.end()) it = occ.blocks.emplace(key, tape_max_blocks_per_sm(key.first * 1024, reduce_mode, n_warps)).first;
-            return it->second;
-        };
         // slot sets: a tape that leaves most of the budget unused keeps several chunks per warp in flight
         int n_sets = 1, per_sm = 1, grid = 1;
         size_t smem = 0;
         if (rt.opt.pipeline && n_ring > 0) n_sets = std::max(1, std::min(rt.opt.max_sets, slot_budget / std::max(1, kp.n_slots)));
         for (;;) {
-            smem = tape_smem_bytes((int)ptrs.size(), kp.n_instr, kp.n_slots, n_sets, n_warps);
+            smem = tape_smem_bytes((int)ptrs.size(), kp.n_instr, kp.n_slots, n_sets, n_warps, elems);
             if (smem > rt.smem_per_cta_max && n_sets > 1) { n_sets--; continue; }
             if (smem > rt.smem_per_cta_max) fail(FMC_ERR_UNSUPPORTED, "internal: tape needs %zu bytes of shared memory per CTA", smem);
             per_sm = blocks_per_sm(smem);
@@ -707,8 +718,8 @@ struct Gen {
         kp.grid = grid;
         static const bool log_tapes = std::getenv("FMC_LOG_TAPES") != nullptr;
         if (log_tapes)
-            std::fprintf(stderr, "[fmc tape] n=%lld instr=%zu (abstract %zu, prologue %zu) ptrs=%zu leaves=%d stores=%d ring=%d regs=%d sets=%d warps=%d smem=%zu ctas/sm=%d grid=%d reduce=%d\n",
-                         (long long)n, total, A.size(), prologue.size(), ptrs.size(), n_leaf_slots, n_result_stores, n_ring, regs_used, n_sets, n_warps, smem, per_sm, grid, reduce_mode);
+            std::fprintf(stderr, "[fmc tape] n=%lld elems=%d instr=%zu (abstract %zu, prologue %zu) ptrs=%zu leaves=%d stores=%d ring=%d regs=%d sets=%d warps=%d smem=%zu ctas/sm=%d grid=%d reduce=%d\n",
+                         (long long)n, elems, total, A.size(), prologue.size(), ptrs.size(), n_leaf_slots, n_result_stores, n_ring, regs_used, n_sets, n_warps, smem, per_sm, grid, reduce_mode);
         submit(kp, reduce_param, false);
         if (keep_plans) plans.push_back(std::move(kp));
     }
@@ -717,6 +728,7 @@ struct Gen {
     void submit(const KernelPlan& kp, double reduce_param, bool patch) {
         TapeParams& P = *params;
         P.n = n;
+        P.elems = kp.elems;
         P.n_instr = kp.n_instr;
         P.n_prologue = kp.n_prologue;
         P.n_ptrs = (int)kp.ptr_local.size();

@@ -7,12 +7,12 @@
 
 namespace fmc {
 
-// tape_kernel.cu
-cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t stream);   // n_warps per CTA: 2 or 4
+// tape_launch.cu + tape_kernel_e16/8/4.cu (one body: tape_interp.cuh)
+cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t stream);   // n_warps per CTA: 1..TAPE_MAX_WARPS; geometry: P.elems
 cudaError_t tape_kernel_setup(size_t* max_smem_per_cta);   // opts the kernels in to the device's full shared memory, allocates the tape ring
 void tape_kernel_teardown();
-size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots, int n_sets, int n_warps);   // dynamic shared memory of one CTA
-int tape_max_blocks_per_sm(size_t smem_bytes, int reduce_mode, int n_warps);
+size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots, int n_sets, int n_warps, int elems);   // dynamic shared memory of one CTA
+int tape_max_blocks_per_sm(size_t smem_bytes, int reduce_mode, int n_warps, int elems);
 
 // reduce_kernel.cu — streaming reduction of a materialised vector (no chain to interpret)
 struct ReduceParams {

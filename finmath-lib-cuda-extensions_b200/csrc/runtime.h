@@ -110,14 +110,16 @@ struct Options {
     // interpreter scheduling knobs (see codegen.cpp: Gen::schedule / Gen::launch)
     int ring_max = TAPE_MAX_RING;   // TMA ring slots per warp, upper bound
     int ring_min = 2;               // ... lower bound when shared memory is tight
-    int target_ctas = 4;            // CTAs per SM the slot budget aims for
+    int target_ctas = 0;            // > 0: CTAs per SM the slot budget aims for (tests / tuning); 0: as many as the vector needs, up to the register limit
     int horizon = 96;               // uses of a leaf further apart than this many instructions are separate TMA copies
     bool pipeline = true;           // cross-chunk prefetch (prologue + T_LOADN)
     int max_sets = 1;               // slot sets per warp (cross-chunk prefetch depth), upper bound; measured: >1 costs occupancy and does not pay
     bool zero_copy_reduce = true;   // reductions publish their result through mapped pinned memory (single-rank runs)
     bool leaf_reduce_kernel = true; // reductions of a materialised vector use the streaming kernel, not the interpreter
     bool p2p_reduce = true;         // sharded runs: exchange reduction partials inside the kernel over NVLink peer memory (else NCCL)
-    int cta_warps = 4;              // warps per interpreter CTA (2 or 4)
+    int cta_warps = 4;              // warps per interpreter CTA (1..TAPE_MAX_WARPS)
+    int tape_elems = 0;             // chunk geometry: elements per lane, 16 / 8 / 4; 0 = chosen per launch from the vector length
+    int min_warps = 24;             // ... the largest geometry that still gives every SM this many warps of work
     bool fuse_ops = true;           // peephole fusion of the abstract code (MULADD_II, ACCUM_S, ADDPROD)
     int grid_limit = 0;             // > 0: cap the interpreter grid (tests: many chunks per warp at small sizes)
     int max_regs = 8;               // register-file slots the code generator may use, <= TAPE_REGS. Measured on the LMM step: 16 slots

@@ -1,11 +1,11 @@
 // tape_isa.h — instruction set of the op-tape interpreter (shared by the host code generator and the kernel).
 //
-// Machine model. One WARP interprets the tape for one chunk of TAPE_CHUNK consecutive paths at a time
-// (lane l owns elements 128g+4l..128g+4l+3, g = 0..3, of the chunk, i.e. four 128-bit groups), warps are fully
-// independent of each other (no block barrier on the elementwise path):
-//   acc            accumulator, TAPE_E real registers per lane
+// Machine model. One WARP interprets the tape for one chunk of 32 * E consecutive paths at a time, E = 16, 8 or 4 elements
+// per lane chosen per launch (TapeHeader::elems; lane l owns elements 128g+4l..128g+4l+3, g = 0..E/4-1, of the chunk, i.e.
+// E/4 groups of 128 bits); warps are fully independent of each other (no block barrier on the elementwise path):
+//   acc            accumulator, E real registers per lane
 //   p              one predicate per element (for choose)
-//   slot[0..S-1]   per-warp shared-memory tiles of TAPE_SLOT_BYTES each.
+//   slot[0..S-1]   per-warp shared-memory tiles of 128 * E bytes each.
 //                  slots [0, n_ring)         "ring": destinations of TMA bulk copies (cp.async.bulk) of leaf-vector
 //                                            chunks, each guarded by its own mbarrier; the code generator issues the
 //                                            T_LOAD of a chunk as early as the slot is free, so the copy overlaps the
@@ -17,7 +17,7 @@
 //                                            occupant has been consumed, so every later chunk starts with its first
 //                                            leaves already in flight or landed.
 //                  slots [n_ring, S)         register file for intermediate values (T_STR writes, *_S reads)
-// Instruction word (8 bytes): x = op | slot_byte_offset (slot * TAPE_SLOT_BYTES, low 11 bits are the opcode);
+// Instruction word (8 bytes): x = op | slot_byte_offset (slot * 128 * E: the low log2(128 E) bits are the opcode);
 //                             y = float immediate bits | pointer-table index.
 // Multi-word instructions (T_MULADD_II, ..., T_RATIO) take the y of the following word(s) as further immediates.
 // Binary opcodes come in three flavours: _I (operand = immediate), _S (operand = slot), _W (operand = ring slot
@@ -25,17 +25,20 @@
 // Every primitive rounds once, exactly like the Java float code; the compound RandomVariable ops (accrue, discount,
 // addProduct) exist as single instructions but still round after every elementary operation (no FMA).
 //
-// The opcode numbering is the index into the interpreter's branch-target table (tape_kernel.cu): keep both in sync.
+// The opcode numbering is the index into the interpreter's branch-target table (tape_interp.cuh): keep both in sync.
 #pragma once
 #include <stdint.h>
 
 namespace fmc {
 
-constexpr int TAPE_E = 16;                             // elements per lane
-constexpr int TAPE_WARPS = 4;                          // warps per CTA (2 for small vectors: finer CTA granularity)
-constexpr int TAPE_CHUNK = 32 * TAPE_E;                // 512 paths per warp iteration
-constexpr int TAPE_SLOT_BYTES = TAPE_CHUNK * 4;        // 2 KB
-constexpr int TAPE_SLOT_SHIFT = 11;
+// chunk geometry: E elements per lane (16, 8 or 4), chosen per launch
+constexpr int TAPE_E_MAX = 16;
+constexpr int TAPE_WARPS = 4;                          // warps per CTA (default)
+constexpr int TAPE_MAX_WARPS = 8;                      // ... upper bound (block reduction scratch)
+constexpr bool tape_valid_elems(int e) { return e == 16 || e == 8 || e == 4; }
+constexpr int tape_chunk(int elems) { return 32 * elems; }                 // paths per warp iteration: 512 / 256 / 128
+constexpr int tape_slot_bytes(int elems) { return 128 * elems; }           // 2 KB / 1 KB / 512 B
+constexpr int tape_slot_shift(int elems) { return elems == 16 ? 11 : elems == 8 ? 10 : 9; }
 constexpr int TAPE_MAX_RING = 16;                      // ring slots per warp (mbarriers per warp)
 constexpr int TAPE_REGS = 16;                          // register-file slots the code generator may use
 constexpr int TAPE_MAX_INSTR = 2046;
@@ -95,15 +98,12 @@ struct Exchange { double* tables[XMAX_RANKS]; int rank, nranks; };   // nranks <
 
 struct TapeInstr { uint32_t x, y; };
 
-inline TapeInstr enc_imm(uint32_t op, uint32_t slot, float imm) {
-    union { float f; uint32_t u; } c; c.f = imm;
-    return TapeInstr{ op | (slot << TAPE_SLOT_SHIFT), c.u };
-}
-inline TapeInstr enc_idx(uint32_t op, uint32_t slot, uint32_t idx) { return TapeInstr{ op | (slot << TAPE_SLOT_SHIFT), idx }; }
+inline TapeInstr enc_idx(uint32_t op, uint32_t slot, uint32_t idx, int shift) { return TapeInstr{ op | (slot << shift), idx }; }
 
 // Everything a launch needs except the two tables.
 struct TapeHeader {
     long long n;              // elements per vector
+    int elems;                // chunk geometry: elements per lane (16, 8 or 4)
     int n_instr;              // instructions including the final T_END (two more padding words follow)
     int n_prologue;           // leading T_LOADs, closed by a T_END: run once per slot set before the warp's first chunks;
                               // the body starts at instr[n_prologue + 1]

@@ -87,7 +87,7 @@ float jmaxf(float a, float b) {
     if (a == 0.f && b == 0.f) return (std::signbit(a) && std::signbit(b)) ? -0.f : 0.f;
     return a > b ? a : b;
 }
-float jpow(float x, float e) {       // mirrors f_pow in tape_kernel.cu
+float jpow(float x, float e) {       // mirrors f_pow in tape_interp.cuh
     const double dx = (double)x, de = (double)e;
     if (de != de) return (float)de;
     if (de == 0.0) return 1.0f;
@@ -98,17 +98,18 @@ float jpow(float x, float e) {       // mirrors f_pow in tape_kernel.cu
     return (float)std::pow(dx, de);
 }
 
-constexpr int C = TAPE_CHUNK;
+constexpr int CMAX = 32 * TAPE_E_MAX;      // largest chunk; the geometry of a launch is P.elems
 
 struct Warp {
     const TapeParams& P;
+    const int C;                              // paths per chunk of this launch
     std::vector<float> slots;                 // [n_slots][C]
     std::vector<int> issued, waited;          // per ring slot: TMA copies armed / waited for
     std::vector<char> reg_written;            // per slot: register-file slot holds a value of the current chunk
     std::vector<long long> slot_chunk;        // chunk the ring slot's (pending or landed) data belongs to
     std::set<const float*>& stored;           // buffers written by this launch
     explicit Warp(const TapeParams& p, std::set<const float*>& st)
-        : P(p), slots((size_t)p.n_slots * C, NAN), issued(p.n_ring, 0), waited(p.n_ring, 0), reg_written(p.n_slots, 0),
+        : P(p), C(tape_chunk(p.elems)), slots((size_t)p.n_slots * tape_chunk(p.elems), NAN), issued(p.n_ring, 0), waited(p.n_ring, 0), reg_written(p.n_slots, 0),
           slot_chunk(p.n_ring, -1), stored(st) {}
 
     void load(uint32_t slot, uint32_t pidx, long long chunk) {
@@ -143,6 +144,8 @@ struct Partial { double c = 0, s = 0, s2 = 0, mn = 0, mx = 0; };
 
 void run_warp(const TapeParams& P, long long first_chunk, long long stride, std::set<const float*>& stored, Partial& part,
               std::vector<double>& values /* RM_MOMENTS two-pass */) {
+    const int C = tape_chunk(P.elems);
+    const int SHIFT = tape_slot_shift(P.elems);
     const long long n_chunks = (P.n + C - 1) / C;
     std::vector<Warp> sets;
     for (int u = 0; u < P.n_sets; u++) sets.emplace_back(P, stored);
@@ -153,8 +156,8 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
         if (chunk >= n_chunks) continue;
         for (int pc = 0; pc < P.n_prologue; pc++) {
             const TapeInstr in = P.instr[pc];
-            if ((in.x & ((1u << TAPE_SLOT_SHIFT) - 1u)) != T_LOAD) bad("prologue instruction %d is not a T_LOAD", pc);
-            sets[u].load(in.x >> TAPE_SLOT_SHIFT, in.y, chunk);
+            if ((in.x & ((1u << SHIFT) - 1u)) != T_LOAD) bad("prologue instruction %d is not a T_LOAD", pc);
+            sets[u].load(in.x >> SHIFT, in.y, chunk);
         }
     }
     long long k = 0;
@@ -162,14 +165,14 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
         Warp& w = sets[(size_t)(k % P.n_sets)];
         const long long base = chunk * C;
         const long long next = chunk + stride * P.n_sets;
-        float acc[C]; bool pred[C];
+        float acc[CMAX]; bool pred[CMAX];
         for (int e = 0; e < C; e++) { acc[e] = 0.f; pred[e] = false; }
         std::fill(w.reg_written.begin(), w.reg_written.end(), 0);
         const float* endb = nullptr;
         for (int pc = P.n_prologue + 1;; pc++) {
             if (pc >= P.n_instr) bad("ran off the end of the tape");
             const TapeInstr in = P.instr[pc];
-            const uint32_t op = in.x & ((1u << TAPE_SLOT_SHIFT) - 1u), slot = in.x >> TAPE_SLOT_SHIFT;
+            const uint32_t op = in.x & ((1u << SHIFT) - 1u), slot = in.x >> SHIFT;
             float imm; std::memcpy(&imm, &in.y, 4);
             if (op == T_END) {
                 if (in.y != 0u) {
@@ -264,7 +267,7 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
             }
             case T_STR:
                 if ((int)slot < P.n_ring || (int)slot >= P.n_slots) bad("T_STR into slot %d outside the register file", (int)slot);
-                std::memcpy(&w.slots[(size_t)slot * C], acc, sizeof(acc));
+                std::memcpy(&w.slots[(size_t)slot * C], acc, sizeof(float) * (size_t)C);
                 w.reg_written[slot] = 1;
                 break;
             case T_SETP: for (int e = 0; e < C; e++) pred[e] = acc[e] >= 0.0f; break;
@@ -290,7 +293,7 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
                 if ((int)slot < P.n_ring) bad("T_ACCUM_S on a ring slot");
                 const float* b = w.read(slot, chunk);
                 for (int e = 0; e < C; e++) acc[e] = acc[e] + b[e];
-                std::memcpy(&w.slots[(size_t)slot * C], acc, sizeof(acc));
+                std::memcpy(&w.slots[(size_t)slot * C], acc, sizeof(float) * (size_t)C);
                 break;
             }
             default: bad("opcode %d unknown", (int)op);
@@ -325,10 +328,11 @@ void dump_tape(const TapeParams& P, int grid) {
     static const char* names[] = {"END", "LOAD", "WAIT", "STG", "STGS", "STR", "SETP", "SQR", "SQRT", "EXP", "LOG", "SIN", "COS", "ABS", "INV",
                                   "ISNAN", "POW", "MULADD_II", "LOADN", "ACCUM_S", "?"};
     static const char* bins[] = {"MOV", "ADD", "SUB", "BUS", "MUL", "DIV", "VID", "MIN", "MAX", "SEL", "ADDPROD", "ACCRUE", "DISCOUNT"};
-    std::fprintf(stderr, "[tape] n=%lld grid=%d instr=%d prologue=%d ptrs=%d ring=%d slots=%d reduce=%d\n", P.n, grid, P.n_instr, P.n_prologue,
+    std::fprintf(stderr, "[tape] n=%lld elems=%d grid=%d instr=%d prologue=%d ptrs=%d ring=%d slots=%d reduce=%d\n", P.n, P.elems, grid, P.n_instr, P.n_prologue,
                  P.n_ptrs, P.n_ring, P.n_slots, P.reduce_mode);
+    const int SHIFT = tape_slot_shift(P.elems);
     for (int i = 0; i < P.n_instr; i++) {
-        const uint32_t op = P.instr[i].x & ((1u << TAPE_SLOT_SHIFT) - 1u), slot = P.instr[i].x >> TAPE_SLOT_SHIFT;
+        const uint32_t op = P.instr[i].x & ((1u << SHIFT) - 1u), slot = P.instr[i].x >> SHIFT;
         float imm; std::memcpy(&imm, &P.instr[i].y, 4);
         if (op == T_MULADDMUL) std::fprintf(stderr, "  %4d MULADDMUL %g\n", i, imm);
         else if (op == T_RATIO) std::fprintf(stderr, "  %4d RATIO %g\n", i, imm);
@@ -356,16 +360,17 @@ cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t
         return cudaSuccess;
     }
     try {
+        if (!tape_valid_elems(P.elems)) bad("bad chunk geometry: %d elements per lane", P.elems);
         if (P.n_ring < 0 || P.n_ring > TAPE_MAX_RING || P.n_slots < P.n_ring) bad("bad slot counts: ring %d slots %d", P.n_ring, P.n_slots);
         if (P.n_instr < 1 || P.n_instr > TAPE_MAX_INSTR + 1) bad("bad instruction count %d", P.n_instr);
         if (P.n_prologue < 0 || P.n_prologue + 1 >= P.n_instr) bad("bad prologue length %d", P.n_prologue);
         if (P.n_sets < 1 || P.n_sets > 4) bad("bad slot-set count %d", P.n_sets);
         if (grid < 1) bad("empty grid");
-        if (tape_smem_bytes(P.n_ptrs, P.n_instr, P.n_slots, P.n_sets, n_warps) > 232448 - 1024) bad("shared memory of one CTA exceeds the device limit");
+        if (tape_smem_bytes(P.n_ptrs, P.n_instr, P.n_slots, P.n_sets, n_warps, P.elems) > 232448 - 1024) bad("shared memory of one CTA exceeds the device limit");
         std::set<const float*> stored;
         Partial part;
         std::vector<double> values;
-        if (n_warps != 2 && n_warps != 4) bad("bad warp count %d", n_warps);
+        if (n_warps < 1 || n_warps > TAPE_MAX_WARPS) bad("bad warp count %d", n_warps);
         const long long stride = (long long)grid * n_warps;
         for (long long w = 0; w < stride; w++) run_warp(P, w, stride, stored, part, values);
         if (P.reduce_mode != RM_NONE) {
@@ -394,15 +399,16 @@ cudaError_t launch_cast_f64_f32(const double* src, float* dst, long long n, int,
     return cudaSuccess;
 }
 cudaError_t tape_kernel_setup(size_t* m) { if (m) *m = 232448 - 1024; return cudaSuccess; }
-size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots, int n_sets, int n_warps) {
+size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots, int n_sets, int n_warps, int elems) {
     size_t s = (size_t)n_warps * (size_t)n_sets * TAPE_MAX_RING * 8;
     s += ((size_t)n_ptrs * 8 + 15) & ~(size_t)15;
     s = (s + ((size_t)n_instr + 2) * 8 + 127) & ~(size_t)127;
-    return s + (size_t)n_warps * (size_t)n_sets * (size_t)n_slots * TAPE_SLOT_BYTES;
+    return s + (size_t)n_warps * (size_t)n_sets * (size_t)n_slots * (size_t)tape_slot_bytes(elems);
 }
-int tape_max_blocks_per_sm(size_t smem_bytes, int reduce_mode, int n_warps) {
+int tape_max_blocks_per_sm(size_t smem_bytes, int, int n_warps, int elems) {
     const int by_smem = (int)((233472 - 1024) / (smem_bytes + 1024));
-    const int by_regs = (reduce_mode != RM_NONE ? 6 : 8) * (4 / n_warps);
+    const int regs = elems == 16 ? 128 : elems == 8 ? 72 : 40;            // __maxnreg__ of the three geometries (tape_interp.cuh)
+    const int by_regs = 65536 / (regs * 32 * n_warps);
     return std::max(1, std::min(by_smem, by_regs));
 }
 

@@ -283,7 +283,7 @@ def test_long_tape_register_pressure_and_cuts(fc, O, data):
     assert bits_equal(c.getRealizationsFloat(), co)
 
 
-SCHED_DEFAULTS = {"ring_max": 16, "ring_min": 2, "target_ctas": 4, "horizon": 96, "pipeline": 1, "max_sets": 1, "grid_limit": 0, "max_regs": 8}
+SCHED_DEFAULTS = {"ring_max": 16, "ring_min": 2, "target_ctas": 0, "horizon": 96, "pipeline": 1, "max_sets": 1, "grid_limit": 0, "max_regs": 8}
 
 
 @pytest.mark.parametrize("opts", [
