@@ -383,7 +383,7 @@ int fmc_sync(void) {
 }
 static void set_option_locked(Runtime& rt, const char* key, double value) {
     // everything that steers the code generator invalidates the cached tapes
-    static const char* const keeps_cache[] = {"flush_threshold", "profile", "p2p_reduce", "zero_copy_reduce", "leaf_reduce_kernel"};
+    static const char* const keeps_cache[] = {"flush_threshold", "profile", "tape_upload_stream", "p2p_reduce", "zero_copy_reduce", "leaf_reduce_kernel"};
     bool keep = false;
     for (const char* k : keeps_cache) keep = keep || !std::strcmp(key, k);
     if (!keep) tape_cache_clear();
@@ -402,6 +402,8 @@ static void set_option_locked(Runtime& rt, const char* key, double value) {
     else if (!std::strcmp(key, "max_sets")) rt.opt.max_sets = std::max(1, std::min((int)value, 4));
     else if (!std::strcmp(key, "grid_limit")) rt.opt.grid_limit = std::max(0, (int)value);
     else if (!std::strcmp(key, "fuse_ops")) rt.opt.fuse_ops = value != 0.0;
+    else if (!std::strcmp(key, "fuse_ops2")) rt.opt.fuse_ops2 = value != 0.0;
+    else if (!std::strcmp(key, "tape_upload_stream")) rt.opt.tape_upload_stream = value != 0.0;
     else if (!std::strcmp(key, "p2p_reduce")) rt.opt.p2p_reduce = value != 0.0;
     else if (!std::strcmp(key, "zero_copy_reduce")) rt.opt.zero_copy_reduce = value != 0.0;
     else if (!std::strcmp(key, "leaf_reduce_kernel")) rt.opt.leaf_reduce_kernel = value != 0.0;
@@ -448,6 +450,7 @@ int fmc_get_option(const char* key, double* value) {
         else if (!std::strcmp(key, "max_sets")) *value = rt.opt.max_sets;
         else if (!std::strcmp(key, "grid_limit")) *value = rt.opt.grid_limit;
         else if (!std::strcmp(key, "fuse_ops")) *value = rt.opt.fuse_ops ? 1.0 : 0.0;
+        else if (!std::strcmp(key, "fuse_ops2")) *value = rt.opt.fuse_ops2 ? 1.0 : 0.0;
         else if (!std::strcmp(key, "p2p_reduce")) *value = rt.opt.p2p_reduce ? 1.0 : 0.0;
         else if (!std::strcmp(key, "p2p_ready")) *value = rt.p2p_ready ? 1.0 : 0.0;
         else if (!std::strcmp(key, "device_index")) *value = rt.device;

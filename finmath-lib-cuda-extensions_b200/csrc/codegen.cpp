@@ -54,7 +54,7 @@ struct Info {
 };
 
 // ---- abstract accumulator-machine code (before ring scheduling) ----
-enum AKind : uint8_t { K_NONE = 0, K_IMM, K_REG, K_LEAF };
+enum AKind : uint8_t { K_NONE = 0, K_IMM, K_REG, K_LEAF, K_RELOAD /* extension word: pointer-table slot of the leaf a fused form re-arms its ring slot with */ };
 enum BinOp : uint16_t { B_MOV = 0, B_ADD, B_SUB, B_BUS, B_MUL, B_DIV, B_VID, B_MIN, B_MAX, B_SEL, B_ADDPROD, B_ACCRUE, B_DISCOUNT };
 constexpr uint16_t A_BIN = 0x100;   // AIns::op = A_BIN | BinOp for binary instructions, a plain TapeOp otherwise
 constexpr uint16_t A_EXT = 0x200;   // extension word of the two-word instruction before it: y = second immediate
@@ -493,6 +493,43 @@ struct Gen {
             }
             A.push_back(a);
         }
+        // third pass: one dispatch per LMM drift term / state update (at ~1 chunk per warp the interpreter runs at the latency of
+        // a lone warp: ~130 cycles per dispatch whatever the handler does, so the number of dispatches is what counts)
+        //   MOV x ; RATIO a, b, c, d ; ACCUM_S r                        -> RATIOACC x, a, b, c, d | r
+        //   MULADDMUL a, b, c ; ADD x ; ADDPROD w, d ; STG p            -> AXPYST x, a, b, c, d | w, p, (reload)
+        if (rt.opt.fuse_ops2) {
+            out.swap(A);
+            A.clear();
+            auto is_src = [](const AIns& t) { return t.kind == K_REG || t.kind == K_LEAF; };
+            for (size_t i = 0; i < out.size(); i++) {
+                const AIns& a = out[i];
+                if (a.op == (A_BIN | B_MOV) && is_src(a) && i + 4 < out.size() && out[i + 1].op == T_RATIO && out[i + 2].op == A_EXT && out[i + 3].op == A_EXT
+                    && out[i + 4].op == T_ACCUM_S && out[i + 4].kind == K_REG && !(a.kind == K_REG && a.arg == out[i + 4].arg)) {
+                    const AIns& r = out[i + 1];
+                    A.push_back(mk((uint16_t)T_RATIOACC_S, a.kind, a.arg, r.y, r.src, 0));
+                    A.push_back(mk(A_EXT, K_NONE, 0, (uint32_t)r.arg, r.src2));
+                    A.push_back(out[i + 2]);
+                    A.push_back(mk(A_EXT, K_REG, out[i + 4].arg, out[i + 3].y, out[i + 3].src));
+                    i += 4;
+                    continue;
+                }
+                if (a.op == T_MULADDMUL && i + 4 < out.size() && out[i + 1].op == A_EXT && out[i + 2].op == (A_BIN | B_ADD) && is_src(out[i + 2])
+                    && out[i + 3].op == (A_BIN | B_ADDPROD) && is_src(out[i + 3]) && out[i + 4].op == T_STG
+                    && !(out[i + 2].kind == out[i + 3].kind && out[i + 2].arg == out[i + 3].arg)) {
+                    const AIns& x = out[i + 2];
+                    const AIns& w = out[i + 3];
+                    A.push_back(mk((uint16_t)T_AXPYST_S, x.kind, x.arg, a.y, a.src, 0));
+                    A.push_back(mk(A_EXT, K_NONE, 0, (uint32_t)a.arg, a.src2));
+                    A.push_back(out[i + 1]);
+                    A.push_back(mk(A_EXT, w.kind, w.arg, w.y, w.src));
+                    A.push_back(mk(A_EXT, K_NONE, 0, out[i + 4].y, -1));
+                    A.push_back(mk(A_EXT, K_RELOAD, 0, 0xffffffffu, -1));
+                    i += 4;
+                    continue;
+                }
+                A.push_back(a);
+            }
+        }
         n_leaf_refs = leaf_refs;
     }
 
@@ -546,64 +583,123 @@ struct Gen {
             if (pipeline) pro_leaf[s] = ev[e].leaf;
         }
         // 3. walk the code
-        int refill_after_ext = -1, ext_left = 0;
+        // make sure event e sits in a ring slot (its T_LOAD has been emitted)
+        auto ensure_issued = [&](int e) {
+            if (ev[e].slot >= 0) return;
+            // not issued yet and no slot was free in time: take the slot whose occupant is needed last
+            // (while an event is waiting in the queue every slot is occupied: freed slots are refilled at once)
+            int vs = -1; int32_t far = -1;
+            for (uint32_t s = 0; s < R; s++) {
+                const int o = slot_ev[s];
+                if (o < 0) continue;
+                const int32_t nu = ev[o].use[ev[o].k];
+                if (nu > far) { far = nu; vs = (int)s; }
+            }
+            if (vs < 0) fail(FMC_ERR_UNSUPPORTED, "internal: no ring slot to evict");
+            const int o = slot_ev[vs];
+            {
+                if (!ev[o].waited) body.push_back(enc_idx(T_WAIT, (uint32_t)vs, 0, shift));
+                // the evicted occupant's remaining uses become a new event, queued by its next use
+                Event rest; rest.leaf = ev[o].leaf;
+                rest.use.assign(ev[o].use.begin() + (long)ev[o].k, ev[o].use.end());
+                ev[o].use.resize(ev[o].k);
+                const int ne = (int)ev.size();
+                ev.push_back(std::move(rest));
+                map_uses(ne);
+                size_t at = q;
+                while (at < order.size() && ev[order[at]].use[0] < ev[ne].use[0]) at++;
+                order.insert(order.begin() + (long)at, ne);
+            }
+            // e is somewhere in the queue (normally its head): take it out
+            for (size_t k = q; k < order.size(); k++) if (order[k] == e) { order.erase(order.begin() + (long)k); break; }
+            issue(body, e, vs);
+        };
+        // what has to happen once the extension words of the instruction being emitted are out: ring slots whose last use it
+        // was are refilled (their T_LOAD must not separate an instruction from its extension words)
+        struct Pending { int ext_left; int slot; bool append; uint32_t value; };
+        std::vector<Pending> pending;
+        uint32_t fused_reload = 0xffffffffu;     // pointer-table slot for the K_RELOAD word of the instruction being emitted
+        auto after_word = [&]() {
+            for (size_t k = 0; k < pending.size();) {
+                if (--pending[k].ext_left > 0) { k++; continue; }
+                const Pending pd = pending[k];
+                pending.erase(pending.begin() + (long)k);
+                if (pd.append) body.push_back(TapeInstr{ T_END, pd.value });
+                else refill(pd.slot);
+            }
+        };
+        // the slot's last use is a form that can re-arm it itself: take the next event off the queue without emitting a T_LOAD
+        auto take_reload = [&](int s, uint32_t& ptr) -> bool {
+            if (q >= order.size()) return false;
+            const int e = order[q++];
+            ev[e].slot = s; ev[e].waited = false; slot_ev[s] = e;
+            ptr = (uint32_t)info[ev[e].leaf].slot;
+            return true;
+        };
         for (int32_t i = 0; i < (int32_t)A.size(); i++) {
             const AIns& a = A[i];
-            if (a.kind == K_LEAF) {
-                const int e = ev_at[i];
-                if (ev[e].slot < 0) {
-                    // not issued yet and no slot was free in time: take the slot whose occupant is needed last
-                    // (while an event is waiting in the queue every slot is occupied: freed slots are refilled at once)
-                    int vs = -1; int32_t far = -1;
-                    for (uint32_t s = 0; s < R; s++) {
-                        const int o = slot_ev[s];
-                        if (o < 0) continue;
-                        const int32_t nu = ev[o].use[ev[o].k];
-                        if (nu > far) { far = nu; vs = (int)s; }
+            int n_ext = 0;
+            if (a.op != A_EXT) while (i + 1 + n_ext < (int32_t)A.size() && A[i + 1 + n_ext].op == A_EXT) n_ext++;
+            if (a.op == A_EXT) {
+                uint32_t x = T_END, y = a.y;
+                if (a.kind == K_REG) x |= (R + (uint32_t)a.arg) << shift;
+                else if (a.kind == K_RELOAD) y = fused_reload;
+                else if (a.kind == K_LEAF) {
+                    Event& E2 = ev[ev_at[i]];
+                    x |= (uint32_t)E2.slot << shift;
+                    E2.k++;
+                    if (E2.k >= E2.use.size()) {
+                        int left = 1;                                      // this word and the extension words still to come
+                        for (int32_t j = i + 1; j < (int32_t)A.size() && A[j].op == A_EXT; j++) left++;
+                        pending.push_back(Pending{left, E2.slot, false, 0u});
                     }
-                    if (vs < 0) fail(FMC_ERR_UNSUPPORTED, "internal: no ring slot to evict");
-                    const int o = slot_ev[vs];
-                    {
-                        if (!ev[o].waited) body.push_back(enc_idx(T_WAIT, (uint32_t)vs, 0, shift));
-                        // the evicted occupant's remaining uses become a new event, queued by its next use
-                        Event rest; rest.leaf = ev[o].leaf;
-                        rest.use.assign(ev[o].use.begin() + (long)ev[o].k, ev[o].use.end());
-                        ev[o].use.resize(ev[o].k);
-                        const int ne = (int)ev.size();
-                        ev.push_back(std::move(rest));
-                        map_uses(ne);
-                        size_t at = q;
-                        while (at < order.size() && ev[order[at]].use[0] < ev[ne].use[0]) at++;
-                        order.insert(order.begin() + (long)at, ne);
-                    }
-                    // e is somewhere in the queue (normally its head): take it out
-                    for (size_t k = q; k < order.size(); k++) if (order[k] == e) { order.erase(order.begin() + (long)k); break; }
-                    issue(body, e, vs);
                 }
+                body.push_back(TapeInstr{ x, y });
+                note(a);
+                after_word();
+            } else if (a.kind == K_LEAF) {
+                const int e = ev_at[i];
+                ensure_issued(e);
+                // second operands of the fused forms travel in extension words: in their slot and waited for before the instruction
+                for (int32_t j = i + 1; j <= i + n_ext; j++) {
+                    if (A[j].kind != K_LEAF) continue;
+                    const int e2 = ev_at[j];
+                    ensure_issued(e2);
+                    if (!ev[e2].waited) { body.push_back(enc_idx(T_WAIT, (uint32_t)ev[e2].slot, 0, shift)); ev[e2].waited = true; }
+                }
+                if (ev_at[i] != e || ev[e].slot < 0) fail(FMC_ERR_UNSUPPORTED, "internal: operand evicted by the second operand of its own instruction");
                 Event& E = ev[e];
+                if (a.op == T_AXPYST_S && !E.waited) { body.push_back(enc_idx(T_WAIT, (uint32_t)E.slot, 0, shift)); E.waited = true; }
                 const uint32_t fl = E.waited ? 1u : 2u;        // _S / _W
                 E.waited = true;
-                const uint32_t opc = (a.op == T_ADDAFF_S) ? (fl == 1u ? (uint32_t)T_ADDAFF_S : (uint32_t)T_ADDAFF_W)
-                                   : (a.op == T_ADDAFFDISC_S) ? (fl == 1u ? (uint32_t)T_ADDAFFDISC_S : (uint32_t)T_ADDAFFDISC_W)
-                                                          : T_BIN0 + 3u * (uint32_t)(a.op & 0xff) + fl;
-                body.push_back(TapeInstr{ opc | ((uint32_t)E.slot << shift), a.y });
+                const bool last = E.k + 1 >= E.use.size();
+                uint32_t opc, reload_ptr = 0xffffffffu;
+                bool append_reload = false;
+                fused_reload = 0xffffffffu;
+                if (a.op == T_ADDAFF_S) opc = fl == 1u ? (uint32_t)T_ADDAFF_S : (uint32_t)T_ADDAFF_W;
+                else if (a.op == T_ADDAFFDISC_S) {
+                    if (last && rt.opt.fuse_ops2 && take_reload(E.slot, reload_ptr)) { opc = fl == 1u ? (uint32_t)T_ADDAFFDISC_SL : (uint32_t)T_ADDAFFDISC_WL; append_reload = true; }
+                    else opc = fl == 1u ? (uint32_t)T_ADDAFFDISC_S : (uint32_t)T_ADDAFFDISC_W;
+                }
+                else if (a.op == T_RATIOACC_S) opc = fl == 1u ? (uint32_t)T_RATIOACC_S : (uint32_t)T_RATIOACC_W;
+                else if (a.op == T_AXPYST_S) { opc = (uint32_t)T_AXPYST_S; if (last && take_reload(E.slot, reload_ptr)) fused_reload = reload_ptr; }
+                else opc = T_BIN0 + 3u * (uint32_t)(a.op & 0xff) + fl;
+                const int slot_used = E.slot;
+                body.push_back(TapeInstr{ opc | ((uint32_t)slot_used << shift), a.y });
                 note(a);
-                E.k++;
-                // a two-word instruction keeps its extension word right behind it: the slot is refilled after that word
-                if (E.k >= E.use.size()) {
-                    if (a.op == T_ADDAFF_S) { refill_after_ext = E.slot; ext_left = 1; }
-                    else if (a.op == T_ADDAFFDISC_S) { refill_after_ext = E.slot; ext_left = 2; }
-                    else refill(E.slot);
+                ev[e].k++;
+                // a multi-word instruction keeps its extension words right behind it: the slot is refilled after them
+                if (last) {
+                    if (append_reload) pending.push_back(Pending{n_ext, slot_used, true, reload_ptr});
+                    else if (reload_ptr != 0xffffffffu) { /* re-armed by the instruction itself */ }
+                    else if (n_ext > 0) pending.push_back(Pending{n_ext, slot_used, false, 0u});
+                    else refill(slot_used);
                 }
             } else if (a.op & A_BIN) {
                 const uint32_t bop = T_BIN0 + 3u * (uint32_t)(a.op & 0xff);
                 if (a.kind == K_IMM) body.push_back(TapeInstr{ bop, a.y });
                 else body.push_back(TapeInstr{ (bop + 1u) | ((R + (uint32_t)a.arg) << shift), a.y });
                 note(a);
-            } else if (a.op == A_EXT) {
-                body.push_back(TapeInstr{ T_END, a.y });                  // only its y is read
-                note(a);
-                if (refill_after_ext >= 0 && --ext_left == 0) { refill(refill_after_ext); refill_after_ext = -1; }
             } else if (a.op == T_MULADD_II || a.op == T_ADDMUL_II || a.op == T_MULADDMUL || a.op == T_RATIO) {
                 body.push_back(TapeInstr{ (uint32_t)a.op, a.y });
                 note(a);
@@ -614,11 +710,20 @@ struct Gen {
                 if (a.kind == K_REG) body.push_back(TapeInstr{ T_END | ((R + (uint32_t)a.arg) << shift), 1u });
                 else body.push_back(TapeInstr{ T_END, 0u });
             } else {
+                // (the fused forms with their first operand in the register file land here too: _S with a register-file slot)
+                for (int32_t j = i + 1; j <= i + n_ext; j++) {
+                    if (A[j].kind != K_LEAF) continue;
+                    const int e2 = ev_at[j];
+                    ensure_issued(e2);
+                    if (!ev[e2].waited) { body.push_back(enc_idx(T_WAIT, (uint32_t)ev[e2].slot, 0, shift)); ev[e2].waited = true; }
+                }
+                fused_reload = 0xffffffffu;
                 const uint32_t slot = (a.kind == K_REG) ? R + (uint32_t)a.arg : 0u;
                 body.push_back(TapeInstr{ (uint32_t)a.op | (slot << shift), a.y });
                 if (a.op != T_STG && a.op != T_STGS) note(a);
             }
         }
+        if (!pending.empty()) fail(FMC_ERR_UNSUPPORTED, "internal: extension words missing behind a multi-word instruction");
         if (pipeline) for (uint32_t s = 0; s < R; s++)
             if (pro_leaf[s] >= 0 && !loadn_done[s]) fail(FMC_ERR_UNSUPPORTED, "internal: ring slot %u not re-armed", s);
     }
@@ -759,7 +864,7 @@ struct Gen {
             }
         if (rt.opt.profile) rt.profile_begin();
         const auto t_launch0 = std::chrono::steady_clock::now();
-        FMC_CUDA(launch_tape(P, kp.grid, kp.n_warps, rt.stream));
+        FMC_CUDA(launch_tape(P, kp.grid, kp.n_warps, rt.stream, rt.opt.tape_upload_stream ? rt.copy_stream : nullptr));
         rt.hostprof.launch += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_launch0).count();
         if (rt.opt.profile) rt.profile_end(4ull * (uint64_t)n * (uint64_t)(kp.n_leaf_slots + kp.n_result_stores), 4ull * (uint64_t)n * (uint64_t)kp.ptr_local.size());
         rt.stats.n_kernels++; rt.stats.n_tape_kernels++; rt.stats.n_tape_instr += (uint64_t)kp.n_instr;

@@ -8,7 +8,8 @@
 namespace fmc {
 
 // tape_launch.cu + tape_kernel_e16/8/4.cu (one body: tape_interp.cuh)
-cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t stream);   // n_warps per CTA: 1..TAPE_MAX_WARPS; geometry: P.elems
+// n_warps per CTA: 1..TAPE_MAX_WARPS; geometry: P.elems; a tape too long for the inline argument block is uploaded on copy_stream (nullptr: on stream)
+cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t stream, cudaStream_t copy_stream);
 cudaError_t tape_kernel_setup(size_t* max_smem_per_cta);   // opts the kernels in to the device's full shared memory, allocates the tape ring
 void tape_kernel_teardown();
 size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots, int n_sets, int n_warps, int elems);   // dynamic shared memory of one CTA

@@ -2,6 +2,7 @@
 // (the scheduler / code generator that turns pending nodes into interpreter tapes is in codegen.cpp)
 #include <algorithm>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <chrono>
 #include <cstring>
@@ -217,6 +218,7 @@ void Runtime::profile_begin() {
 void Runtime::profile_end(uint64_t algorithmic_bytes, uint64_t touched_bytes) {
     FMC_CUDA(cudaEventRecord(prof_events[prof_used].second, stream));
     prof_used++;
+    prof_launch_bytes.push_back(algorithmic_bytes);
     prof_bytes += algorithmic_bytes;
     prof_touched += touched_bytes ? touched_bytes : algorithmic_bytes;
     prof_launches++;
@@ -224,11 +226,16 @@ void Runtime::profile_end(uint64_t algorithmic_bytes, uint64_t touched_bytes) {
 void Runtime::profile_read(double* ms, uint64_t* bytes, uint64_t* launches) {
     FMC_CUDA(cudaStreamSynchronize(stream));
     double total = 0.0;
+    static const char* dump = std::getenv("FMC_PROFILE_DUMP");       // development aid: one line per launch (microseconds, algorithmic bytes)
+    FILE* df = dump ? std::fopen(dump, "a") : nullptr;
     for (size_t i = 0; i < prof_used; i++) {
         float t = 0.f;
         FMC_CUDA(cudaEventElapsedTime(&t, prof_events[i].first, prof_events[i].second));
         total += t;
+        if (df) std::fprintf(df, "%zu %.2f %llu\n", i, 1e3 * (double)t, (unsigned long long)(i < prof_launch_bytes.size() ? prof_launch_bytes[i] : 0));
     }
+    if (df) { std::fprintf(df, "# read\n"); std::fclose(df); }
+    prof_launch_bytes.clear();
     if (ms) *ms = total;
     if (bytes) *bytes = prof_bytes;
     if (launches) *launches = prof_launches;

@@ -121,9 +121,11 @@ struct Options {
     int tape_elems = 0;             // chunk geometry: elements per lane, 16 / 8 / 4; 0 = chosen per launch from the vector length
     int min_warps = 24;             // ... the largest geometry that still gives every SM this many warps of work
     bool fuse_ops = true;           // peephole fusion of the abstract code (MULADD_II, ACCUM_S, ADDPROD)
+    bool fuse_ops2 = true;          // ... and the one-dispatch forms on top of it (RATIOACC, AXPYST, ADDAFFDISC with its slot's reload)
     int grid_limit = 0;             // > 0: cap the interpreter grid (tests: many chunks per warp at small sizes)
     int max_regs = 8;               // register-file slots the code generator may use, <= TAPE_REGS. Measured on the LMM step: 16 slots
                                     // let a few kernels drop to one CTA per SM (8.36 ms simulation); 8: 8.14 ms, 4: 8.00 ms but more spills
+    bool tape_upload_stream = true; // long tapes reach the device through the copy stream, ahead of the kernels queued on the compute stream
     bool tape_cache = true;         // replay the launches of a cone whose structure was lowered before (codegen.cpp)
 };
 
@@ -221,6 +223,7 @@ public:
     // profile mode: event pairs around interpreter launches + their algorithmic bytes
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
+    std::vector<uint64_t> prof_launch_bytes;               // algorithmic bytes of each launch since the last read
     uint64_t prof_bytes = 0, prof_launches = 0, prof_touched = 0;   // touched: every vector a kernel reads or writes, re-reads of earlier results included
     void profile_begin();                                  // records the start event of the next launch
     void profile_end(uint64_t algorithmic_bytes, uint64_t touched_bytes = 0);

@@ -71,6 +71,13 @@ enum TapeOp : uint32_t {
     T_RATIO,         // acc = (imm3 / (acc * imm + imm2)) * imm4             (four words: p / (1 + L p) * sigma of an LMM drift term)
     T_ADDAFFDISC_S,  // acc = (acc + (slot + imm) * imm2) / (1 + slot * imm3) (three words: one swap period of a swaption)
     T_ADDAFFDISC_W,
+    T_ADDAFFDISC_SL, // the same (four words), then the ring slot is re-armed with this chunk of ptrs[y of the fourth word]: the slot's
+    T_ADDAFFDISC_WL, //   last use and the T_LOAD that follows it in one dispatch
+    T_RATIOACC_S,    // acc = (imm3 / (slot * imm + imm2)) * imm4 + slot2; slot2 = acc   (four words; the fourth word's x names slot2, a
+    T_RATIOACC_W,    //   register-file slot: one LMM drift term added to its running sum = MOV ; RATIO ; ACCUM_S)
+    T_AXPYST_S,      // acc = (acc * imm + imm2) * imm3 + slot + slot2 * imm4; ptrs[p] = acc; then slot is re-armed with ptrs[q] unless
+                     //   q == 0xffffffff   (six words: imm, imm2, imm3, imm4 | slot2, p, q: one LMM state update = MULADDMUL ; ADD_S ;
+                     //   ADDPROD_S ; STG and the T_LOAD behind the slot's last use)
     T_NUM_OPS
 };
 constexpr uint32_t T_BIN0 = 20;
@@ -79,7 +86,7 @@ constexpr uint32_t T_BIN0 = 20;
 //   MIN Math.min(acc, b)   MAX Math.max(acc, b)   (NaN propagating, -0 < +0)      SEL p ? acc : b
 //   ADDPROD  acc + b * s        ACCRUE  acc * (1 + b * s)        DISCOUNT  acc / (1 + b * s)     (_S/_W only)
 static_assert(T_MOV_I == T_BIN0, "binary opcode layout");
-static_assert(T_ADDMUL_II == T_BIN0 + 39 && T_ADDAFF_W == T_BIN0 + 41 && T_ADDAFFDISC_W == T_BIN0 + 45 && T_NUM_OPS == T_BIN0 + 46, "binary opcode layout");
+static_assert(T_ADDMUL_II == T_BIN0 + 39 && T_ADDAFF_W == T_BIN0 + 41 && T_ADDAFFDISC_W == T_BIN0 + 45 && T_AXPYST_S == T_BIN0 + 50 && T_NUM_OPS == T_BIN0 + 51, "binary opcode layout");
 
 enum ReduceMode : int {
     RM_NONE = 0,

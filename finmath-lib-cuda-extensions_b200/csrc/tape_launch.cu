@@ -41,11 +41,15 @@ constexpr size_t RING_SLOT_BYTES = RING_PTR_BYTES + sizeof(TapeInstr) * (TAPE_MA
 struct TapeRing {
     char* dev = nullptr; char* host = nullptr;
     cudaEvent_t ev[RING_SLOTS] = {nullptr}; bool used[RING_SLOTS] = {false};
+    cudaEvent_t ev_up[RING_SLOTS] = {nullptr};     // the slot's upload (on the copy stream) has finished
     unsigned next = 0;
 } g_ring;
 }  // namespace
 
-cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t stream) {
+// A long tape goes to the device through the COPY stream as soon as the host has it: the host runs several launches ahead of the
+// device, so the copy overlaps the kernels already queued on the compute stream, which only waits for the copy's event (a copy
+// on the compute stream itself would sit between two kernels: ~10 us of idle GPU per launch).
+cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t stream, cudaStream_t copy_stream) {
     const int E = P.elems;
     if (E != 16 && E != 8 && E != 4) return cudaErrorInvalidValue;
     if (n_warps < 1 || n_warps > TAPE_MAX_WARPS) return cudaErrorInvalidValue;
@@ -67,19 +71,29 @@ cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t
     char* h = g_ring.host + (size_t)slot * RING_SLOT_BYTES;
     char* d = g_ring.dev + (size_t)slot * RING_SLOT_BYTES;
     std::memcpy(h, P.ptrs, sizeof(float*) * (size_t)P.n_ptrs);
-    std::memcpy(h + RING_PTR_BYTES, P.instr, sizeof(TapeInstr) * (size_t)words);
-    cudaError_t e = cudaMemcpyAsync(d, h, RING_PTR_BYTES + sizeof(TapeInstr) * (size_t)words, cudaMemcpyHostToDevice, stream);
+    // pointer table and tape are adjacent in the slot when the table is packed to its real size
+    const size_t ptr_bytes = (sizeof(float*) * (size_t)P.n_ptrs + 15) & ~(size_t)15;
+    std::memcpy(h + ptr_bytes, P.instr, sizeof(TapeInstr) * (size_t)words);
+    cudaStream_t up = copy_stream ? copy_stream : stream;
+    cudaError_t e = cudaMemcpyAsync(d, h, ptr_bytes + sizeof(TapeInstr) * (size_t)words, cudaMemcpyHostToDevice, up);
     if (e != cudaSuccess) return e;
-    e = cudaEventRecord(g_ring.ev[slot], stream);
-    if (e != cudaSuccess) return e;
-    g_ring.used[slot] = true;
+    if (up != stream) {
+        e = cudaEventRecord(g_ring.ev_up[slot], up);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, g_ring.ev_up[slot], 0);
+        if (e != cudaSuccess) return e;
+    }
     TapeArgsDev a;
     a.h = static_cast<const TapeHeader&>(P);
     a.ptrs = reinterpret_cast<float* const*>(d);
-    a.instr = reinterpret_cast<const TapeInstr*>(d + RING_PTR_BYTES);
-    return E == 16 ? tape_launch_dev_e16(rk, a, grid, n_warps * 32, smem, stream)
-         : E == 8  ? tape_launch_dev_e8(rk, a, grid, n_warps * 32, smem, stream)
-                   : tape_launch_dev_e4(rk, a, grid, n_warps * 32, smem, stream);
+    a.instr = reinterpret_cast<const TapeInstr*>(d + ptr_bytes);
+    e = E == 16 ? tape_launch_dev_e16(rk, a, grid, n_warps * 32, smem, stream)
+      : E == 8  ? tape_launch_dev_e8(rk, a, grid, n_warps * 32, smem, stream)
+                : tape_launch_dev_e4(rk, a, grid, n_warps * 32, smem, stream);
+    if (e != cudaSuccess) return e;
+    e = cudaEventRecord(g_ring.ev[slot], stream);            // the slot is free again when this kernel has run
+    if (e != cudaSuccess) return e;
+    g_ring.used[slot] = true;
+    return cudaSuccess;
 }
 
 cudaError_t tape_kernel_setup(size_t* max_smem_per_cta) {
@@ -97,7 +111,10 @@ cudaError_t tape_kernel_setup(size_t* max_smem_per_cta) {
     if (!g_ring.dev) {
         e = cudaMalloc(&g_ring.dev, RING_SLOT_BYTES * RING_SLOTS);
         if (e == cudaSuccess) e = cudaMallocHost(&g_ring.host, RING_SLOT_BYTES * RING_SLOTS);
-        for (int i = 0; i < RING_SLOTS && e == cudaSuccess; i++) { e = cudaEventCreateWithFlags(&g_ring.ev[i], cudaEventDisableTiming); g_ring.used[i] = false; }
+        for (int i = 0; i < RING_SLOTS && e == cudaSuccess; i++) {
+            e = cudaEventCreateWithFlags(&g_ring.ev[i], cudaEventDisableTiming); g_ring.used[i] = false;
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_ring.ev_up[i], cudaEventDisableTiming);
+        }
         g_ring.next = 0;
     }
     return e;
@@ -106,7 +123,10 @@ cudaError_t tape_kernel_setup(size_t* max_smem_per_cta) {
 void tape_kernel_teardown() {
     if (g_ring.dev) cudaFree(g_ring.dev);
     if (g_ring.host) cudaFreeHost(g_ring.host);
-    for (int i = 0; i < RING_SLOTS; i++) if (g_ring.ev[i]) { cudaEventDestroy(g_ring.ev[i]); g_ring.ev[i] = nullptr; }
+    for (int i = 0; i < RING_SLOTS; i++) {
+        if (g_ring.ev[i]) { cudaEventDestroy(g_ring.ev[i]); g_ring.ev[i] = nullptr; }
+        if (g_ring.ev_up[i]) { cudaEventDestroy(g_ring.ev_up[i]); g_ring.ev_up[i] = nullptr; }
+    }
     g_ring.dev = nullptr; g_ring.host = nullptr;
 }
 

@@ -191,26 +191,55 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
                 pc++;
                 continue;
             }
-            if (op == T_MULADDMUL || op == T_RATIO || op == T_ADDAFFDISC_S || op == T_ADDAFFDISC_W) {
-                const int ext = (op == T_RATIO) ? 3 : 2;
+            if (op == T_MULADDMUL || op == T_RATIO || op == T_ADDAFFDISC_S || op == T_ADDAFFDISC_W || op == T_ADDAFFDISC_SL || op == T_ADDAFFDISC_WL
+                || op == T_RATIOACC_S || op == T_RATIOACC_W || op == T_AXPYST_S) {
+                const int ext = (op == T_AXPYST_S) ? 5 : (op == T_RATIO || op == T_ADDAFFDISC_SL || op == T_ADDAFFDISC_WL || op == T_RATIOACC_S || op == T_RATIOACC_W) ? 3 : 2;
                 if (pc + ext >= P.n_instr) bad("multi-word instruction at the end of the tape");
-                float im[4] = {imm, 0.f, 0.f, 0.f};
+                float im[6] = {imm, 0.f, 0.f, 0.f, 0.f, 0.f};
+                uint32_t ey[6] = {in.y, 0, 0, 0, 0, 0}, ex[6] = {0, 0, 0, 0, 0, 0};
                 for (int k = 1; k <= ext; k++) {
-                    if ((P.instr[pc + k].x) != T_END) bad("extension word %d of opcode %d is not a plain T_END word", k, (int)op);
+                    const bool names_slot = (k == 3) && (op == T_RATIOACC_S || op == T_RATIOACC_W || op == T_AXPYST_S);
+                    if ((P.instr[pc + k].x & ((1u << SHIFT) - 1u)) != T_END) bad("extension word %d of opcode %d carries an opcode", k, (int)op);
+                    if (!names_slot && P.instr[pc + k].x != T_END) bad("extension word %d of opcode %d is not a plain T_END word", k, (int)op);
                     std::memcpy(&im[k], &P.instr[pc + k].y, 4);
+                    ey[k] = P.instr[pc + k].y; ex[k] = P.instr[pc + k].x >> SHIFT;
                 }
                 if (op == T_MULADDMUL) {
                     for (int e = 0; e < C; e++) { float t = acc[e] * im[0]; t = t + im[1]; acc[e] = t * im[2]; }
                 } else if (op == T_RATIO) {
                     for (int e = 0; e < C; e++) { float t = acc[e] * im[0]; t = t + im[1]; t = im[2] / t; acc[e] = t * im[3]; }
+                } else if (op == T_RATIOACC_S || op == T_RATIOACC_W) {
+                    if (op == T_RATIOACC_W) w.wait(slot);
+                    const float* b = w.read(slot, chunk);
+                    const uint32_t s2 = ex[3];
+                    if ((int)s2 < P.n_ring) bad("T_RATIOACC accumulates into a ring slot");
+                    for (int e = 0; e < C; e++) { float t = b[e] * im[0]; t = t + im[1]; t = im[2] / t; acc[e] = t * im[3]; }
+                    const float* c2 = w.read(s2, chunk);
+                    for (int e = 0; e < C; e++) acc[e] = acc[e] + c2[e];
+                    std::memcpy(&w.slots[(size_t)s2 * C], acc, sizeof(float) * (size_t)C);
+                } else if (op == T_AXPYST_S) {
+                    const float* b = w.read(slot, chunk);
+                    for (int e = 0; e < C; e++) { float t = acc[e] * im[0]; t = t + im[1]; t = t * im[2]; acc[e] = t + b[e]; }
+                    const float* c2 = w.read(ex[3], chunk);          // read BEFORE the reload: the two operands never share a slot
+                    if (ex[3] == slot) bad("T_AXPYST with both operands in one slot");
+                    for (int e = 0; e < C; e++) { const float t = c2[e] * im[3]; acc[e] = acc[e] + t; }
+                    if ((int)ey[4] >= P.n_ptrs) bad("pointer index %d out of range", (int)ey[4]);
+                    float* dst = P.ptrs[ey[4]];
+                    stored.insert(dst);
+                    for (int e = 0; e < C && base + e < P.n; e++) dst[base + e] = acc[e];
+                    if (ey[5] != 0xffffffffu) {
+                        if ((int)slot >= P.n_ring) bad("T_AXPYST re-arms a slot outside the ring");
+                        w.load(slot, ey[5], chunk);
+                    }
                 } else {
-                    if (op == T_ADDAFFDISC_W) w.wait(slot);
+                    if (op == T_ADDAFFDISC_W || op == T_ADDAFFDISC_WL) w.wait(slot);
                     const float* b = w.read(slot, chunk);
                     for (int e = 0; e < C; e++) {
                         float t = b[e] + im[0]; t = t * im[1]; const float num = acc[e] + t;
                         float d = b[e] * im[2]; d = d + 1.0f;
                         acc[e] = num / d;
                     }
+                    if (op == T_ADDAFFDISC_SL || op == T_ADDAFFDISC_WL) w.load(slot, ey[3], chunk);
                 }
                 pc += ext;
                 continue;
@@ -336,6 +365,9 @@ void dump_tape(const TapeParams& P, int grid) {
         float imm; std::memcpy(&imm, &P.instr[i].y, 4);
         if (op == T_MULADDMUL) std::fprintf(stderr, "  %4d MULADDMUL %g\n", i, imm);
         else if (op == T_RATIO) std::fprintf(stderr, "  %4d RATIO %g\n", i, imm);
+        else if (op == T_ADDAFFDISC_SL || op == T_ADDAFFDISC_WL) std::fprintf(stderr, "  %4d ADDAFFDISC_%cL s%u %g\n", i, op == T_ADDAFFDISC_SL ? 'S' : 'W', slot, imm);
+        else if (op == T_RATIOACC_S || op == T_RATIOACC_W) std::fprintf(stderr, "  %4d RATIOACC_%c s%u %g\n", i, op == T_RATIOACC_S ? 'S' : 'W', slot, imm);
+        else if (op == T_AXPYST_S) std::fprintf(stderr, "  %4d AXPYST_S s%u %g\n", i, slot, imm);
         else if (op == T_ADDAFFDISC_S || op == T_ADDAFFDISC_W) std::fprintf(stderr, "  %4d ADDAFFDISC_%c s%u %g\n", i, op == T_ADDAFFDISC_S ? 'S' : 'W', slot, imm);
         else if (op == T_ADDMUL_II) std::fprintf(stderr, "  %4d ADDMUL_II %g\n", i, imm);
         else if (op == T_ADDAFF_S || op == T_ADDAFF_W) std::fprintf(stderr, "  %4d ADDAFF_%c s%u %g\n", i, op == T_ADDAFF_S ? 'S' : 'W', slot, imm);
@@ -349,7 +381,7 @@ void dump_tape(const TapeParams& P, int grid) {
 
 }  // namespace
 
-cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t) {
+cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t, cudaStream_t) {
     if (std::getenv("FMC_EMU_DUMP")) dump_tape(P, grid);
     static const bool noexec = std::getenv("FMC_EMU_NOEXEC") != nullptr;    // host-side profiling: launches cost nothing
     if (noexec) {
