@@ -119,7 +119,8 @@ struct Options {
     bool p2p_reduce = true;         // sharded runs: exchange reduction partials inside the kernel over NVLink peer memory (else NCCL)
     int cta_warps = 4;              // warps per interpreter CTA (1..TAPE_MAX_WARPS)
     int tape_elems = 0;             // chunk geometry: elements per lane, 16 / 8 / 4; 0 = chosen per launch from the vector length
-    int min_warps = 24;             // ... the largest geometry that still gives every SM this many warps of work
+    int min_warps = 5;              // ... the largest geometry that still gives every SM this many warps of work (measured on the LMM step: 16-element
+                                    // chunks win down to ~400 k paths, 8-element chunks below)
     bool fuse_ops = true;           // peephole fusion of the abstract code (MULADD_II, ACCUM_S, ADDPROD)
     bool fuse_ops2 = true;          // ... and the one-dispatch forms on top of it (RATIOACC, AXPYST, ADDAFFDISC with its slot's reload)
     int grid_limit = 0;             // > 0: cap the interpreter grid (tests: many chunks per warp at small sizes)
