@@ -887,7 +887,17 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
     if (epoch == 0) { for (auto& nd : nodes) nd.epoch = 0; epoch = 1; }
     stats.n_flushes++;
 
-    std::unique_ptr<PhaseTimer> ph(new PhaseTimer(0));
+    struct Phase {                       // FMC_HOST_PROFILE only: no allocation, no clock call otherwise
+        int id = -1; std::chrono::steady_clock::time_point t0;
+        void reset(int next) {
+            if (!g_phase.on) return;
+            const auto now = std::chrono::steady_clock::now();
+            if (id >= 0) g_phase.us[id] += std::chrono::duration<double, std::micro>(now - t0).count();
+            id = next; t0 = now;
+        }
+        ~Phase() { reset(-1); }
+    } ph;
+    ph.reset(0);
     // ---- 1. collect the cone of lazy nodes, in depth-first post-order from the targets ----
     // Post-order (operands first, each value as late as its first consumer allows) keeps few intermediates alive at a
     // time: e.g. an Euler step whose caller computed all 80 drifts before applying any of them is emitted component
@@ -909,6 +919,15 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
         }
     }
     Gen g(*this, n);
+    // the per-cone vectors keep their capacity from flush to flush (a calibration runs thousands of cones per second: growing
+    // them from empty every time was a sixth of the host time of a step)
+    static thread_local std::vector<Info> info_keep;
+    static thread_local std::vector<int32_t> use_keep;
+    struct Keep {
+        Gen& g; std::vector<Info>& i; std::vector<int32_t>& u;
+        Keep(Gen& g_, std::vector<Info>& i_, std::vector<int32_t>& u_) : g(g_), i(i_), u(u_) { i.clear(); u.clear(); g.info.swap(i); g.use_list.swap(u); }
+        ~Keep() { g.info.swap(i); g.use_list.swap(u); }
+    } keep(g, info_keep, use_keep);
     constexpr int32_t LEAF_BASE = 0x40000000;            // Node::local of a leaf until the cone size is known: LEAF_BASE + ordinal
     static thread_local std::vector<std::pair<int32_t, int>> stack;
     static thread_local std::vector<int32_t> leaf_nodes, leaf_uses;
@@ -1002,7 +1021,7 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
         else { g_cache.misses++; fresh.reset(new ConePlan); fresh->key = key; g.keep_plans = true; }
     }
     if (hit) {
-        ph.reset(); ph.reset(new PhaseTimer(5));
+        ph.reset(5);
         // buffers of the nodes this cone stores (or spills), all up front
         std::vector<float*> got;
         try {
@@ -1018,7 +1037,7 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
         for (int32_t L = 0; L < n_cone; L++) g.info[L].eph = (hit->node_flags[(size_t)L] & 2u) != 0;
         for (const KernelPlan& kp : hit->kernels) g.submit(kp, red ? red->param : 0.0, true);
     } else {
-    ph.reset(); ph.reset(new PhaseTimer(1));
+    ph.reset(1);
     // ---- 2. store / ephemeral classification (reverse topological order) ----
     for (int32_t L = n_cone - 1; L >= 0; L--) {
         Info& f = g.info[L];
@@ -1055,7 +1074,7 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
         if (target_local >= 0) add_use(target_local, n_cone);
     }
 
-    ph.reset(); ph.reset(new PhaseTimer(2));
+    ph.reset(2);
     // ---- 3. emit ----
     g.begin_kernel();
     for (int32_t L = 0; L < n_cone; L++) {
@@ -1087,7 +1106,7 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
     }
     }   // cache miss
 
-    ph.reset(); ph.reset(new PhaseTimer(6));
+    ph.reset(6);
     // ---- 4. bookkeeping: stored / spilled nodes become materialised and drop their operands ----
     for (int32_t L = 0; L < n_cone; L++) {
         Info& f = g.info[L];

@@ -149,10 +149,20 @@ int32_t Runtime::record(NodeOp op, int64_t n, Operand a, Operand b, Operand c) {
 void Runtime::retain(int32_t idx) { nodes[idx].ext_refs++; }
 
 void Runtime::maybe_free(int32_t first) {
-    // iterative cascade: freeing a lazy node releases its operands
-    std::vector<int32_t> work{first};
-    while (!work.empty()) {
-        const int32_t idx = work.back(); work.pop_back();
+    // iterative cascade: freeing a lazy node releases its operands (explicit stack: chains of a few thousand pending nodes are
+    // normal; the common cases — nothing to free, or one node — never touch the heap)
+    {
+        const Node& nd = nodes[first];
+        if (nd.state == NS_FREE || nd.ext_refs != 0 || nd.int_refs != 0) return;
+    }
+    int32_t small[16];
+    int n_small = 0;
+    std::vector<int32_t> big;
+    auto push = [&](int32_t v) { if (n_small < 16) small[n_small++] = v; else big.push_back(v); };
+    auto pop = [&]() -> int32_t { if (!big.empty()) { const int32_t v = big.back(); big.pop_back(); return v; } return small[--n_small]; };
+    push(first);
+    while (n_small > 0 || !big.empty()) {
+        const int32_t idx = pop();
         Node& nd = nodes[idx];
         if (nd.state == NS_FREE || nd.ext_refs != 0 || nd.int_refs != 0) continue;
         if (nd.state == NS_LAZY) {
@@ -160,7 +170,7 @@ void Runtime::maybe_free(int32_t first) {
             for (int k = 0; k < 3; k++) if (nd.in[k] >= 0) {
                 Node& in = nodes[nd.in[k]];
                 if (in.int_refs > 0) in.int_refs--;
-                work.push_back(nd.in[k]);
+                if (in.int_refs == 0 && in.ext_refs == 0) push(nd.in[k]);
             }
         } else if (nd.buf) {
             pool.free(nd.buf);
