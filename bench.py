@@ -124,6 +124,8 @@ def run_reference(args) -> None:
     paths_per_thread = args.ref_paths_per_thread
     total = cores * paths_per_thread
     models = [lib.lmm(total, N_PERIODS, DELTA, 1, SEED, 0, (i * paths_per_thread, (i + 1) * paths_per_thread)) for i in range(cores)]
+    for m in models:
+        m.use_market_curve()
     pool = ThreadPoolExecutor(cores)
 
     def step():
@@ -142,10 +144,21 @@ def run_reference(args) -> None:
     from oracle.workloads_oracle import driver_f64
     lib64 = driver_f64()
     models64 = [lib64.lmm(total, N_PERIODS, DELTA, 1, SEED, 0, (i * paths_per_thread, (i + 1) * paths_per_thread)) for i in range(cores)]
+    for m in models64:
+        m.use_market_curve()
     list(pool.map(lambda m: m.step(), models64))
     t0 = time.perf_counter()
     list(pool.map(lambda m: m.step(), models64))
     value64 = total * N_PERIODS / (time.perf_counter() - t0)
+    # the calibration as the reference test runs it: 10 000 paths, ONE thread (T-ATM:154,319), for a fixed budget of 2 iterations
+    calibration = None
+    if not args.no_calibration:
+        cm = lib.lmm(10000, N_PERIODS, DELTA, 1, SEED, 0)
+        cm.use_market_curve()
+        r2 = cm.calibrate(max_iterations=2)
+        calibration = {"t_atm_10k_paths_2_iterations": {"evaluations": r2["evaluations"], "seconds": r2["seconds"], "seconds_per_evaluation": r2["seconds_per_evaluation"],
+                                                        "cores": 1, "note": "single thread, like numberOfThreads = 1 in T-ATM:319"}}
+        cm.close()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -158,6 +171,7 @@ def run_reference(args) -> None:
         "cpu_double_array": {"value": value64, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{total} paths, 1 step; C++ restatement of finmath-lib's RandomVariableFromDoubleArray (not part of the ratio)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "calibration": calibration,
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -202,6 +216,7 @@ def run_ours(args) -> None:
     p0, p1 = rank * paths_per_gpu, (rank + 1) * paths_per_gpu
     lib = DriverLib()
     model = lib.lmm(total_paths, N_PERIODS, DELTA, 1, SEED, 0, (p0, p1))
+    model.use_market_curve()                                  # T-ATM:526-663 swap curve (idealised schedules), not a synthetic one
     if args.valuation_threads != 1:
         if world > 1:
             raise SystemExit("--valuation-threads > 1 is a single-rank option: sharded ranks must issue their reductions in one order")
@@ -284,6 +299,30 @@ def run_ours(args) -> None:
     st3 = fc.stats()
     pinned_ms = max_over_ranks(1e3 * pinned_s) / args.steps
 
+    # ---- the calibration itself (BASELINE.json metric: "LMM ATM calibration sec"): Levenberg-Marquardt with the settings of
+    # T-ATM:317-340 on the bench's model for a fixed budget of iterations, and on T-ATM's own 10 000 paths to convergence ----
+    calibration = None
+    if not args.no_calibration:
+        p_init = model.parameters()
+        barrier()
+        r = model.calibrate(max_iterations=args.calibration_iterations)
+        calibration = {"paths_per_gpu": paths_per_gpu, "paths_total": total_paths, "lm_iterations": r["iterations"], "evaluations": r["evaluations"],
+                       "seconds": max_over_ranks(r["seconds"]), "seconds_per_evaluation": r["seconds_per_evaluation"],
+                       "rms_error": r["rms_error"], "mean_deviation": r["mean_deviation"],
+                       "settings": "Levenberg-Marquardt, lambda 0.1, accuracy 1e-7, parameter step 1e-4, 48 parameters, 144 products, 1 thread (T-ATM:317-340)"}
+        model.set_parameters(p_init)
+        if world == 1:
+            cm = lib.lmm(10000, N_PERIODS, DELTA, 1, SEED, 0, (0, 10000))
+            cm.use_market_curve()
+            r2 = cm.calibrate(max_iterations=2)
+            calibration["t_atm_10k_paths_2_iterations"] = {"evaluations": r2["evaluations"], "seconds": r2["seconds"], "seconds_per_evaluation": r2["seconds_per_evaluation"]}
+            r3 = cm.calibrate(max_iterations=200)
+            calibration["t_atm_10k_paths_to_convergence"] = {"iterations": r2["iterations"] + r3["iterations"], "evaluations": r2["evaluations"] + r3["evaluations"],
+                                                             "seconds": r2["seconds"] + r3["seconds"], "mean_deviation": r3["mean_deviation"],
+                                                             "rms_error": r3["rms_error"], "reference_bound": "|mean deviation| < 2e-4 (T-ATM:466)",
+                                                             "ok": bool(abs(r3["mean_deviation"]) < 2e-4)}
+            cm.close()
+
     # ---- the workload at the parity sample's size, on every rank's slice of the SAME global paths (compared with the oracle below) ----
     sample_values = None
     if not args.no_cpu_baseline:
@@ -292,6 +331,7 @@ def run_ours(args) -> None:
         per = (per + 3) // 4 * 4                                  # slice boundaries on multiples of 4 elements
         s0, s1 = min(sp, rank * per), min(sp, (rank + 1) * per)
         sm = lib.lmm(sp, N_PERIODS, DELTA, 1, SEED, 0, (s0, s1))
+        sm.use_market_curve()
         sample_values = sm.step()
         sm.close()
         barrier()
@@ -325,6 +365,7 @@ def run_ours(args) -> None:
         olib = driver()
         sample_paths = args.cpu_sample_paths if world == 1 else args.multi_gpu_check_paths
         om = olib.lmm(sample_paths, N_PERIODS, DELTA, 1, SEED, 0)
+        om.use_market_curve()
         t0 = time.perf_counter()
         ovalues = om.step()
         dt = time.perf_counter() - t0
@@ -348,7 +389,7 @@ def run_ours(args) -> None:
         "config": {"workload": "LIBORMarketModelCalibrationATMTest inner loop: LMM Euler simulation 80x80, 1 factor + 144 ATM swaptions",
                    "paths_per_gpu": paths_per_gpu, "paths_total": total_paths, "time_steps": N_PERIODS, "seed": SEED,
                    "parallelism": f"path-sharded x{world}", "valuation_threads": args.valuation_threads, "l2": "inputs larger than L2 (simulation state >> 126 MB)",
-                   "forward_curve": "synthetic", "wall_ms_per_step": wall_ms / args.steps},
+                   "forward_curve": "EUR swap curve of T-ATM:526-663 (idealised schedules)", "wall_ms_per_step": wall_ms / args.steps},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": st2["h2d_bytes"] // args.steps,
                 "d2h_bytes_per_step": st2["d2h_bytes"] // args.steps, "host_input_bytes": host_bytes,
                 "input": "pageable host double[] through createRandomVariable(time, double[]) (cast on host threads into pinned staging)"},
@@ -361,6 +402,7 @@ def run_ours(args) -> None:
         "nodes_stored_per_step": st["n_nodes_stored"] / args.steps, "nodes_fused_per_step": st["n_nodes_fused"] / args.steps,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "host_profile": host_prof,
         ("parity" if world == 1 else "multi_gpu_parity"): parity,
+        "calibration": calibration,
         "price_check": {"first_values": [float(v) for v in values[:3]], "e2e_equal": bool((values == values_e2e).all()),
                         "e2e_pinned_equal": bool((values == values_pinned).all())},
     }
@@ -383,6 +425,8 @@ def main():
                     help="N > 1: total paths of the sharded run that rank 0 compares with the CPU oracle (untimed)")
     ap.add_argument("--ref-paths-per-thread", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-calibration", action="store_true")
+    ap.add_argument("--calibration-iterations", type=int, default=1, help="Levenberg-Marquardt iterations of the calibration key (1 iteration = 50 simulations)")
     ap.add_argument("--valuation-threads", type=int, default=1,
                     help="host threads valuing the calibration products (the reference test uses 1, LIBORMarketModelCalibrationATMTest.java:319)")
     args = ap.parse_args()

@@ -258,6 +258,62 @@ int fmd_lmm_bermudan(void* handle, int first_exercise, int last_exercise, int st
         *value = bermudan_swaption_value(*h->last_model, spec, regression_fn());
     });
 }
+// initial forward rates and calibration products from the market curve of LIBORMarketModelCalibrationATMTest.java:526-663 instead of the synthetic one
+int fmd_lmm_use_market_curve(void* handle) {
+    return guarded([&] {
+        auto* h = static_cast<LmmHandle*>(handle);
+        const int n = (int)h->L0.size();
+        h->L0 = MarketCurveATM().forwardRates(n, h->delta);
+        h->products = atm_calibration_products(h->L0, h->delta, n);
+        h->last_model.reset();
+    });
+}
+int fmd_lmm_get_forward_rates(void* handle, double* out) {
+    auto* h = static_cast<LmmHandle*>(handle);
+    std::memcpy(out, h->L0.data(), sizeof(double) * h->L0.size());
+    return 0;
+}
+// The calibration of LIBORMarketModelCalibrationATMTest.java:317-358: Levenberg-Marquardt over the piecewise-constant volatility
+// parameters, objective = implied normal volatilities of the calibration swaptions (SwaptionSimple, VOLATILITYNORMAL) against
+// their market quotes; every evaluation is one simulation + valuation (fmd_lmm_step). params_out: calibrated parameters;
+// info_out[6]: iterations, evaluations, root mean squared error, mean deviation (model - target volatility), seconds, seconds per evaluation.
+int fmd_lmm_calibrate(void* handle, int max_iterations, double accuracy, double lambda, double parameter_step, double* params_out, double* info_out) {
+    return guarded([&] {
+        auto* h = static_cast<LmmHandle*>(handle);
+        const size_t nprod = h->products.size();
+        std::vector<double> target(nprod), annuity(nprod), maturity(nprod);
+        Curve curve(h->L0, h->delta);
+        for (size_t k = 0; k < nprod; k++) {
+            const SwaptionSpec& sp = h->products[k];
+            target[k] = sp.targetVolatility;
+            annuity[k] = curve.annuity(sp.exerciseIndex, sp.numberOfPeriods, h->delta);
+            maturity[k] = sp.exerciseIndex * h->delta;
+        }
+        const auto t0 = std::chrono::steady_clock::now();
+        auto objective = [&](const std::vector<double>& p) {
+            h->last_model.reset();
+            PiecewiseConstantVolatility vol = h->vol;
+            vol.param = p;
+            h->last_model.reset(new LIBORMarketModel(h->factory, h->device_brownian, h->L0, vol));
+            std::vector<double> v = lmm_value_products(*h->last_model, h->products, h->valuation_threads);
+            for (size_t k = 0; k < nprod; k++) v[k] = atm_normal_implied_vol(v[k], annuity[k], maturity[k]);
+            return v;
+        };
+        const LevenbergMarquardtResult r = levenberg_marquardt(objective, h->vol.param, target, max_iterations, accuracy, lambda, parameter_step);
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        h->vol.param = r.parameters;
+        std::memcpy(params_out, r.parameters.data(), sizeof(double) * r.parameters.size());
+        double dev = 0.0;
+        for (size_t k = 0; k < nprod; k++) dev += r.values[k] - target[k];
+        info_out[0] = r.iterations; info_out[1] = r.evaluations; info_out[2] = r.rootMeanSquaredError; info_out[3] = dev / (double)nprod;
+        info_out[4] = secs; info_out[5] = secs / std::max(1, r.evaluations);
+    });
+}
+int fmd_lmm_set_parameters(void* handle, const double* params) {
+    auto* h = static_cast<LmmHandle*>(handle);
+    std::memcpy(h->vol.param.data(), params, sizeof(double) * h->vol.param.size());
+    return 0;
+}
 int fmd_lmm_simulate(void* handle) {
     return guarded([&] {
         auto* h = static_cast<LmmHandle*>(handle);

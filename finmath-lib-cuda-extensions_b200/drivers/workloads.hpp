@@ -266,6 +266,144 @@ inline std::vector<double> synthetic_forward_rates(int n, double delta) {
     return L;
 }
 
+// The EUR curve of LIBORMarketModelCalibrationATMTest.java:526-663: a single discount curve (log-linear interpolation of the
+// discount factors, constant extrapolation) calibrated to 21 par swap rates, fixed leg annual against 6M floating, and the 6M
+// forward curve derived from it. finmath-lib's schedule generator, business-day calendar and day-count conventions are not
+// part of the reference tree: the schedules are idealised here (year fractions = period lengths, no spot lag), the pillars sit
+// at the swap maturities, and each pillar is solved in turn (the curve left of a pillar does not depend on it), which is what
+// the library's multi-dimensional solver converges to for this triangular system. The hot path only sees the resulting
+// initial forward rates.
+struct MarketCurveATM {
+    std::vector<double> pillarT{0.0}, pillarLogDF{0.0};
+    double logDF(double t) const {
+        if (t <= 0.0) return 0.0;
+        if (t >= pillarT.back()) return pillarLogDF.back();                         // ExtrapolationMethod.CONSTANT (T-ATM:612)
+        size_t k = 1;
+        while (pillarT[k] < t) k++;
+        const double w = (t - pillarT[k - 1]) / (pillarT[k] - pillarT[k - 1]);
+        return (1.0 - w) * pillarLogDF[k - 1] + w * pillarLogDF[k];                  // InterpolationEntity.LOG_OF_VALUE, LINEAR (T-ATM:600-613)
+    }
+    double discountFactor(double t) const { return std::exp(logDF(t)); }
+    MarketCurveATM() {
+        static const double maturity[] = {0.5, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 15, 20, 25, 30, 35, 40, 45, 50};          // T-ATM:527
+        static const double rates[] = {-0.00216, -0.00208, -0.00222, -0.00216, -0.0019, -0.0014, -0.00072, 0.00011, 0.00103, 0.00196, 0.00285,
+                                       0.00367, 0.0044, 0.00604, 0.00733, 0.00767, 0.00773, 0.00765, 0.00752, 0.007138, 0.007};    // T-ATM:532
+        for (int i = 0; i < 21; i++) {
+            const double T = maturity[i], S = rates[i];
+            pillarT.push_back(T); pillarLogDF.push_back(pillarLogDF.back());
+            // par condition of a swap from 0 to T, single curve: 1 - P(T) = S * sum_j tau_j P(t_j), fixed payments yearly (one stub of T < 1)
+            auto f = [&](double x) {
+                pillarLogDF.back() = x;
+                double annuity = 0.0;
+                if (T < 1.0) annuity = T * discountFactor(T);
+                else for (int j = 1; j <= (int)std::lround(T); j++) annuity += discountFactor((double)j);
+                return 1.0 - discountFactor(T) - S * annuity;
+            };
+            double lo = pillarLogDF[pillarLogDF.size() - 2] - 1.0, hi = pillarLogDF[pillarLogDF.size() - 2] + 1.0;      // f is increasing in -x
+            for (int it = 0; it < 200; it++) { const double mid = 0.5 * (lo + hi); if (f(mid) > 0.0) lo = mid; else hi = mid; }
+            pillarLogDF.back() = 0.5 * (lo + hi);
+        }
+    }
+    // ForwardCurveFromDiscountCurve(discountCurve, "6M"): L(T_i) = (P(T_i) / P(T_i + delta) - 1) / delta
+    std::vector<double> forwardRates(int n, double delta) const {
+        std::vector<double> L((size_t)n);
+        for (int i = 0; i < n; i++) L[(size_t)i] = (discountFactor(i * delta) / discountFactor((i + 1) * delta) - 1.0) / delta;
+        return L;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// net.finmath.optimizer.LevenbergMarquardt as LIBORMarketModelCalibrationATMTest.java:317-340 configures it
+// (RegularizationMethod.LEVENBERG, lambda 0.1, <= 200 iterations, accuracy 1e-7 on the change of the root mean squared error,
+// ONE thread, finite-difference derivatives with parameterStep 1e-4): restated from the library's published algorithm
+// (finmath-lib 5.1.3 is an un-vendored dependency). One iteration = one evaluation of the objective at the trial point and,
+// after an accepted step, #parameters more for the forward-difference Jacobian — every evaluation is one full Monte-Carlo
+// simulation + valuation of all calibration products: the hot path.
+// ---------------------------------------------------------------------------------------------------------------------
+struct LevenbergMarquardtResult {
+    std::vector<double> parameters, values;
+    int iterations = 0, evaluations = 0;
+    double rootMeanSquaredError = 0.0;
+};
+
+inline LevenbergMarquardtResult levenberg_marquardt(const std::function<std::vector<double>(const std::vector<double>&)>& objective,
+                                                    std::vector<double> initialParameters, const std::vector<double>& targetValues,
+                                                    int maxIteration, double errorTolerance, double lambda, double parameterStep) {
+    const size_t np = initialParameters.size(), nv = targetValues.size();
+    const double lambdaDivisor = 1.3, lambdaMultiplicator = 2.0;
+    LevenbergMarquardtResult res;
+    auto meanSquaredError = [&](const std::vector<double>& v) {
+        double e = 0.0;
+        for (size_t k = 0; k < nv; k++) { const double d = v[k] - targetValues[k]; e += d * d; }      // weights 1 (T-ATM:262)
+        return e / (double)nv;
+    };
+    std::vector<double> parameterCurrent = initialParameters, parameterTest = initialParameters, valueCurrent(nv, NAN), valueTest;
+    std::vector<std::vector<double>> derivativeCurrent(np, std::vector<double>(nv, 0.0));
+    double errorMeanSquaredCurrent = INFINITY, errorRootMeanSquaredChange = INFINITY;
+    bool derivativeValid = false;
+    int iteration = 0;
+    for (;;) {
+        iteration++;
+        valueTest = objective(parameterTest); res.evaluations++;
+        const double errorMeanSquaredTest = meanSquaredError(valueTest);
+        if (errorMeanSquaredTest < errorMeanSquaredCurrent) {              // NaN compares false: a rejected point
+            errorRootMeanSquaredChange = std::sqrt(errorMeanSquaredCurrent) - std::sqrt(errorMeanSquaredTest);
+            parameterCurrent = parameterTest; valueCurrent = valueTest; errorMeanSquaredCurrent = errorMeanSquaredTest;
+            derivativeValid = false;
+            lambda /= lambdaDivisor;
+        } else {
+            errorRootMeanSquaredChange = std::sqrt(errorMeanSquaredTest) - std::sqrt(errorMeanSquaredCurrent);
+            lambda *= lambdaMultiplicator;
+        }
+        if (iteration > maxIteration || errorRootMeanSquaredChange <= errorTolerance) break;
+        if (!derivativeValid) {                                            // forward differences, one simulation per parameter
+            for (size_t i = 0; i < np; i++) {
+                std::vector<double> p = parameterCurrent;
+                p[i] += parameterStep;
+                const std::vector<double> v = objective(p); res.evaluations++;
+                for (size_t k = 0; k < nv; k++) derivativeCurrent[i][k] = (v[k] - valueCurrent[k]) / parameterStep;
+            }
+            derivativeValid = true;
+        }
+        // (J^T J + lambda I) delta = J^T (target - value), solved by Gaussian elimination with partial pivoting
+        std::vector<double> H(np * np), beta(np);
+        for (size_t i = 0; i < np; i++) {
+            double b = 0.0;
+            for (size_t k = 0; k < nv; k++) b += (targetValues[k] - valueCurrent[k]) * derivativeCurrent[i][k];
+            beta[i] = b;
+            for (size_t j = 0; j <= i; j++) {
+                double a = 0.0;
+                for (size_t k = 0; k < nv; k++) a += derivativeCurrent[i][k] * derivativeCurrent[j][k];
+                if (i == j) a += lambda;                                   // RegularizationMethod.LEVENBERG
+                H[i * np + j] = a; H[j * np + i] = a;
+            }
+        }
+        std::vector<double> delta = beta;
+        for (size_t c = 0; c < np; c++) {
+            size_t piv = c;
+            for (size_t r = c + 1; r < np; r++) if (std::fabs(H[r * np + c]) > std::fabs(H[piv * np + c])) piv = r;
+            if (piv != c) { for (size_t j = 0; j < np; j++) std::swap(H[c * np + j], H[piv * np + j]); std::swap(delta[c], delta[piv]); }
+            const double d = H[c * np + c];
+            if (d == 0.0) continue;
+            for (size_t r = c + 1; r < np; r++) {
+                const double m = H[r * np + c] / d;
+                if (m == 0.0) continue;
+                for (size_t j = c; j < np; j++) H[r * np + j] -= m * H[c * np + j];
+                delta[r] -= m * delta[c];
+            }
+        }
+        for (size_t c = np; c-- > 0;) {
+            double x = delta[c];
+            for (size_t j = c + 1; j < np; j++) x -= H[c * np + j] * delta[j];
+            delta[c] = H[c * np + c] != 0.0 ? x / H[c * np + c] : 0.0;
+        }
+        for (size_t i = 0; i < np; i++) parameterTest[i] = parameterCurrent[i] + delta[i];
+    }
+    res.parameters = parameterCurrent; res.values = valueCurrent; res.iterations = iteration;
+    res.rootMeanSquaredError = std::sqrt(errorMeanSquaredCurrent);
+    return res;
+}
+
 // one pass of the calibration inner loop: simulate the model, value every calibration product.
 // threads > 1: the products are valued by that many host threads (product k by thread k mod threads), the way the
 // library's calibration does with numberOfThreads > 1; the reference test runs with ONE thread (T-ATM:319), the default.

@@ -42,6 +42,10 @@ class DriverLib:
         L.fmd_lmm_implied_vols.argtypes = [vp, vp, vp]
         L.fmd_lmm_bermudan.argtypes = [vp, i32, i32, i32, i32, dbl, dp]
         L.fmd_lmm_simulate.argtypes = [vp]
+        L.fmd_lmm_use_market_curve.argtypes = [vp]
+        L.fmd_lmm_get_forward_rates.argtypes = [vp, vp]
+        L.fmd_lmm_set_parameters.argtypes = [vp, vp]
+        L.fmd_lmm_calibrate.argtypes = [vp, i32, dbl, dbl, dbl, vp, vp]
         L.fmd_lmm_set_valuation_threads.argtypes = [vp, i32]
         self.L = L
 
@@ -115,6 +119,31 @@ class Lmm:
             p = vp_.ctypes.data
         self.lib.check(self.lib.L.fmd_lmm_step(self.h, p, int(from_host), out.ctypes.data))
         return out
+
+    def use_market_curve(self) -> None:
+        """Initial forward rates from the EUR swap curve of LIBORMarketModelCalibrationATMTest.java:526-663 (instead of the synthetic curve)."""
+        self.lib.check(self.lib.L.fmd_lmm_use_market_curve(self.h))
+        self.n_products = self.lib.L.fmd_lmm_num_products(self.h)
+
+    def forward_rates(self) -> np.ndarray:
+        out = np.empty(self.n_periods)
+        self.lib.L.fmd_lmm_get_forward_rates(self.h, out.ctypes.data)
+        return out
+
+    def set_parameters(self, params) -> None:
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        assert p.size == self.n_parameters
+        self.lib.L.fmd_lmm_set_parameters(self.h, p.ctypes.data)
+
+    def calibrate(self, max_iterations: int = 200, accuracy: float = 1e-7, lmbda: float = 0.1, parameter_step: float = 1e-4) -> dict:
+        """Levenberg-Marquardt calibration of the volatility parameters to the ATM swaption quotes with the settings of
+        LIBORMarketModelCalibrationATMTest.java:317-340 by default. Every evaluation is one simulation + valuation of all products."""
+        params = np.empty(self.n_parameters)
+        info = np.empty(6)
+        self.lib.check(self.lib.L.fmd_lmm_calibrate(self.h, int(max_iterations), float(accuracy), float(lmbda), float(parameter_step),
+                                                    params.ctypes.data, info.ctypes.data))
+        return {"parameters": params, "iterations": int(info[0]), "evaluations": int(info[1]), "rms_error": float(info[2]),
+                "mean_deviation": float(info[3]), "seconds": float(info[4]), "seconds_per_evaluation": float(info[5])}
 
     def simulate(self) -> None:
         self.lib.check(self.lib.L.fmd_lmm_simulate(self.h))

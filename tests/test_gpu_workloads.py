@@ -68,3 +68,39 @@ def test_bermudan_swaption_matches_oracle(libs):
         vg, vc = mg.bermudan(*spec), mc.bermudan(*spec)
         assert vg > 0
         assert abs(vg - vc) <= 1e-4 * abs(vc), (spec, vg, vc)
+
+
+def test_lmm_parity_at_100k_paths_and_bermudan_at_200k(libs):
+    """The headline workload at sizes nearer the bench's (parity was only shown at 1 000 / 4 099 / 20 000 paths)."""
+    gpu, cpu = libs
+    mg, mc = gpu.lmm(100_000), cpu.lmm(100_000)
+    vg, vc = mg.step(), mc.step()
+    assert np.array_equal(mg.libor(80, 79), mc.libor(80, 79)) and np.array_equal(mg.libor(37, 52), mc.libor(37, 52))
+    assert np.max(np.abs(vg - vc) / np.abs(vc)) <= 1e-9
+    del mg, mc
+    mg, mc = gpu.lmm(200_000), cpu.lmm(200_000)
+    mg.simulate(); mc.simulate()
+    spec = (10, 30, 2, 40, 0.02)
+    vg, vc = mg.bermudan(*spec), mc.bermudan(*spec)
+    assert abs(vg - vc) <= 1e-4 * abs(vc), (vg, vc)
+
+
+def test_lmm_atm_calibration_matches_the_oracle_and_the_reference_bound(libs):
+    """BASELINE.json metric "LMM ATM calibration": LIBORMarketModelCalibrationATMTest.java:154-358 — 10 000 paths, one factor, seed
+    31415, Levenberg-Marquardt (lambda 0.1, accuracy 1e-7, parameter step 1e-4, one thread) over the 48 piecewise-constant
+    volatilities against the 144 in-horizon ATM swaption quotes, initial rates from the EUR swap curve of the test.
+    (a) the same optimiser source on the CUDA backend and on the CPU oracle, for a fixed budget of iterations: calibrated
+        parameters and mean deviation within 1e-4 relative (north star);
+    (b) the CUDA run carried to convergence: |mean deviation| < 2e-4, the reference's own pass criterion (T-ATM:466)."""
+    gpu, cpu = libs
+    mg, mc = gpu.lmm(10_000), cpu.lmm(10_000)
+    mg.use_market_curve(); mc.use_market_curve()
+    assert np.array_equal(mg.forward_rates(), mc.forward_rates()) and mg.n_products == mc.n_products == 144
+    rg, rc = mg.calibrate(max_iterations=2), mc.calibrate(max_iterations=2)
+    assert rg["iterations"] == rc["iterations"] and rg["evaluations"] == rc["evaluations"]
+    assert np.max(np.abs(rg["parameters"] - rc["parameters"]) / np.abs(rc["parameters"])) <= 1e-4
+    assert abs(rg["mean_deviation"] - rc["mean_deviation"]) <= 1e-4 * max(abs(rc["mean_deviation"]), 1e-4)
+    assert abs(rg["rms_error"] - rc["rms_error"]) <= 1e-4 * rc["rms_error"]
+    full = mg.calibrate(max_iterations=200)          # continues from the parameters reached above
+    assert abs(full["mean_deviation"]) < 2e-4, full
+    assert full["rms_error"] < 2e-4, full
