@@ -306,8 +306,8 @@ void merge_ranks(Runtime& rt, int mode, double part[3], bool already_global) {
             const double delta = bv - v, w = bc / tot;
             m = m + bm + delta * delta * c * w;
             v = v + delta * w;
-        } else if (mode == RM_MIN) v = (v != v || bv != bv) ? NAN : std::min(v, bv);
-        else if (mode == RM_MAX) v = (v != v || bv != bv) ? NAN : std::max(v, bv);
+        } else if (mode == RM_MIN) v = (v != v || bv != bv) ? NAN : (v == 0.0 && bv == 0.0) ? ((std::signbit(v) || std::signbit(bv)) ? -0.0 : 0.0) : std::min(v, bv);   // java.lang.Math.min: -0 < +0
+        else if (mode == RM_MAX) v = (v != v || bv != bv) ? NAN : (v == 0.0 && bv == 0.0) ? ((std::signbit(v) && std::signbit(bv)) ? -0.0 : 0.0) : std::max(v, bv);
         else v += bv;
         c = tot;
     }
@@ -383,7 +383,7 @@ int fmc_sync(void) {
 }
 static void set_option_locked(Runtime& rt, const char* key, double value) {
     // everything that steers the code generator invalidates the cached tapes
-    static const char* const keeps_cache[] = {"flush_threshold", "profile", "tape_upload_stream", "p2p_reduce", "zero_copy_reduce", "leaf_reduce_kernel"};
+    static const char* const keeps_cache[] = {"flush_threshold", "profile", "tape_upload_stream", "exchange", "exchange_timeout_s", "p2p_reduce", "zero_copy_reduce", "leaf_reduce_kernel"};
     bool keep = false;
     for (const char* k : keeps_cache) keep = keep || !std::strcmp(key, k);
     if (!keep) tape_cache_clear();
@@ -405,6 +405,8 @@ static void set_option_locked(Runtime& rt, const char* key, double value) {
     else if (!std::strcmp(key, "fuse_ops2")) rt.opt.fuse_ops2 = value != 0.0;
     else if (!std::strcmp(key, "tape_upload_stream")) rt.opt.tape_upload_stream = value != 0.0;
     else if (!std::strcmp(key, "p2p_reduce")) rt.opt.p2p_reduce = value != 0.0;
+    else if (!std::strcmp(key, "exchange")) { const int m = (int)value; if (m < 0 || m > 2) fail(FMC_ERR_INVALID, "exchange must be 0 (NCCL), 1 (in-kernel peer memory) or 2 (shared host memory)"); rt.opt.exchange = m; }
+    else if (!std::strcmp(key, "exchange_timeout_s")) rt.opt.exchange_timeout_s = std::max(1.0, value);
     else if (!std::strcmp(key, "zero_copy_reduce")) rt.opt.zero_copy_reduce = value != 0.0;
     else if (!std::strcmp(key, "leaf_reduce_kernel")) rt.opt.leaf_reduce_kernel = value != 0.0;
     else if (!std::strcmp(key, "cta_warps")) rt.opt.cta_warps = std::max(1, std::min((int)value, (int)TAPE_MAX_WARPS));
@@ -453,6 +455,9 @@ int fmc_get_option(const char* key, double* value) {
         else if (!std::strcmp(key, "fuse_ops2")) *value = rt.opt.fuse_ops2 ? 1.0 : 0.0;
         else if (!std::strcmp(key, "p2p_reduce")) *value = rt.opt.p2p_reduce ? 1.0 : 0.0;
         else if (!std::strcmp(key, "p2p_ready")) *value = rt.p2p_ready ? 1.0 : 0.0;
+        else if (!std::strcmp(key, "exchange")) *value = rt.opt.exchange;
+        else if (!std::strcmp(key, "exchange_timeout_s")) *value = rt.opt.exchange_timeout_s;
+        else if (!std::strcmp(key, "exchange_in_use")) *value = rt.use_xhost() ? 2.0 : rt.use_p2p() ? 1.0 : 0.0;
         else if (!std::strcmp(key, "device_index")) *value = rt.device;
         else if (!std::strcmp(key, "zero_copy_reduce")) *value = rt.opt.zero_copy_reduce ? 1.0 : 0.0;
         else if (!std::strcmp(key, "leaf_reduce_kernel")) *value = rt.opt.leaf_reduce_kernel ? 1.0 : 0.0;
@@ -532,7 +537,8 @@ int fmc_regression_normal_eq(const fmc_vec* basis, const double* scalars, int k,
         for (int32_t v : need) if (rt.nodes[v].state == NS_LAZY) lazy.push_back(v);
         if (!lazy.empty()) rt.run_cone(lazy, nullptr);
         const int m = k * (k + 1) / 2 + k;
-        if (n == 0) { for (int i = 0; i < k * k; i++) XtX[i] = NAN; for (int i = 0; i < k; i++) Xty[i] = NAN; return; }
+        auto all_nan = [&] { for (int i = 0; i < k * k; i++) XtX[i] = NAN; for (int i = 0; i < k; i++) Xty[i] = NAN; };
+        if (n == 0 && rt.comm_size == 1) { all_nan(); return; }
         P.n = n; P.k = k; P.y = rt.nodes[yi].buf;
         for (int i = 0; i < k; i++) {
             P.basis[i] = bidx[i] >= 0 ? rt.nodes[bidx[i]].buf : nullptr;
@@ -545,8 +551,9 @@ int fmc_regression_normal_eq(const fmc_vec* basis, const double* scalars, int k,
         const int64_t tiles = (n + regression_tile_elems() - 1) / regression_tile_elems();
         int grid = (int)std::min<int64_t>(tiles, (int64_t)per_sm * rt.sm_count);
         grid = std::max(1, std::min(grid, rt.max_grid));
-        FMC_CUDA(launch_regression(P, grid, rt.stream));
-        rt.stats.n_kernels++;
+        // an empty slice of a sharded vector contributes zeros and still joins the all-reduce (the other ranks are in it)
+        if (n > 0) { FMC_CUDA(launch_regression(P, grid, rt.stream)); rt.stats.n_kernels++; }
+        else FMC_CUDA(cudaMemsetAsync(rt.d_result + 64, 0, sizeof(double) * (size_t)m, rt.stream));
         double cnt = (double)n;
         if (rt.comm_size > 1) {
             // one all-reduce of the k(k+1)/2 + k sums plus the path count
@@ -556,6 +563,7 @@ int fmc_regression_normal_eq(const fmc_vec* basis, const double* scalars, int k,
         FMC_CUDA(cudaMemcpyAsync(rt.h_result + 64, rt.d_result + 64, sizeof(double) * (m + 1), cudaMemcpyDeviceToHost, rt.stream));
         FMC_CUDA(cudaStreamSynchronize(rt.stream));
         if (rt.comm_size > 1) cnt = rt.h_result[64 + m];
+        if (cnt == 0.0) { all_nan(); return; }
         const double* s = rt.h_result + 64;
         int t = 0;
         for (int i = 0; i < k; i++)

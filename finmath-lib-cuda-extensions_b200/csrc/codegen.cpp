@@ -847,13 +847,16 @@ struct Gen {
         P.result = rt.d_result;
         P.host_result = nullptr; P.ticket = 0.0;
         for (int r = 0; r < XMAX_RANKS; r++) P.xchg.tables[r] = nullptr;
+        P.xchg.host_table = nullptr;
         P.xchg.rank = 0; P.xchg.nranks = 1;
         if (kp.reduce_mode != RM_NONE) {
             rt.fill_exchange(P.xchg, &P.ticket);                                          // sharded run: ticket = the exchange's own sequence
             double* slot = rt.reduce_slot >= 0 ? rt.h_ticket_dev + 4 * rt.reduce_slot : nullptr;
-            if (P.xchg.nranks > 1) P.host_result = slot;
+            rt.last_tape_xhost = P.xchg.nranks > 1 && P.xchg.host_table != nullptr;
+            if (rt.last_tape_xhost) { /* published in the shared host table */ }
+            else if (P.xchg.nranks > 1) P.host_result = slot;
             else if (rt.comm_size == 1 && rt.opt.zero_copy_reduce && slot) { P.ticket = (rt.reduce_ticket += 1.0); P.host_result = slot; }
-            rt.last_tape_ticket = P.host_result ? P.ticket : 0.0;
+            rt.last_tape_ticket = (P.host_result || rt.last_tape_xhost) ? P.ticket : 0.0;
         }
         for (size_t k = 0; k < kp.ptr_local.size(); k++) P.ptrs[k] = info[kp.ptr_local[k]].buf;
         std::memcpy(P.instr, kp.words.data(), sizeof(TapeInstr) * kp.words.size());
@@ -1133,7 +1136,8 @@ bool Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
     if (spec.weight >= 0) materialize(spec.weight);
     const bool empty = nodes[idx].n == 0;
     if (empty && comm_size == 1) { out[0] = 0.0; out[1] = NAN; out[2] = NAN; return false; }
-    const bool p2p = comm_size > 1 && p2p_ready;
+    const bool p2p = use_p2p();
+    bool xhost_launch = false;                // this reduction's kernel publishes into the shared host table
     // the result slot of this reduction (released when the result has been read, also on the error paths)
     struct Slot {
         Runtime& rt; int s = -1;
@@ -1154,9 +1158,11 @@ bool Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
         P.host_result = nullptr; P.ticket = 0.0;
         fill_exchange(P.xchg, &P.ticket);
         double* slot = reduce_slot >= 0 ? h_ticket_dev + 4 * reduce_slot : nullptr;
-        if (P.xchg.nranks > 1) P.host_result = slot;
+        xhost_launch = P.xchg.nranks > 1 && P.xchg.host_table != nullptr;
+        if (xhost_launch) { /* published in the shared host table */ }
+        else if (P.xchg.nranks > 1) P.host_result = slot;
         else if (comm_size == 1 && opt.zero_copy_reduce && slot) { P.ticket = (reduce_ticket += 1.0); P.host_result = slot; }
-        ticket = P.host_result ? P.ticket : 0.0;
+        ticket = (P.host_result || xhost_launch) ? P.ticket : 0.0;
         const int64_t tiles = (P.n + reduce_tile_elems() - 1) / reduce_tile_elems();
         int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)sm_count * 8));
         grid = std::min(grid, max_grid);
@@ -1169,11 +1175,46 @@ bool Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
         stats.n_kernels++; stats.n_flushes++;
     } else {
         std::vector<int32_t> t{idx};
+        last_tape_xhost = false;
         run_cone(t, &spec);                   // the fused chain -> reduce launch sets params->ticket (Gen::launch)
         ticket = last_tape_ticket;
+        xhost_launch = last_tape_xhost;
     }
     const auto t_sync0 = std::chrono::steady_clock::now();
     const uint64_t stamp_at_launch = pool.free_stamp;   // blocks freed so far were last used by work queued before this kernel
+    if (xhost_launch) {
+        // Every rank's kernel stores its {count, value, M2} and then the ticket into slot [ticket % XSLOTS][rank] of the table in
+        // shared host memory; every rank's host waits here for the R tickets and hands the partials to the caller's merge in rank
+        // order (capi.cpp: merge_ranks) — the same arithmetic on every rank. No kernel waits for a peer and the compute stream is
+        // free for whatever was queued behind the reduction. A rank cannot run ahead of the others by more than one reduction, so
+        // a slot is not reused before everybody has read it.
+        const int xs = (int)((long long)ticket % XSLOTS);
+        const auto t_dead = t_sync0 + std::chrono::duration_cast<std::chrono::steady_clock::duration>(std::chrono::duration<double>(opt.exchange_timeout_s));
+        for (int r = 0; r < comm_size; r++) {
+            volatile double* t = xhost + ((size_t)xs * XMAX_RANKS + (size_t)r) * 4;
+            unsigned spins = 0;
+            while (t[3] != ticket) {
+#if defined(__x86_64__) || defined(__i386__)
+                __builtin_ia32_pause();
+#endif
+                if ((++spins & 0xfffu) == 0u) {
+                    if (r == comm_rank) {                  // my own kernel: has it failed?
+                        const cudaError_t q = cudaStreamQuery(stream);
+                        if (q != cudaSuccess && q != cudaErrorNotReady) FMC_CUDA(q);
+                    }
+                    if (std::chrono::steady_clock::now() > t_dead)
+                        fail(FMC_ERR_COMM, "reduction exchange timed out after %.0f s: rank %d did not deliver its partial (option exchange_timeout_s)", opt.exchange_timeout_s, r);
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            h_result[4 * r] = t[0]; h_result[4 * r + 1] = t[1]; h_result[4 * r + 2] = t[2];
+        }
+        out[0] = h_result[4 * comm_rank]; out[1] = h_result[4 * comm_rank + 1]; out[2] = h_result[4 * comm_rank + 2];
+        settled_stamp = std::max(settled_stamp, stamp_at_launch);
+        hostprof.sync += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_sync0).count();
+        stats.d2h += 32 * (uint64_t)comm_size;
+        return false;
+    }
     if (ticket != 0.0) {
         // the last block of the reduction wrote {count, value, M2} (after the in-kernel exchange: of ALL ranks) and then the
         // ticket into mapped pinned memory: spin on the ticket instead of a 32-byte copy plus a stream synchronisation

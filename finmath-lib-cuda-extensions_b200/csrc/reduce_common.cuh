@@ -20,7 +20,7 @@
 
 namespace fmc {
 
-constexpr long long XTIMEOUT_CYCLES = 8000000000ll;      // ~4 s
+constexpr long long XTIMEOUT_CYCLES = 120000000000ll;    // ~60 s (the in-kernel exchange, option exchange=1, is no longer the default)
 
 struct Part { double c, v, m; };       // count, value (sum | mean | min | max), M2
 
@@ -65,6 +65,17 @@ __device__ __forceinline__ Part shfl_down(Part p, int d) {
 static __device__ __noinline__ void finish_reduction(int mode, Part q, const Exchange& X, double ticket, double* __restrict__ result, double* host)
 {
     bool ok = true;
+    if (X.nranks > 1 && X.host_table) {
+        // exchange through shared host memory: publish this rank's partial and leave; every rank's HOST waits for the R tickets
+        // of the slot and merges them in rank order (Runtime::reduce), so no kernel holds its stream for another rank
+        const int slot = (int)((long long)ticket % XSLOTS);
+        volatile double* t = X.host_table + ((long long)slot * XMAX_RANKS + X.rank) * 4;
+        t[0] = q.c; t[1] = q.v; t[2] = q.m;
+        __threadfence_system();
+        t[3] = ticket;
+        result[0] = q.c; result[1] = q.v; result[2] = q.m;
+        return;
+    }
     if (X.nranks > 1) {
         const int slot = (int)((long long)ticket % XSLOTS);
         for (int r = 0; r < X.nranks; r++) {                          // my partial into everybody's table (mine included)

@@ -53,7 +53,7 @@ void Runtime::init(int device_index) {
     max_grid = sm_count * 16;
     FMC_CUDA(cudaMalloc(&d_partials, sizeof(double) * 128 * (size_t)max_grid));
     FMC_CUDA(cudaMalloc(&d_counter, sizeof(unsigned int) * 4));
-    FMC_CUDA(cudaMemset(d_counter, 0, sizeof(unsigned int) * 4));
+    FMC_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(unsigned int) * 4, stream));     // on the compute stream: ordered before the first kernel that counts
     FMC_CUDA(cudaMalloc(&d_result, sizeof(double) * 1024));
     FMC_CUDA(cudaMallocHost(&h_result, sizeof(double) * 1024));
     FMC_CUDA(cudaHostAlloc(&h_ticket, sizeof(double) * 4 * TICKET_SLOTS, cudaHostAllocMapped));

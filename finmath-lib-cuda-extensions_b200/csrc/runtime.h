@@ -116,7 +116,11 @@ struct Options {
     int max_sets = 1;               // slot sets per warp (cross-chunk prefetch depth), upper bound; measured: >1 costs occupancy and does not pay
     bool zero_copy_reduce = true;   // reductions publish their result through mapped pinned memory (single-rank runs)
     bool leaf_reduce_kernel = true; // reductions of a materialised vector use the streaming kernel, not the interpreter
-    bool p2p_reduce = true;         // sharded runs: exchange reduction partials inside the kernel over NVLink peer memory (else NCCL)
+    bool p2p_reduce = true;         // sharded runs, exchange == 1: partials exchanged inside the kernel over NVLink peer memory
+    int exchange = 2;               // how the ranks of a sharded run exchange reduction partials: 2 a table in shared host memory that every
+                                    // rank's kernel writes and every rank's host merges (no kernel waits for a peer); 1 inside the kernel over
+                                    // NVLink peer memory (a rendez-vous of the kernels); 0 ncclAllGather behind the kernel
+    double exchange_timeout_s = 120.0;   // a peer that has not delivered its partial after this long is taken for dead (FMC_ERR_COMM)
     int cta_warps = 4;              // warps per interpreter CTA (1..TAPE_MAX_WARPS)
     int tape_elems = 0;             // chunk geometry: elements per lane, 16 / 8 / 4; 0 = chosen per launch from the vector length
     int min_warps = 5;              // ... the largest geometry that still gives every SM this many warps of work (measured on the LMM step: 16-element
@@ -273,6 +277,14 @@ public:
     double* xtable = nullptr;
     double* peer_tables[XMAX_RANKS] = {nullptr};
     bool p2p_ready = false;
+    // exchange through shared host memory (POSIX shm, registered with CUDA): [XSLOTS][XMAX_RANKS][4] doubles
+    double* xhost = nullptr;            // this process's mapping
+    double* xhost_dev = nullptr;        // device-side address of the same memory
+    size_t xhost_bytes = 0;
+    bool xhost_ready = false;
+    bool last_tape_xhost = false;       // the last fused chain -> reduce launch published into the host table
+    bool use_xhost() const { return comm_size > 1 && xhost_ready && opt.exchange == 2; }
+    bool use_p2p() const { return comm_size > 1 && p2p_ready && opt.exchange == 1 && opt.p2p_reduce; }
     double xticket = 0.0;                                 // same sequence on every rank: reset by comm_init
     void fill_exchange(Exchange& x, double* ticket);      // parameters of the next reduction kernel
     void allreduce_sum(double* dev, int count);           // in place on the compute stream

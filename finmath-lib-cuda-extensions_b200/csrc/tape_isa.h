@@ -101,7 +101,9 @@ enum ReduceMode : int {
 // in this process (cudaIpc), slot [ticket % XSLOTS][rank] = {count, value, M2, ticket}
 constexpr int XMAX_RANKS = 8;
 constexpr int XSLOTS = 64;
-struct Exchange { double* tables[XMAX_RANKS]; int rank, nranks; };   // nranks <= 1: no exchange
+// host_table != nullptr: the ranks meet in a table in shared HOST memory instead (comm.cpp): the kernel only publishes its own
+// partial there and returns, the hosts merge — no kernel ever waits for another rank
+struct Exchange { double* tables[XMAX_RANKS]; double* host_table; int rank, nranks; };   // nranks <= 1: no exchange
 
 struct TapeInstr { uint32_t x, y; };
 
@@ -138,7 +140,7 @@ struct TapeParams : TapeHeader {
 // a trivial fused reduction took 32 us with the 20 KB TapeParams by value, 22 us below 4 KB), so a tape that fits travels
 // inline in a 4 KB argument block and a longer one through a ring of device buffers filled by cudaMemcpyAsync.
 constexpr int TAPE_INLINE_PTRS = 64;
-constexpr int TAPE_INLINE_INSTR = 428;     // words including the closing T_END and the two padding words
+constexpr int TAPE_INLINE_INSTR = 426;     // words including the closing T_END and the two padding words
 struct TapeArgsInline { TapeHeader h; float* ptrs[TAPE_INLINE_PTRS]; TapeInstr instr[TAPE_INLINE_INSTR]; };
 struct TapeArgsDev { TapeHeader h; float* const* ptrs; const TapeInstr* instr; };
 static_assert(sizeof(TapeArgsInline) <= 4096, "the inline argument block must stay within the 4 KB fast path");
