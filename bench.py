@@ -171,7 +171,7 @@ def run_reference(args) -> None:
         "cpu_double_array": {"value": value64, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{total} paths, 1 step; C++ restatement of finmath-lib's RandomVariableFromDoubleArray (not part of the ratio)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "calibration": calibration,
+        "calibration": calibration, "extras": extras,
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -190,6 +190,13 @@ def rel_diff(got, want):
     import numpy as np
     got = np.asarray(got, dtype=np.float64); want = np.asarray(want, dtype=np.float64)
     return float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-12)))
+
+
+def _chain16(x, y):
+    c = x
+    for k in range(4):
+        c = c.mult(1.0001).add(y).sub(0.001).mult(y)
+    return c
 
 
 def run_ours(args) -> None:
@@ -323,6 +330,71 @@ def run_ours(args) -> None:
                                                              "ok": bool(abs(r3["mean_deviation"]) < 2e-4)}
             cm.close()
 
+    # ---- the other configurations of BASELINE.json, each as a compact extra key of the same line ----
+    extras = {}
+    if not args.no_extras:
+        import numpy as np
+        # config 3: Bermudan swaption (11 exercise dates, k = 6 regression, choose) at 1 Mi paths IN TOTAL, sharded over the ranks (strong scaling)
+        bp = 1 << 20
+        per = ((bp + world - 1) // world + 3) // 4 * 4
+        b0, b1 = min(bp, rank * per), min(bp, (rank + 1) * per)
+        bm = lib.lmm(bp, N_PERIODS, DELTA, 1, SEED, 0, (b0, b1))
+        bm.use_market_curve()
+        spec = (10, 30, 2, 40, 0.02)
+        bm.simulate(); bv = bm.bermudan(*spec); barrier()
+        t_sim, t_val = [], []
+        for _ in range(3):
+            barrier(); t0 = time.perf_counter(); bm.simulate(); capi.check(capi.load().fmc_sync()); t1 = time.perf_counter()
+            bv = bm.bermudan(*spec); t2 = time.perf_counter()
+            t_sim.append(max_over_ranks(t1 - t0)); t_val.append(max_over_ranks(t2 - t1))
+        extras["bermudan_1m_paths_sharded"] = {"paths_total": bp, "ranks": world, "simulate_ms": 1e3 * min(t_sim), "valuation_ms": 1e3 * min(t_val), "value": bv,
+                                               "what": "BASELINE config 3: backward induction, regression on 6 basis functions at 11 exercise dates, choose(); strong scaling"}
+        bm.close()
+        if world == 1:
+            # config 2 path sweep (5 k ... 500 k paths; the 1 Mi point is the headline above): one calibration step, device-resident
+            sweep = {}
+            for pth in (5000, 10000, 20000, 50000, 100000, 200000, 500000):
+                sm_ = lib.lmm(pth, N_PERIODS, DELTA, 1, SEED, 0, (0, pth))
+                sm_.use_market_curve()
+                for _ in range(3):
+                    sm_.step()
+                capi.timer_start()
+                for _ in range(5):
+                    sm_.step()
+                sweep[str(pth)] = capi.timer_stop() / 5
+                sm_.close()
+            extras["path_sweep_ms_per_step"] = sweep
+            # config 5: raw operations at 1e8 elements against the HBM roofline (algorithmic bytes / CUDA-event time of the flush)
+            n_raw = 100_000_000
+            rng = np.random.RandomState(SEED)
+            xs = [fc.RandomVariableCuda(0.0, rng.random_sample(n_raw).astype(np.float32)) for _ in range(3)]
+            x, y, z = xs
+            peak_ = float(measured_peaks()[0].get("hbm_gbs", 6650.0))
+
+            def raw(fn, bytes_per_elt):
+                ts = []
+                for i in range(5):
+                    capi.check(capi.load().fmc_sync()); capi.timer_start(); r = fn(); capi.check(capi.load().fmc_flush()); ts.append(capi.timer_stop()); del r
+                ms = float(np.median(ts[2:]))
+                g = bytes_per_elt * n_raw / (ms * 1e-3) / 1e9
+                return {"ms": ms, "GBps": g, "frac_of_measured_peak": g / peak_}
+            ops = {"add(vec)": (lambda: x.add(y), 12), "mult(scalar)": (lambda: x.mult(3.1415), 8), "accrue": (lambda: x.accrue(y, 0.5), 12),
+                   "discount": (lambda: x.discount(y, 0.5), 12), "addProduct(vec,vec)": (lambda: x.addProduct(y, z), 16), "exp": (lambda: x.exp(), 8),
+                   "log": (lambda: x.log(), 8), "chain of 16 ops": (lambda: _chain16(x, y), 12),
+                   "getAverage": (lambda: x.getAverage(), 4), "getVariance": (lambda: x.getVariance(), 4),
+                   "payoff chain -> getAverage": (lambda: x.sub(0.5).floor(0.0).div(1.1).mult(0.9).getAverage(), 4)}
+            extras["raw_ops_1e8"] = {k: raw(f, b) for k, (f, b) in ops.items()}
+            del xs, x, y, z
+            # Brownian generation (MT19937 + inverse normal), 1 Mi paths x 80 steps
+            td = fc.TimeDiscretization(0.0, N_PERIODS, DELTA)
+            tsb = []
+            for i in range(4):
+                capi.check(capi.load().fmc_sync()); t0 = time.perf_counter()
+                bmo = fc.BrownianMotionCuda(td, 1, 1 << 20, SEED + 1)
+                inc = bmo.getBrownianIncrement(0, 0); capi.check(capi.load().fmc_sync()); tsb.append(time.perf_counter() - t0); del bmo, inc
+            extras["brownian_1m_x_80"] = {"first_ms": 1e3 * tsb[0], "cached_jump_ms": 1e3 * min(tsb[1:]), "increments_per_s": (1 << 20) * 80 / min(tsb[1:]),
+                                          "GBps_written": 4 * (1 << 20) * 80 / min(tsb[1:]) / 1e9}
+
     # ---- the workload at the parity sample's size, on every rank's slice of the SAME global paths (compared with the oracle below) ----
     sample_values = None
     if not args.no_cpu_baseline:
@@ -402,7 +474,7 @@ def run_ours(args) -> None:
         "nodes_stored_per_step": st["n_nodes_stored"] / args.steps, "nodes_fused_per_step": st["n_nodes_fused"] / args.steps,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "host_profile": host_prof,
         ("parity" if world == 1 else "multi_gpu_parity"): parity,
-        "calibration": calibration,
+        "calibration": calibration, "extras": extras,
         "price_check": {"first_values": [float(v) for v in values[:3]], "e2e_equal": bool((values == values_e2e).all()),
                         "e2e_pinned_equal": bool((values == values_pinned).all())},
     }
@@ -426,6 +498,7 @@ def main():
     ap.add_argument("--ref-paths-per-thread", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-calibration", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the Bermudan / path-sweep / raw-op extra keys")
     ap.add_argument("--calibration-iterations", type=int, default=1, help="Levenberg-Marquardt iterations of the calibration key (1 iteration = 50 simulations)")
     ap.add_argument("--valuation-threads", type=int, default=1,
                     help="host threads valuing the calibration products (the reference test uses 1, LIBORMarketModelCalibrationATMTest.java:319)")

@@ -100,6 +100,9 @@ public:
     std::shared_ptr<BrownianMotionCuda> getCloneWithModifiedSeed(int seed) const {                  // BMC:111-114
         return std::make_shared<BrownianMotionCuda>(td_, factors_, paths_, seed, seedMode_, p0_, p1_);
     }
+    std::shared_ptr<BrownianMotionCuda> getCloneWithModifiedTimeDiscretization(TimeDiscretization newTimeDiscretization) const {   // BMC:116-120
+        return std::make_shared<BrownianMotionCuda>(std::move(newTimeDiscretization), factors_, paths_, seed_, seedMode_, p0_, p1_);
+    }
     int getSeed() const { return seed_; }
 private:
     void generate() {                                                                               // BMC:141-182
