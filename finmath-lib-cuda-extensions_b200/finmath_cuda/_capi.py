@@ -146,6 +146,9 @@ def ensure_init(device_index: int | None = None) -> None:
             device_index = int(env)
         elif "LOCAL_RANK" in os.environ:
             device_index = int(os.environ["LOCAL_RANK"])
+        elif int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            # several ranks, no device named: the default (-1, the last device) would put every rank on ONE GPU
+            raise CudaError("WORLD_SIZE > 1 but neither LOCAL_RANK nor FINMATH_CUDA_DEVICE_INDEX is set: name the device of this rank")
         else:
             device_index = -1
     check(load().fmc_init(device_index))
@@ -179,6 +182,20 @@ def timer_stop() -> float:
     ms = C.c_float()
     check(load().fmc_timer_stop(C.byref(ms)))
     return float(ms.value)
+
+
+def sync() -> None:
+    """Execute everything pending and wait for the device (cuCtxSynchronize, RandomVariableCuda.java:472-476)."""
+    check(load().fmc_sync())
+
+
+def pool_trim() -> None:
+    """RandomVariableCuda.clean() (RVC:751-753): cached device blocks go back to the driver."""
+    check(load().fmc_pool_trim())
+
+
+def reset_stats() -> None:
+    check(load().fmc_reset_stats())
 
 
 def set_option(key: str, value: float) -> None:

@@ -12,8 +12,14 @@ the reference tree), so this is a restatement of its published behaviour, not of
     operations (mult, add, sub, div, squared, exp, log, sqrt, invert, choose, average ...), i.e. they run on the GPU;
   * type priority = AAD_PRIORITY_OFFSET + inner priority, so a differentiable operand takes over from a plain one
     (RandomVariableCuda.java:1392-1395 pattern) and "AAD on GPU" (offset + 20) outranks "AAD on CPU" (offset + 1).
-Intermediate values stay alive as long as the tree does (that is AAD); the runtime's lazy nodes make this cheap: a value
-nobody reads again is never materialised twice.
+Retention policy (the reference only states the contract, README.md:50-52,119). A node of the operator tree
+keeps exactly the VALUES its own derivative rule reads and nothing else: add / sub / average / a product with a scalar keep
+none, mult / div keep the two operands, sqrt / exp / invert their own result, log / squared / abs / pow the argument, accrue /
+discount value and rate, choose the trigger. On the GPU type this decides what is ever MATERIALISED: a primal intermediate that no
+rule needs has no handle left once the caller's temporary dies, so the op-tape fuses it away instead of storing a vector per
+node (RETENTION = "all" restores the store-everything behaviour for comparison: benchmarks/aad_footprint.py). During the
+reverse sweep an adjoint is dropped as soon as it has been propagated, and getGradient(release=True) also drops each node's
+retained values right after its rule has run, so the footprint shrinks as the sweep proceeds (the tree is then single-use).
 """
 from __future__ import annotations
 
@@ -29,12 +35,18 @@ AAD_PRIORITY_OFFSET = 1000
 _ids = itertools.count(1)
 
 
+RETENTION = "needed"          # "needed": a node keeps only what its derivative rule reads; "all": every node also keeps its own values
+
+_KEEPS_OWN_VALUE = {"sqrt", "exp", "invert"}
+
+
 class _Node:
     __slots__ = ("id", "op", "args", "values", "param")
 
     def __init__(self, op: Optional[str], args: Sequence["_Node" | None], values: RandomVariable, param=None):
         self.id = next(_ids)
-        self.op, self.args, self.values, self.param = op, list(args), values, param
+        self.op, self.args, self.param = op, list(args), param
+        self.values = values if (RETENTION == "all" or op in _KEEPS_OWN_VALUE) else None
 
 
 class RandomVariableDifferentiableAAD(RandomVariable):
@@ -74,17 +86,20 @@ class RandomVariableDifferentiableAAD(RandomVariable):
     # ------------------------------------------------------------------ operations (values through the inner type)
     def add(self, x): return self._new("add", self.values.add(self._val(x)), [self, x])
     def sub(self, x): return self._new("sub", self.values.sub(self._val(x)), [self, x])
-    def bus(self, x): return self._new("sub", self.values.bus(self._val(x)), [x, self], param=("operands", self._val(x), self.values))
-    def mult(self, x): return self._new("mult", self.values.mult(self._val(x)), [self, x], param=("operands", self.values, self._val(x)))
+    def bus(self, x): return self._new("sub", self.values.bus(self._val(x)), [x, self])
+    def mult(self, x):
+        # a factor is kept only if the OTHER operand is differentiable (d/dx (x y) = y): x * scalar keeps one double
+        keep_self = self.values if isinstance(x, RandomVariableDifferentiableAAD) else None
+        return self._new("mult", self.values.mult(self._val(x)), [self, x], param=("operands", keep_self, self._val(x)))
     def div(self, x): return self._new("div", self.values.div(self._val(x)), [self, x], param=("operands", self.values, self._val(x)))
     def vid(self, x): return self._new("div", self.values.vid(self._val(x)), [x, self], param=("operands", self._val(x), self.values))
-    def squared(self): return self._new("squared", self.values.squared(), [self])
+    def squared(self): return self._new("squared", self.values.squared(), [self], param=self.values)
     def sqrt(self): return self._new("sqrt", self.values.sqrt(), [self])
     def exp(self): return self._new("exp", self.values.exp(), [self])
-    def log(self): return self._new("log", self.values.log(), [self])
+    def log(self): return self._new("log", self.values.log(), [self], param=self.values)
     def invert(self): return self._new("invert", self.values.invert(), [self])
-    def abs(self): return self._new("abs", self.values.abs(), [self])
-    def pow(self, e: float): return self._new("pow", self.values.pow(e), [self], param=float(e))
+    def abs(self): return self._new("abs", self.values.abs(), [self], param=self.values)
+    def pow(self, e: float): return self._new("pow", self.values.pow(e), [self], param=(self.values, float(e)))
     def cap(self, c): return self._new("cap", self.values.cap(self._val(c)), [self, c], param=("operands", self.values, self._val(c)))
     def floor(self, c): return self._new("floor", self.values.floor(self._val(c)), [self, c], param=("operands", self.values, self._val(c)))
     def average(self): return self._new("average", self.values.average(), [self])
@@ -102,8 +117,9 @@ class RandomVariableDifferentiableAAD(RandomVariable):
         return self._new("choose", self.values.choose(self._val(a), self._val(b)), [self, a, b], param=self.values)
 
     # ------------------------------------------------------------------ reverse sweep
-    def getGradient(self, independents: Optional[Sequence["RandomVariableDifferentiableAAD"]] = None) -> Dict[int, RandomVariable]:
-        """d(self)/d(leaf) for every leaf of the operator tree (or the given variables), as inner-type random variables."""
+    def getGradient(self, independents: Optional[Sequence["RandomVariableDifferentiableAAD"]] = None, release: bool = False) -> Dict[int, RandomVariable]:
+        """d(self)/d(leaf) for every leaf of the operator tree (or the given variables), as inner-type random variables.
+        release=True: every node drops the values it retained as soon as its derivative rule has run (single-use tree)."""
         one = _scalar_like(self.values, 1.0)
         adj: Dict[int, RandomVariable] = {self.node.id: one}
         # nodes reachable from self, processed in decreasing id (ids increase along every edge)
@@ -134,11 +150,13 @@ class RandomVariableDifferentiableAAD(RandomVariable):
                 if contrib is None:
                     continue
                 adj[arg.id] = adj[arg.id].add(contrib) if arg.id in adj else contrib
+            if release:
+                nd.param = None; nd.values = None
         return grad
 
 
 def _scalar_like(v: RandomVariable, x: float) -> RandomVariable:
-    return type(v)(x) if isinstance(v, RandomVariableCuda) else RandomVariableCuda(x)
+    return type(v)(x)                  # the inner type's own (value) constructor: RandomVariableCuda(x), the CPU twin's, ...
 
 
 def _indicator(trigger: RandomVariable, if_nonneg: float, if_neg: float) -> RandomVariable:
@@ -154,13 +172,13 @@ def _propagate(nd: _Node, k: int, a: RandomVariable) -> Optional[RandomVariable]
     if op == "div":                                        # x / y
         x, y = p[1], p[2]
         return a.div(y) if k == 0 else a.mult(x).div(y.squared()).mult(-1.0)
-    if op == "squared": return a.mult(nd.args[0].values).mult(2.0)
+    if op == "squared": return a.mult(p).mult(2.0)
     if op == "sqrt": return a.div(v).mult(0.5)
     if op == "exp": return a.mult(v)
-    if op == "log": return a.div(nd.args[0].values)
+    if op == "log": return a.div(p)
     if op == "invert": return a.mult(v.squared()).mult(-1.0)
-    if op == "abs": return a.mult(_indicator(nd.args[0].values, 1.0, -1.0))
-    if op == "pow": return a.mult(nd.args[0].values.pow(p - 1.0)).mult(p)
+    if op == "abs": return a.mult(_indicator(p, 1.0, -1.0))
+    if op == "pow": return a.mult(p[0].pow(p[1] - 1.0)).mult(p[1])
     if op == "cap":                                        # min(x, c): d/dx = 1{x < c}
         x, c = p[1], p[2]
         ind = _indicator(_as_rv(c, x).sub(x), 1.0, 0.0)

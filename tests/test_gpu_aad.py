@@ -154,3 +154,81 @@ def test_lmm_swaption_vega_by_aad_on_the_gpu(fc):
     # Bachelier: value = annuity * sigma * sqrt(T / 2 pi) for the ATM option -> vega ~ value / sigma
     assert abs(vega - V.doubleValue() / sigma0) <= 0.15 * vega
     assert kernels < 60, f"primal + adjoint sweep should fuse into few launches, used {kernels}"
+
+
+def _aad_chain(X, Y):
+    u = X.mult(Y).add(X.mult(0.3).exp()).sub(Y.log().div(X.mult(0.5).add(1.0)))
+    v = u.squared().add(1.0).sqrt().accrue(Y, 0.25)
+    w = v.sub(2.0).floor(0.0).add(X.cap(1.0)).add(Y.invert()).add(X.discount(Y, 0.5)).add(X.abs().pow(1.5))
+    return X.sub(1.0).choose(w.mult(X), w.addProduct(Y, Y))
+
+
+def test_aad_on_the_gpu_matches_aad_on_the_oracle(fc, O):
+    """The SAME RandomVariableDifferentiableAAD code over RandomVariableCuda and over the CPU oracle twin (RandomVariableFromFloatArray
+    semantics, oracle/oracle_random_variable.py): primal values bit-equal where every op is exact, every gradient within 1e-5
+    relative — an oracle-backed check of the reverse sweep instead of finite differences of the GPU computation itself."""
+    from oracle.oracle_random_variable import OracleRandomVariable
+    n = 40_000
+    rng = np.random.default_rng(11)
+    x0, y0 = rng.random(n) + 0.5, rng.random(n) + 0.5
+    res = {}
+    for name, ctor in (("gpu", fc.RandomVariableCuda), ("cpu", OracleRandomVariable)):
+        X, Y = fc.RandomVariableDifferentiableAAD(ctor(0.0, x0)), fc.RandomVariableDifferentiableAAD(ctor(0.0, y0))
+        F = _aad_chain(X, Y)
+        g = F.getGradient()
+        mean = F.average()
+        gm = mean.getGradient()
+        res[name] = (F.getRealizations(), g[X.getID()].getRealizations(), g[Y.getID()].getRealizations(),
+                     gm[X.getID()].getRealizations(), mean.doubleValue())
+    (fg, gxg, gyg, gmg, mg), (fcpu, gxc, gyc, gmc, mc) = res["gpu"], res["cpu"]
+    assert np.max(np.abs(fg - fcpu) / np.maximum(np.abs(fcpu), 1e-6)) <= 2e-7          # exp / log / pow: <= 1 ulp each
+    for a, b in ((gxg, gxc), (gyg, gyc), (gmg, gmc)):
+        assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-3)) <= 1e-5
+    assert abs(mg - mc) <= 1e-6 * abs(mc)
+
+
+def test_aad_retention_policy_bounds_the_device_footprint(fc):
+    """a node of the operator tree keeps only what its derivative rule reads, so primal intermediates nobody needs are
+    fused away instead of stored; release=True frees retained values during the sweep. Same gradient, a fraction of the memory."""
+    import finmath_cuda.differentiable as D
+    n, NP, delta, L0, sigma0, strike = 200_000, 12, 0.5, 0.02, 0.006, 0.02
+    td = fc.TimeDiscretization(0.0, NP, delta)
+    bm = fc.BrownianMotionCuda(td, 1, n, 31415)
+    plain = fc.RandomVariableCudaFactory()
+    for t in range(NP):
+        bm.getBrownianIncrement(t, 0)
+
+    def vega(retention, release):
+        D.RETENTION = retention
+        try:
+            fc.sync(); fc.pool_trim(); fc.reset_stats()
+            base = fc.stats()["bytes_in_use"]
+            sig = fc.RandomVariableDifferentiableAAD(plain.createRandomVariable(0.0, sigma0))
+            libor = [plain.createRandomVariable(0.0, L0) for _ in range(NP)]
+            exercise, at_ex = NP // 2, None
+            for t in range(NP):
+                if t == exercise: at_ex = list(libor)
+                dW, acc, new = bm.getBrownianIncrement(t, 0), None, list(libor)
+                for i in range(t + 1, NP):
+                    tr = sig.mult(libor[i].mult(delta).add(1.0).invert().mult(delta))
+                    acc = tr if acc is None else acc.add(tr)
+                    new[i] = libor[i].add(acc.mult(sig).mult(delta)).add(sig.mult(dW))
+                libor = new
+            value = None
+            for i in range(NP - 1, exercise - 1, -1):
+                payoff = at_ex[i].sub(strike).mult(delta)
+                value = payoff if value is None else value.add(payoff)
+                value = value.discount(at_ex[i], delta)
+            V = value.floor(0.0).average()
+            del libor, new, at_ex, value, acc, tr, payoff
+            g = V.getGradient(release=release)[sig.getID()].getAverage()
+            return g, fc.stats()["bytes_high_water"] - base
+        finally:
+            D.RETENTION = "needed"
+
+    g_all, mem_all = vega("all", False)
+    g_need, mem_need = vega("needed", False)
+    g_rel, mem_rel = vega("needed", True)
+    assert g_all > 0 and abs(g_need - g_all) <= 1e-9 * abs(g_all) and abs(g_rel - g_all) <= 1e-9 * abs(g_all)
+    assert mem_need <= 0.6 * mem_all, (mem_need, mem_all)
+    assert mem_rel <= mem_need, (mem_rel, mem_need)
