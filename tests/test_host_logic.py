@@ -187,3 +187,31 @@ def test_world_size_2_sharding_over_gloo(tmp_path):
     assert res["cnt"] == 1001
     assert abs(res["avg"] - res["avg_full"]) <= 1e-12 * abs(res["avg_full"])
     assert abs(res["var"] - res["var_full"]) <= 1e-10 * abs(res["var_full"])
+
+
+def test_java_shim_binds_only_declared_symbols_with_matching_arity():
+    """java/.../FmCuda.java cannot be compiled here (no JDK): at least every downcall handle must name a function of
+    include/fmcuda.h, with as many parameters as the C prototype has, and the RandomVariable surface must be complete."""
+    java_dir = os.path.join(ROOT, "java", "src", "main", "java", "net", "finmath", "cuda", "montecarlo")
+    src = open(os.path.join(java_dir, "FmCuda.java")).read()
+    header = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    protos = {m.group(1): m.group(2) for m in re.finditer(r"\bint\s+(fmc_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", header, flags=re.S)}
+    protos["fmc_last_error"] = "void"
+    bound = re.findall(r'h\("(fmc_[a-z0-9_]+)",\s*FunctionDescriptor\.of\(([^;]*?)\)\);', src)
+    assert len(bound) >= 24
+    for name, desc in bound:
+        assert name in protos, f"FmCuda.java binds {name}, which include/fmcuda.h does not declare"
+        params = protos[name].strip()
+        n_c = 0 if params in ("", "void") else len(params.split(","))
+        n_java = len([a for a in desc.split(",") if a.strip()]) - 1          # first layout is the return value
+        assert n_c == n_java, (name, n_c, n_java)
+    rvc = open(os.path.join(java_dir, "RandomVariableCuda.java")).read()
+    for method in ("equals", "getFiltrationTime", "getTypePriority", "get", "size", "getMin", "getMax", "getAverage", "getVariance", "getSampleVariance",
+                   "getStandardDeviation", "getStandardError", "getQuantile", "getQuantileExpectation", "getHistogram", "isDeterministic", "cache",
+                   "getRealizations", "doubleValue", "getOperator", "getRealizationsStream", "apply", "cap", "floor", "add", "sub", "bus", "mult", "div",
+                   "vid", "pow", "average", "squared", "sqrt", "invert", "abs", "exp", "log", "sin", "cos", "accrue", "discount", "choose", "addProduct",
+                   "addRatio", "subRatio", "isNaN"):
+        assert re.search(r"public\s+\S+(\[\])*\s+%s\(" % method, rvc), f"RandomVariableCuda.java lacks {method}()"
+    assert len(re.findall(r"@Override", rvc)) >= 64                          # RandomVariableCuda.java:785-1701 overrides 64 methods
+    assert "serialVersionUID = 7620120320663270600L" in rvc and "transient long" in rvc
+    assert rvc.count("{") == rvc.count("}") and src.count("{") == src.count("}")
