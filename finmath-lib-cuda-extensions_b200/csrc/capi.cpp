@@ -329,11 +329,31 @@ int fmc_reduce(int kind, fmc_vec a, fmc_vec weights, double* out) {
         ReduceSpec spec;
         double p[3];
         auto run = [&](const ReduceSpec& sp, int merge_mode) { const bool global = rt.reduce(x, sp, p); merge_ranks(rt, merge_mode, p, global); };
+        // RVF:322-330 sums with Kahan's compensation: an infinite element makes the compensation term inf - inf = NaN, so every
+        // element AFTER it turns the sum into NaN; only an infinity at the very last index survives as +-inf. The device sum
+        // returns +-inf in both cases: when that happens (rare) the reference's answer is reconstructed with two more passes.
+        auto kahan_infinity = [&](double sum) -> double {
+            const int64_t n = rt.nodes[x].n;
+            const int32_t d = temp(rt, rt.record(N_SUB, n, N(x), N(x)));          // inf - inf = NaN, finite - finite = 0
+            const int32_t f = rt.record(N_ISNAN, n, N(d));
+            ReduceSpec cs; cs.mode = RM_SUM;
+            double q[3];
+            const bool global = rt.reduce(f, cs, q);
+            merge_ranks(rt, RM_SUM, q, global);
+            rt.release_ext(f);
+            if (q[1] != 1.0 || rt.comm_size > 1) return NAN;                     // (sharded: an infinity at the global last index is reported as NaN too)
+            rt.materialize(x);
+            float last = 0.f;
+            FMC_CUDA(cudaMemcpyAsync(&last, rt.nodes[x].buf + (n - 1), sizeof(float), cudaMemcpyDeviceToHost, rt.stream));
+            FMC_CUDA(cudaStreamSynchronize(rt.stream));
+            return std::isinf(last) ? sum : NAN;
+        };
         switch (kind) {
         case FMC_RED_SUM:
         case FMC_RED_AVERAGE:
             spec.mode = RM_SUM;
             run(spec, RM_SUM);
+            if (std::isinf(p[1])) p[1] = kahan_infinity(p[1]);
             if (kind == FMC_RED_SUM) *out = (p[0] == 0.0) ? 0.0 : p[1];
             else *out = (p[0] == 0.0) ? NAN : p[1] / p[0];                       // RVF:318-320, 333
             break;

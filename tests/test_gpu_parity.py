@@ -565,8 +565,22 @@ class _OracleRV:
 
 
 def _same_reduction(g, w):
-    # a non-finite element: the reference's Kahan loop turns inf into NaN (RVF:322-330) unless it comes last; not mirrored
+    # (a non-finite element: the reference's Kahan loop turns inf into NaN (RVF:322-330) unless it comes last; getAverage mirrors that,
+    # the other reductions may keep the infinity)
     return (g != g and w != w) or (w != w and abs(g) == float("inf")) or g == w or abs(g - w) <= 1e-9 * abs(w) + 1e-300
+
+
+def test_average_of_a_vector_with_infinities_follows_the_kahan_loop(fc, O):
+    """RVF:322-330: an infinity anywhere but at the last index turns the compensated sum into NaN; at the last index it survives."""
+    base = np.linspace(-1.0, 2.0, 3000).astype(np.float32)
+    for pos, val in ((17, np.inf), (2999, np.inf), (2999, -np.inf), (0, -np.inf), (1500, np.inf)):
+        x = base.copy(); x[pos] = val
+        got, want = fc.RandomVariableCuda(0.0, x.astype(np.float64)).getAverage(), O.average(x)
+        assert (got != got and want != want) or got == want, (pos, val, got, want)
+        got2 = fc.RandomVariableCuda(0.0, x.astype(np.float64)).mult(1.0).add(0.0).getAverage()       # through a fused chain
+        assert (got2 != got2 and want != want) or got2 == want, (pos, val, got2, want)
+    x = base.copy(); x[5] = np.inf; x[2999] = np.inf
+    assert math.isnan(fc.RandomVariableCuda(0.0, x.astype(np.float64)).getAverage()) and math.isnan(O.average(x))
 
 
 def test_fuzzed_programs_match_the_oracle(fc, O):
