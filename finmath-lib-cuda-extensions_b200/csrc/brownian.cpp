@@ -127,13 +127,13 @@ void brownian_generate(Runtime& rt, int seed_mode, int64_t seed, int T, int F, i
         for (int i = 0; i < TF; i++) out_nodes[i] = rt.new_leaf(np);
         if (np == 0) return;
         // tile geometry: PT paths per tile (odd -> conflict-free transposition), T*F*PT floats per tile, two tiles
-        const int64_t tile_budget = 6144;                        // floats per tile (24 KB), 2 tiles
+        const int64_t tile_budget = 3584;                        // floats per tile (14 KB), 2 tiles: with the state and the tail queue 42 KB per block, 5 blocks per SM
         int64_t PT = std::max<int64_t>(tile_budget / TF, 1);
         if (PT * TF < 320) PT = (320 + TF - 1) / TF;             // a regeneration (312 elements) may span at most 2 tiles
         if (PT % 2 == 0) PT += 1;
         if ((size_t)(2 * PT * TF) * sizeof(float) > 200 * 1024) fail(FMC_ERR_UNSUPPORTED, "T*F = %d too large for the Brownian tile buffer", TF);
-        // block decomposition: contiguous path ranges, about 4 blocks per SM
-        int64_t target_blocks = (int64_t)rt.sm_count * 4;
+        // block decomposition: contiguous path ranges, 5 blocks per SM (one wave; the blocks' barrier-separated phases overlap)
+        int64_t target_blocks = (int64_t)rt.sm_count * 5;
         int64_t ppb = (np + target_blocks - 1) / target_blocks;
         ppb = std::max<int64_t>((ppb + PT - 1) / PT * PT, PT);
         // keep the block-relative element index inside 32 bits

@@ -55,22 +55,25 @@ __device__ __forceinline__ void regenerate(const uint32_t* __restrict__ old, uin
 // Wichura AS241 PPND16 in double, without fused multiply-add (Java semantics); same constants as oracle/fm_oracle.c
 __device__ __forceinline__ double mad(double a, double r, double c) { return __dadd_rn(__dmul_rn(a, r), c); }
 
-__device__ double icdf_as241(double p) {
+// The coefficients live in constant memory: a double literal in the code costs two UMOV instructions per use (the kernel is bound
+// by instruction issue), an operand in a constant bank costs none.
+__constant__ double c_a[8] = {3.3871328727963666080e+00, 1.3314166789178437745e+02, 1.9715909503065514427e+03, 1.3731693765509461125e+04,
+                              4.5921953931549871457e+04, 6.7265770927008700853e+04, 3.3430575583588128105e+04, 2.5090809287301226727e+03};
+__constant__ double c_b[8] = {1.0, 4.2313330701600911252e+01, 6.8718700749205790830e+02, 5.3941960214247511077e+03, 2.1213794301586595867e+04,
+                              3.9307895800092710610e+04, 2.8729085735721942674e+04, 5.2264952788528545610e+03};
+
+// central region |p - 0.5| <= 0.425 (85 % of the uniforms): one rational function, one division
+__device__ __forceinline__ double icdf_central(double q) {
+    const double r = __dsub_rn(0.180625, __dmul_rn(q, q));
+    double num = c_a[7], den = c_b[7];
+#pragma unroll
+    for (int i = 6; i >= 0; i--) { num = mad(num, r, c_a[i]); den = mad(den, r, c_b[i]); }
+    return __ddiv_rn(__dmul_rn(q, num), den);
+}
+
+// the tails: log, sqrt and another rational function; kept out of line (the generator runs it on a compacted queue)
+__device__ __noinline__ double icdf_tail(double p) {
     const double q = p - 0.5;
-    if (fabs(q) <= 0.425) {
-        const double r = __dsub_rn(0.180625, __dmul_rn(q, q));
-        double num = 2.5090809287301226727e+03;
-        num = mad(num, r, 3.3430575583588128105e+04); num = mad(num, r, 6.7265770927008700853e+04);
-        num = mad(num, r, 4.5921953931549871457e+04); num = mad(num, r, 1.3731693765509461125e+04);
-        num = mad(num, r, 1.9715909503065514427e+03); num = mad(num, r, 1.3314166789178437745e+02);
-        num = mad(num, r, 3.3871328727963666080e+00);
-        double den = 5.2264952788528545610e+03;
-        den = mad(den, r, 2.8729085735721942674e+04); den = mad(den, r, 3.9307895800092710610e+04);
-        den = mad(den, r, 2.1213794301586595867e+04); den = mad(den, r, 5.3941960214247511077e+03);
-        den = mad(den, r, 6.8718700749205790830e+02); den = mad(den, r, 4.2313330701600911252e+01);
-        den = mad(den, r, 1.0);
-        return __ddiv_rn(__dmul_rn(q, num), den);
-    }
     double r = (q < 0.0) ? p : 1.0 - p;
     if (r <= 0.0) return (q < 0.0) ? -INFINITY : INFINITY;
     r = sqrt(-log(r));
@@ -185,11 +188,19 @@ struct BrownianLaunch {
     float* const* out;                 // [T*F] -> np floats
 };
 
+// Tail uniforms (|u - 0.5| > 0.425: 15 % of them, but 99 % of all warps hold at least one) are not evaluated where they occur —
+// the whole warp would walk the log / sqrt / second-rational branch for a few lanes — but queued in shared memory with their
+// destination and evaluated densely, a block's worth at a time (and always before the tile they belong to is written out).
+constexpr int QCAP = 2 * BTHREADS;            // a full round waiting + one more regeneration's tails
+
 __global__ void __launch_bounds__(BTHREADS)
 brownian_kernel(const BrownianLaunch P)
 {
     extern __shared__ float tiles[];             // [2][TF * PT]
     __shared__ uint32_t st[2][MT_N];
+    __shared__ double q_u[QCAP];
+    __shared__ uint32_t q_dst[QCAP];             // tile slot (low 16 bits: float index in `tiles` / 1 ... see below) and time index
+    __shared__ int q_n;
     const int tid = threadIdx.x;
     const int TF = P.T * P.F;
     const int PT = P.PT;
@@ -202,45 +213,98 @@ brownian_kernel(const BrownianLaunch P)
     const long long e_lo = pb0 * TF, e_hi = pb1 * TF;                            // global element range (1 element = 2 words)
 
     for (int i = tid; i < MT_N; i += BTHREADS) st[0][i] = P.block_states[(long long)blockIdx.x * MT_N + i];
+    if (tid == 0) q_n = 0;
     __syncthreads();
     long long e = P.chunk_of_block[blockIdx.x] * (long long)(MT_CHUNK_WORDS / 2); // element index of the next regeneration's first pair
     int cur = 0;
     long long next_tile = 0;                     // next tile (index within block) to flush
     const long long n_tiles = (pb1 - pb0 + PT - 1) / PT;
 
+    // evaluates queued tails: all of them (force) or full rounds of BTHREADS only. Called by all threads.
+    auto drain = [&](bool force) {
+        for (;;) {
+            __syncthreads();
+            const int n = q_n;
+            if (n == 0 || (!force && n < BTHREADS)) break;
+            const int take = n < BTHREADS ? n : BTHREADS;
+            if (tid < take) {
+                const int k = n - take + tid;
+                const uint32_t d = q_dst[k];
+                const double z = icdf_tail(q_u[k]);
+                tiles[d & 0xffffu] = __double2float_rn(__dmul_rn(z, P.sqrt_dt[d >> 16]));
+            }
+            __syncthreads();
+            if (tid == 0) q_n = n - take;
+        }
+    };
+
+    // Where this thread's element lands is tracked incrementally (the kernel was bound by instruction issue: three runtime
+    // integer divisions and 64-bit index arithmetic per element cost more than the inverse normal): an element advances by
+    // MT_N / 2 per regeneration, i.e. by dq paths and dr rows.
+    const int D = MT_N / 2;
+    const int dq = D / TF, dr = D - dq * TF;
+    const uint32_t magicF = (uint32_t)((0x100000000ull + (unsigned)P.F - 1ull) / (unsigned)P.F);   // row / F == umulhi(row, magicF) for row < 2^16
+    bool tracking = false;
+    int row = 0, plt = 0;                        // row = t * F + f, path within its tile
+    unsigned tpar = 0;                           // parity of the tile index
+    long long next_flush_e = 0;                  // a tile is complete once e has passed this element index
+    {
+        long long tp1 = pb0 + PT; if (tp1 > pb1) tp1 = pb1;
+        next_flush_e = tp1 * TF;
+    }
     while (e < e_hi) {
         regenerate(st[cur], st[cur ^ 1], tid);
         cur ^= 1;
         const long long my = e + tid;
-        if (tid < MT_N / 2 && my >= e_lo && my < e_hi) {
-            const uint32_t hi = temper(st[cur][2 * tid]) >> 6, lo = temper(st[cur][2 * tid + 1]) >> 6;
-            const double u = (double)(((unsigned long long)hi << 26) | (unsigned long long)lo) * 0x1.0p-52;
-            const unsigned rel = (unsigned)(my - e_lo);           // block-relative element (e_lo is a multiple of TF)
-            const unsigned pl = rel / (unsigned)TF;                // path within the block
-            const int row = (int)(rel - pl * (unsigned)TF);
-            const int t = row / P.F;
-            const double z = icdf_as241(u);
-            const float v = __double2float_rn(__dmul_rn(z, P.sqrt_dt[t]));
-            const unsigned ti = pl / (unsigned)PT;
-            tiles[(ti & 1u) * tile_elems + (long long)row * PT + (pl - ti * PT)] = v;
+        if (tid < D && my >= e_lo) {
+            if (!tracking) {                     // once per thread: the only divisions
+                const unsigned rel = (unsigned)(my - e_lo);       // block-relative element (e_lo is a multiple of TF)
+                const unsigned pl = rel / (unsigned)TF;
+                row = (int)(rel - pl * (unsigned)TF);
+                const unsigned ti = pl / (unsigned)PT;
+                plt = (int)(pl - ti * (unsigned)PT);
+                tpar = ti & 1u;
+                tracking = true;
+            }
+            if (my < e_hi) {
+                const uint32_t hi = temper(st[cur][2 * tid]) >> 6, lo = temper(st[cur][2 * tid + 1]) >> 6;
+                const double u = (double)(((unsigned long long)hi << 26) | (unsigned long long)lo) * 0x1.0p-52;
+                const int t = (int)__umulhi((unsigned)row, magicF);
+                const uint32_t slot = (uint32_t)((int)tpar * (int)tile_elems + row * PT + plt);
+                const double q = u - 0.5;
+                if (fabs(q) <= 0.425) {
+                    tiles[slot] = __double2float_rn(__dmul_rn(icdf_central(q), P.sqrt_dt[t]));
+                } else {
+                    const int k = atomicAdd(&q_n, 1);
+                    q_u[k] = u;
+                    q_dst[k] = slot | ((uint32_t)t << 16);
+                }
+            }
+            // advance to this thread's element of the next regeneration
+            row += dr; plt += dq;
+            if (row >= TF) { row -= TF; plt++; }
+            if (plt >= PT) { plt -= PT; tpar ^= 1u; }
+            if (plt >= PT) { plt -= PT; tpar ^= 1u; }
         }
-        e += MT_N / 2;
-        // flush every tile that is now complete
-        while (next_tile < n_tiles) {
-            long long tp1 = pb0 + (next_tile + 1) * PT;
-            if (tp1 > pb1) tp1 = pb1;
-            if (tp1 * TF > e) break;             // last element of the tile not produced yet
+        e += D;
+        // a tile that is now complete is written out — after the tails still queued for it
+        drain(next_tile < n_tiles && next_flush_e <= e);
+        while (next_tile < n_tiles && next_flush_e <= e) {
             __syncthreads();
             const long long tp0 = pb0 + next_tile * PT;
+            long long tp1 = tp0 + PT; if (tp1 > pb1) tp1 = pb1;
             const int npaths = (int)(tp1 - tp0);
             const float* src = tiles + (next_tile & 1) * tile_elems;
             const int warp = tid >> 5, lane = tid & 31;
-            for (int row = warp; row < TF; row += BTHREADS / 32) {
-                float* dst = P.out[row] + (tp0 - P.p0);
-                for (int j = lane; j < npaths; j += 32) dst[j] = src[(long long)row * PT + j];
+            for (int r = warp; r < TF; r += BTHREADS / 32) {
+                float* dst = P.out[r] + (tp0 - P.p0);
+                const float* sr = src + r * PT;
+                for (int j = lane; j < npaths; j += 32) dst[j] = sr[j];
             }
             __syncthreads();
             next_tile++;
+            long long tq1 = pb0 + (next_tile + 1) * PT; if (tq1 > pb1) tq1 = pb1;
+            next_flush_e = tq1 * TF;
         }
     }
 }
