@@ -104,7 +104,7 @@ struct alignas(64) Node {        // exactly one cache line: the cone walk of eve
 static_assert(sizeof(Node) == 64, "Node is one cache line");
 
 struct Options {
-    int64_t flush_threshold = 6144;
+    int64_t flush_threshold = 4096;
     bool fuse = true;
     bool profile = false;       // time every interpreter launch with CUDA events (benchmarks)
     // interpreter scheduling knobs (see codegen.cpp: Gen::schedule / Gen::launch)

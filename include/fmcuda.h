@@ -133,7 +133,7 @@ int fmc_mt19937_raw(int seed_mode, int64_t seed, uint64_t skip, int64_t count, u
 /* ---- execution control ---- */
 int fmc_flush(void);                    /* execute every pending node that is still referenced */
 int fmc_sync(void);                     /* flush + wait for the device (cuCtxSynchronize, RVC:472-476) */
-/* options: "flush_threshold" (pending nodes before an automatic flush; default 6144),
+/* options: "flush_threshold" (pending nodes before an automatic flush; default 4096),
  *          "fuse" (1 default; 0 = execute every op as its own kernel, the reference's execution model),
  *          "profile" (0 default; see fmc_profile_read);
  *          interpreter scheduling knobs (tuning / tests; defaults in csrc/runtime.h): "ring_max", "ring_min", "target_ctas",
