@@ -306,6 +306,27 @@ def run_ours(args) -> None:
     st3 = fc.stats()
     pinned_ms = max_over_ranks(1e3 * pinned_s) / args.steps
 
+    # ---- the same step for PRICE products (ValueUnit.VALUE): the objective function collects all 144 value vectors and averages
+    # them in a second loop; the runtime sums the vectors one flush produced in one launch. Single rank only; not the headline:
+    # T-ATM calibrates to implied volatilities, whose products take their own average one by one (T-ATM:261,511).
+    price_products = None
+    if world == 1:
+        model.set_price_products(True)
+        for _ in range(max(1, min(args.warmup, 3))):
+            values_pp = model.step()
+        capi.timer_start()
+        for _ in range(args.steps):
+            values_pp = model.step()
+        pp_ms = capi.timer_stop() / args.steps
+        model.set_price_products(False)
+        rel = rel_diff(values_pp, values)
+        price_products = {"ms_per_step": pp_ms, "value": total_paths * N_PERIODS / (pp_ms * 1e-3), "unit": UNIT,
+                          "max_rel_diff_vs_headline_values": rel, "ok": bool(rel <= 1e-9),
+                          "what": "all product value vectors first, their averages in a second loop (AbstractLIBORCovarianceModelParametric's "
+                                  "objective function with ValueUnit.VALUE products); batched averages in the runtime"}
+        if not price_products["ok"]:
+            raise SystemExit(f"bench: price-product step differs from the headline step: {price_products}")
+
     # ---- the calibration itself (BASELINE.json metric: "LMM ATM calibration sec"): Levenberg-Marquardt with the settings of
     # T-ATM:317-340 on the bench's model for a fixed budget of iterations, and on T-ATM's own 10 000 paths to convergence ----
     calibration = None
@@ -474,7 +495,7 @@ def run_ours(args) -> None:
         "nodes_stored_per_step": st["n_nodes_stored"] / args.steps, "nodes_fused_per_step": st["n_nodes_fused"] / args.steps,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "host_profile": host_prof,
         ("parity" if world == 1 else "multi_gpu_parity"): parity,
-        "calibration": calibration, "extras": extras,
+        "calibration": calibration, "price_products_step": price_products, "extras": extras,
         "price_check": {"first_values": [float(v) for v in values[:3]], "e2e_equal": bool((values == values_e2e).all()),
                         "e2e_pinned_equal": bool((values == values_pinned).all())},
     }

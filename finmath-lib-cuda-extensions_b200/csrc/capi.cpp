@@ -403,7 +403,7 @@ int fmc_sync(void) {
 }
 static void set_option_locked(Runtime& rt, const char* key, double value) {
     // everything that steers the code generator invalidates the cached tapes
-    static const char* const keeps_cache[] = {"flush_threshold", "profile", "tape_upload_stream", "exchange", "exchange_timeout_s", "p2p_reduce", "zero_copy_reduce", "leaf_reduce_kernel"};
+    static const char* const keeps_cache[] = {"flush_threshold", "profile", "tape_upload_stream", "exchange", "exchange_timeout_s", "p2p_reduce", "zero_copy_reduce", "leaf_reduce_kernel", "batch_reduce"};
     bool keep = false;
     for (const char* k : keeps_cache) keep = keep || !std::strcmp(key, k);
     if (!keep) tape_cache_clear();
@@ -423,6 +423,7 @@ static void set_option_locked(Runtime& rt, const char* key, double value) {
     else if (!std::strcmp(key, "grid_limit")) rt.opt.grid_limit = std::max(0, (int)value);
     else if (!std::strcmp(key, "fuse_ops")) rt.opt.fuse_ops = value != 0.0;
     else if (!std::strcmp(key, "fuse_ops2")) rt.opt.fuse_ops2 = value != 0.0;
+    else if (!std::strcmp(key, "batch_reduce")) { rt.opt.batch_reduce = value != 0.0; rt.flush_batches.clear(); rt.prefetched.clear(); }
     else if (!std::strcmp(key, "tape_upload_stream")) rt.opt.tape_upload_stream = value != 0.0;
     else if (!std::strcmp(key, "p2p_reduce")) rt.opt.p2p_reduce = value != 0.0;
     else if (!std::strcmp(key, "exchange")) { const int m = (int)value; if (m < 0 || m > 2) fail(FMC_ERR_INVALID, "exchange must be 0 (NCCL), 1 (in-kernel peer memory) or 2 (shared host memory)"); rt.opt.exchange = m; }
@@ -473,6 +474,7 @@ int fmc_get_option(const char* key, double* value) {
         else if (!std::strcmp(key, "grid_limit")) *value = rt.opt.grid_limit;
         else if (!std::strcmp(key, "fuse_ops")) *value = rt.opt.fuse_ops ? 1.0 : 0.0;
         else if (!std::strcmp(key, "fuse_ops2")) *value = rt.opt.fuse_ops2 ? 1.0 : 0.0;
+        else if (!std::strcmp(key, "batch_reduce")) *value = rt.opt.batch_reduce ? 1.0 : 0.0;
         else if (!std::strcmp(key, "p2p_reduce")) *value = rt.opt.p2p_reduce ? 1.0 : 0.0;
         else if (!std::strcmp(key, "p2p_ready")) *value = rt.p2p_ready ? 1.0 : 0.0;
         else if (!std::strcmp(key, "exchange")) *value = rt.opt.exchange;

@@ -1136,6 +1136,18 @@ bool Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
     if (spec.weight >= 0) materialize(spec.weight);
     const bool empty = nodes[idx].n == 0;
     if (empty && comm_size == 1) { out[0] = 0.0; out[1] = NAN; out[2] = NAN; return false; }
+    // batched averages (runtime.h): a sum that an earlier batch already delivered, or the sums of idx and of the vectors that
+    // were materialised together with it, in one launch
+    if (opt.batch_reduce && comm_size == 1 && spec.mode == RM_SUM && spec.weight < 0 && !empty) {
+        auto pf = prefetched.find(idx);
+        if (pf != prefetched.end() && pf->second.gen == nodes[idx].gen && nodes[idx].state == NS_MAT) {
+            out[0] = (double)nodes[idx].n; out[1] = pf->second.sum; out[2] = 0.0;
+            reduce_streak = true;
+            return false;
+        }
+        if (nodes[idx].state == NS_LAZY && reduce_streak) flush_all();     // the tail of a series of averages: same treatment
+        if (nodes[idx].state == NS_MAT && opt.leaf_reduce_kernel && reduce_batch(idx, out)) { reduce_streak = true; return false; }
+    }
     const bool p2p = use_p2p();
     bool xhost_launch = false;                // this reduction's kernel publishes into the shared host table
     // the result slot of this reduction (released when the result has been read, also on the error paths)

@@ -30,6 +30,23 @@ struct ReduceParams {
     Exchange xchg;            // peer tables of a path-sharded run (reduce_common.cuh)
 };
 cudaError_t launch_reduce(const ReduceParams& P, int grid, cudaStream_t stream);
+// The sums of K materialised vectors of the same length in ONE launch (Runtime::reduce_batch: the averages of all vectors one
+// flush produced, e.g. the calibration products of one objective-function evaluation). blocks_per_vec CTAs work on each vector
+// exactly as launch_reduce's grid of that size would (same tiles, same order of additions: the sum of a vector does not
+// depend on whether it was reduced alone or in a batch). The last CTA of each vector writes its sum to host_out[j] (mapped
+// pinned memory), the last of those writes the ticket to host_out[BATCH_MAX].
+constexpr int BATCH_MAX = 256;
+struct BatchSumParams {
+    long long n;
+    int k;                      // vectors, <= BATCH_MAX
+    int blocks_per_vec;
+    double* partials;           // [k][blocks_per_vec][2] {count, sum}
+    unsigned int* counters;     // [BATCH_MAX + 1], zero between launches
+    double* host_out;           // [BATCH_MAX + 1] mapped pinned memory: sums, then the ticket
+    double ticket;
+    const float* x[BATCH_MAX];
+};
+cudaError_t launch_batch_sum(const BatchSumParams& P, cudaStream_t stream);
 // dst[i] = (float)src[i]; both device pointers, 8-byte aligned (dst offsets of the upload path are multiples of the chunk size)
 cudaError_t launch_cast_f64_f32(const double* src, float* dst, long long n, int sm_count, cudaStream_t stream);
 int reduce_tile_elems();

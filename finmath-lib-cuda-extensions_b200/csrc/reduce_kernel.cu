@@ -132,7 +132,69 @@ reduce_kernel(const __grid_constant__ ReduceParams P)
     }
 }
 
+// ---- sums of K vectors in one launch (kernels.h: BatchSumParams) ----
+__global__ void __launch_bounds__(RT)
+batch_sum_kernel(const __grid_constant__ BatchSumParams P)
+{
+    const int j = blockIdx.x / P.blocks_per_vec, b = blockIdx.x - j * P.blocks_per_vec, B = P.blocks_per_vec;
+    const float* __restrict__ x = P.x[j];
+    const long long n = P.n;
+    const int tid = threadIdx.x;
+    double acc = 0.0;
+    long long cnt = 0;                                                  // merge() skips empty partials: keep the counts like reduce_kernel
+    const long long n_tiles = n / RTILE;
+    for (long long t = b; t < n_tiles; t += B) {                       // the walk of reduce_kernel<RM_SUM> with gridDim.x == B
+        const long long base = t * RTILE + (long long)tid * 4;
+        float4 v[RU];
+#pragma unroll
+        for (int u = 0; u < RU; u++) v[u] = ldg4(x + base + (long long)u * RT * 4);
+#pragma unroll
+        for (int u = 0; u < RU; u++) acc += ((double)v[u].x + (double)v[u].y) + ((double)v[u].z + (double)v[u].w);
+        cnt += 4 * RU;
+    }
+    if (b == 0)
+        for (long long i = n_tiles * RTILE + tid; i < n; i += RT) { acc += (double)x[i]; cnt++; }
+
+    __shared__ Part red_smem[RT / 32];
+    __shared__ bool is_last;
+    Part part = {(double)cnt, acc, 0.0};
+    Part blk = block_reduce(RM_SUM, part, red_smem);
+    if (tid == 0) {
+        double* dst = P.partials + 2 * ((long long)j * B + b);
+        dst[0] = blk.c; dst[1] = blk.v;
+        __threadfence();
+        is_last = (atomicAdd(P.counters + j, 1u) == (unsigned)B - 1u);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    Part q = {0.0, 0.0, 0.0};
+    for (int k = tid; k < B; k += RT) {
+        const volatile double* src = P.partials + 2 * ((long long)j * B + k);
+        Part t = {src[0], src[1], 0.0};
+        q = merge(RM_SUM, q, t);
+    }
+    q = block_reduce(RM_SUM, q, red_smem);
+    if (tid == 0) {
+        P.counters[j] = 0u;
+        volatile double* h = P.host_out;
+        h[j] = q.v;
+        __threadfence_system();
+        if (atomicAdd(P.counters + BATCH_MAX, 1u) == (unsigned)P.k - 1u) {
+            __threadfence_system();
+            P.counters[BATCH_MAX] = 0u;
+            h[BATCH_MAX] = P.ticket;
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_batch_sum(const BatchSumParams& P, cudaStream_t stream) {
+    if (P.k < 1 || P.k > BATCH_MAX || P.blocks_per_vec < 1) return cudaErrorInvalidValue;
+    batch_sum_kernel<<<P.k * P.blocks_per_vec, RT, 0, stream>>>(P);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_reduce(const ReduceParams& P, int grid, cudaStream_t stream) {
     switch (P.mode) {

@@ -82,6 +82,10 @@ void Runtime::shutdown() {
     tape_kernel_teardown();
     tape_cache_clear();
     if (d_upload) { cudaFree(d_upload); d_upload = nullptr; }
+    if (d_batch_partials) { cudaFree(d_batch_partials); d_batch_partials = nullptr; }
+    if (d_batch_counters) { cudaFree(d_batch_counters); d_batch_counters = nullptr; }
+    if (h_batch) { cudaFreeHost(h_batch); h_batch = nullptr; h_batch_dev = nullptr; }
+    flush_batches.clear(); prefetched.clear(); reduce_streak = false; batch_ticket = 0.0;
     for (auto& kv : pinned_) cudaFreeHost((void*)kv.first);
     pinned_.clear();
     cudaFree(d_partials); cudaFree(d_counter); cudaFree(d_result); cudaFreeHost(h_result); cudaFreeHost(h_ticket);
@@ -143,6 +147,7 @@ int32_t Runtime::record(NodeOp op, int64_t n, Operand a, Operand b, Operand c) {
     n_lazy++; n_live_handles++;
     pending.push_back(idx);
     stats.n_ops++;
+    reduce_streak = false;
     return idx;
 }
 
@@ -174,6 +179,7 @@ void Runtime::maybe_free(int32_t first) {
             }
         } else if (nd.buf) {
             pool.free(nd.buf);
+            if (!prefetched.empty()) prefetched.erase(idx);
         }
         nd.buf = nullptr; nd.state = NS_FREE; nd.gen++;
         if (nd.gen == 0) nd.gen = 1;
@@ -207,7 +213,101 @@ void Runtime::flush_all() {
         if (nd.state == NS_LAZY && nd.ext_refs > 0) targets.push_back(idx);
     }
     pending.clear();
-    if (!targets.empty()) run_cone(targets, nullptr);
+    if (targets.empty()) return;
+    run_cone(targets, nullptr);
+    // the vectors this flush materialised together (see runtime.h: batched averages)
+    if (opt.batch_reduce && comm_size == 1 && targets.size() >= 2) {
+        FlushBatch fb;
+        fb.id = ++flush_batch_seq;
+        if (fb.id == 0) fb.id = ++flush_batch_seq;
+        fb.members.reserve(targets.size());
+        for (int32_t t : targets) {
+            Node& nd = nodes[t];
+            if (nd.state != NS_MAT || nd.ext_refs == 0 || batch_of(nd) == fb.id) continue;
+            set_batch_of(nd, fb.id);
+            fb.members.emplace_back(t, nd.gen);
+        }
+        if (fb.members.size() >= 2) {
+            flush_batches.push_back(std::move(fb));
+            if (flush_batches.size() > 64) flush_batches.pop_front();
+        }
+    }
+}
+
+// The sums of the still-referenced, unconsumed vectors that were materialised by the same flush as node idx, in one launch.
+// Returns false (nothing done) when idx has no such siblings.
+bool Runtime::reduce_batch(int32_t idx, double out[3]) {
+    const Node& me = nodes[idx];
+    const uint32_t id = batch_of(me);
+    if (id == 0) return false;
+    FlushBatch* fb = nullptr;
+    for (auto it = flush_batches.rbegin(); it != flush_batches.rend(); ++it) if (it->id == id) { fb = &*it; break; }
+    if (!fb) return false;
+    // candidates in recording order, starting with idx itself (at most BATCH_MAX: the ones recorded right after idx first)
+    std::vector<int32_t> cand;
+    cand.reserve(std::min<size_t>(fb->members.size(), (size_t)BATCH_MAX));
+    size_t at = fb->members.size();
+    for (size_t k = 0; k < fb->members.size(); k++) if (fb->members[k].first == idx && fb->members[k].second == me.gen) { at = k; break; }
+    if (at == fb->members.size()) return false;
+    for (size_t d = 0; d < fb->members.size() && cand.size() < (size_t)BATCH_MAX; d++) {
+        const auto& m = fb->members[(at + d) % fb->members.size()];
+        const Node& nd = nodes[m.first];
+        if (nd.state != NS_MAT || nd.gen != m.second || nd.ext_refs == 0 || nd.int_refs != 0 || nd.n != me.n || !nd.buf) continue;
+        if (batch_of(nd) != id) continue;
+        auto pf = prefetched.find(m.first);
+        if (pf != prefetched.end() && pf->second.gen == nd.gen) continue;
+        cand.push_back(m.first);
+    }
+    if (cand.size() < 2 || cand[0] != idx) return false;
+    const int64_t n = me.n;
+    const int64_t tiles = (n + reduce_tile_elems() - 1) / reduce_tile_elems();
+    int B = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)sm_count * 8));    // the grid Runtime::reduce gives launch_reduce
+    B = std::min(B, max_grid);
+    if (opt.grid_limit > 0) B = std::min(B, opt.grid_limit);
+    if (!d_batch_partials) {
+        FMC_CUDA(cudaMalloc(&d_batch_partials, sizeof(double) * 2 * (size_t)BATCH_MAX * (size_t)max_grid));
+        FMC_CUDA(cudaMalloc(&d_batch_counters, sizeof(unsigned int) * (BATCH_MAX + 1)));
+        FMC_CUDA(cudaMemsetAsync(d_batch_counters, 0, sizeof(unsigned int) * (BATCH_MAX + 1), stream));
+        FMC_CUDA(cudaHostAlloc(&h_batch, sizeof(double) * (BATCH_MAX + 1), cudaHostAllocMapped));
+        FMC_CUDA(cudaHostGetDevicePointer(&h_batch_dev, h_batch, 0));
+        for (int i = 0; i <= BATCH_MAX; i++) h_batch[i] = 0.0;
+    }
+    static thread_local BatchSumParams P;
+    P.n = n; P.k = (int)cand.size(); P.blocks_per_vec = B;
+    P.partials = d_batch_partials; P.counters = d_batch_counters; P.host_out = h_batch_dev;
+    P.ticket = (batch_ticket += 1.0);
+    for (size_t k = 0; k < cand.size(); k++) P.x[k] = nodes[cand[k]].buf;
+    if (opt.profile) profile_begin();
+    const auto t_launch0 = std::chrono::steady_clock::now();
+    FMC_CUDA(launch_batch_sum(P, stream));
+    hostprof.launch += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_launch0).count();
+    if (opt.profile) profile_end(4ull * (uint64_t)n * (uint64_t)cand.size());
+    stats.n_kernels++; stats.n_flushes++;
+    const auto t_sync0 = std::chrono::steady_clock::now();
+    const uint64_t stamp_at_launch = pool.free_stamp;
+    volatile double* h = h_batch;
+    unsigned spins = 0;
+    auto t_query = t_sync0;
+    while (h[BATCH_MAX] != P.ticket) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+        if ((++spins & 0x3ffu) == 0u) {
+            const auto now = std::chrono::steady_clock::now();
+            if (now - t_query < std::chrono::microseconds(200)) continue;
+            t_query = now;
+            const cudaError_t q = cudaStreamQuery(stream);
+            if (q == cudaSuccess) { if (h[BATCH_MAX] == P.ticket) break; fail(FMC_ERR_CUDA, "batched reduction finished without publishing its results"); }
+            if (q != cudaErrorNotReady) FMC_CUDA(q);
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    for (size_t k = 1; k < cand.size(); k++) prefetched[cand[k]] = Prefetched{nodes[cand[k]].gen, h[k]};
+    out[0] = (double)n; out[1] = h[0]; out[2] = 0.0;
+    settled_stamp = std::max(settled_stamp, stamp_at_launch);
+    hostprof.sync += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_sync0).count();
+    stats.d2h += 8 * (uint64_t)cand.size();
+    return true;
 }
 
 void Runtime::materialize(int32_t idx) {

@@ -11,6 +11,8 @@
 #include <thread>
 #include <string>
 #include <unordered_map>
+#include <cstring>
+#include <deque>
 #include <vector>
 
 #include "../../include/fmcuda.h"
@@ -132,6 +134,8 @@ struct Options {
                                     // let a few kernels drop to one CTA per SM (8.36 ms simulation); 8: 8.14 ms, 4: 8.00 ms but more spills
     bool tape_upload_stream = true; // long tapes reach the device through the copy stream, ahead of the kernels queued on the compute stream
     bool tape_cache = true;         // replay the launches of a cone whose structure was lowered before (codegen.cpp)
+    bool batch_reduce = true;       // getAverage() of a vector that one flush materialised together with others: the sums of all of them in one
+                                    // launch, the others' results kept for the calls that follow (Runtime::reduce_batch)
 };
 
 struct Stats {
@@ -213,6 +217,23 @@ public:
     double reduce_ticket = 0.0;
     RuntimeLock* held = nullptr;   // the C-ABI call's lock on `mu` (capi.cpp: guarded)
     double last_tape_ticket = 0.0;      // ticket of the last fused chain -> reduce launch (0: none published)
+    // Batched averages. A caller that first builds many result vectors and then asks for their averages one by one (finmath-lib's
+    // calibration objective: all product values, then value.getAverage() in a second loop) would pay one launch and one blocking
+    // round trip per vector. flush_all() remembers which still-referenced vectors it materialised together; the first
+    // getAverage() of one of them sums ALL of them in one launch (reduce_kernel.cu: batch_sum_kernel) and keeps the other sums
+    // for the calls that follow. Bit-identical to the single-vector kernel; single-rank runs only.
+    struct FlushBatch { uint32_t id; std::vector<std::pair<int32_t, uint32_t>> members; };   // {node, generation}
+    std::deque<FlushBatch> flush_batches;                                // the most recent ones
+    uint32_t flush_batch_seq = 0;
+    struct Prefetched { uint32_t gen; double sum; };
+    std::unordered_map<int32_t, Prefetched> prefetched;                  // node -> its sum, until the node is freed
+    bool reduce_streak = false;         // the last reduction was served by a batch and nothing was recorded since
+    double* d_batch_partials = nullptr; unsigned int* d_batch_counters = nullptr;
+    double* h_batch = nullptr; double* h_batch_dev = nullptr;            // mapped pinned [BATCH_MAX + 1]
+    double batch_ticket = 0.0;
+    static uint32_t batch_of(const Node& nd) { uint32_t b; std::memcpy(&b, &nd.imm[2], 4); return b; }      // valid for NS_MAT nodes (imm unused)
+    static void set_batch_of(Node& nd, uint32_t b) { std::memcpy(&nd.imm[2], &b, 4); }
+    bool reduce_batch(int32_t idx, double out[3]);                       // true: out = {count, sum, 0} of node idx
     int max_grid = 0;
 
     // graph

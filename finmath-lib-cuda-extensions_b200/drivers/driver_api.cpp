@@ -127,6 +127,7 @@ struct LmmHandle {
     PiecewiseConstantVolatility vol;
     std::unique_ptr<LIBORMarketModel> last_model;               // keeps the last simulation alive (Bermudan on top of it)
     int valuation_threads = 1;                                  // host threads valuing the calibration products (T-ATM:319: 1)
+    bool price_products = false;                                // workloads.hpp: lmm_value_products
 };
 
 template <typename F>
@@ -216,7 +217,7 @@ int fmd_lmm_step(void* handle, const double* vol_params, int from_host, double* 
             bm = h->host_brownian;
         }
         h->last_model.reset(new LIBORMarketModel(h->factory, bm, h->L0, h->vol));
-        const std::vector<double> v = lmm_value_products(*h->last_model, h->products, h->valuation_threads);
+        const std::vector<double> v = lmm_value_products(*h->last_model, h->products, h->valuation_threads, h->price_products);
         std::memcpy(values_out, v.data(), sizeof(double) * v.size());
     });
 }
@@ -225,6 +226,9 @@ int fmd_lmm_set_valuation_threads(void* handle, int threads) {
         if (threads < 1 || threads > 64) throw std::runtime_error("valuation threads must be in 1..64");
         static_cast<LmmHandle*>(handle)->valuation_threads = threads;
     });
+}
+int fmd_lmm_set_price_products(void* handle, int on) {
+    return guarded([&] { static_cast<LmmHandle*>(handle)->price_products = on != 0; });
 }
 // selected simulated rates for parity checks: L_i(t) realisations
 int fmd_lmm_get_libor(void* handle, int time_index, int libor_index, double* out, int64_t n) {
@@ -295,7 +299,7 @@ int fmd_lmm_calibrate(void* handle, int max_iterations, double accuracy, double 
             PiecewiseConstantVolatility vol = h->vol;
             vol.param = p;
             h->last_model.reset(new LIBORMarketModel(h->factory, h->device_brownian, h->L0, vol));
-            std::vector<double> v = lmm_value_products(*h->last_model, h->products, h->valuation_threads);
+            std::vector<double> v = lmm_value_products(*h->last_model, h->products, h->valuation_threads, h->price_products);
             for (size_t k = 0; k < nprod; k++) v[k] = atm_normal_implied_vol(v[k], annuity[k], maturity[k]);
             return v;
         };

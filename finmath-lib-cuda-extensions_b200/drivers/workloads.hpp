@@ -7,6 +7,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <functional>
 #include <map>
 #include <mutex>
@@ -407,10 +408,23 @@ inline LevenbergMarquardtResult levenberg_marquardt(const std::function<std::vec
 // one pass of the calibration inner loop: simulate the model, value every calibration product.
 // threads > 1: the products are valued by that many host threads (product k by thread k mod threads), the way the
 // library's calibration does with numberOfThreads > 1; the reference test runs with ONE thread (T-ATM:319), the default.
-inline std::vector<double> lmm_value_products(LIBORMarketModel& model, const std::vector<SwaptionSpec>& products, int threads = 1) {
+// price_products: how the averages are taken.
+//   false (default, T-ATM:261,511): products in ValueUnit.VOLATILITYNORMAL — SwaptionSimple.getValue() takes value.getAverage()
+//         itself to imply the volatility, i.e. one blocking reduction per product, interleaved with the recording of the next;
+//   true: products in ValueUnit.VALUE (the alternative LIBORMarketModelCalibrationTest.java:151-154 names) — the objective
+//         function of AbstractLIBORCovarianceModelParametric.getCloneCalibrated first collects all product value vectors and
+//         then calls getAverage() on each in a second loop (finmath-lib 5.1.3 is not in /root/reference: restated from
+//         memory). The runtime then sums all of them in a few launches (fmcuda: batched averages).
+inline std::vector<double> lmm_value_products(LIBORMarketModel& model, const std::vector<SwaptionSpec>& products, int threads = 1, bool price_products = false) {
     model.simulate();
     std::vector<double> values(products.size());
     if (threads <= 1) {
+        if (price_products) {
+            std::vector<RV> v(products.size());
+            for (size_t k = 0; k < products.size(); k++) v[k] = swaption_values(model, products[k]);
+            for (size_t k = 0; k < products.size(); k++) values[k] = v[k]->getAverage();
+            return values;
+        }
         for (size_t k = 0; k < products.size(); k++) values[k] = swaption_values(model, products[k])->getAverage();
         return values;
     }

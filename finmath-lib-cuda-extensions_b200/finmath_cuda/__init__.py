@@ -6,7 +6,7 @@ MonteCarloConditionalExpectationRegression. No CPU fallback: importing works wit
 table can be checked), creating a stochastic vector without one raises.
 """
 from . import _capi
-from ._capi import CudaError, ensure_init, pool_trim, reset_stats, set_option, shutdown, stats, sync
+from ._capi import CudaError, ensure_init, flush, pool_trim, reset_stats, set_option, shutdown, stats, sync
 from .random_variable import RandomVariable, RandomVariableCuda, RandomVariableCudaFactory
 from .brownian_motion import BrownianMotionCuda, TimeDiscretization
 from .conditional_expectation import MonteCarloConditionalExpectationRegression
@@ -15,5 +15,5 @@ from . import distributed
 
 __all__ = [
     "RandomVariable", "RandomVariableCuda", "RandomVariableCudaFactory", "BrownianMotionCuda", "TimeDiscretization",
-    "MonteCarloConditionalExpectationRegression", "RandomVariableDifferentiableAAD", "RandomVariableDifferentiableAADFactory", "CudaError", "ensure_init", "shutdown", "stats", "set_option", "sync", "pool_trim", "reset_stats", "distributed",
+    "MonteCarloConditionalExpectationRegression", "RandomVariableDifferentiableAAD", "RandomVariableDifferentiableAADFactory", "CudaError", "ensure_init", "shutdown", "stats", "set_option", "sync", "flush", "pool_trim", "reset_stats", "distributed",
 ]

@@ -184,6 +184,11 @@ def timer_stop() -> float:
     return float(ms.value)
 
 
+def flush() -> None:
+    """Execute every pending operation that is still referenced (no wait)."""
+    check(load().fmc_flush())
+
+
 def sync() -> None:
     """Execute everything pending and wait for the device (cuCtxSynchronize, RandomVariableCuda.java:472-476)."""
     check(load().fmc_sync())

@@ -47,6 +47,7 @@ class DriverLib:
         L.fmd_lmm_set_parameters.argtypes = [vp, vp]
         L.fmd_lmm_calibrate.argtypes = [vp, i32, dbl, dbl, dbl, vp, vp]
         L.fmd_lmm_set_valuation_threads.argtypes = [vp, i32]
+        L.fmd_lmm_set_price_products.argtypes = [vp, i32]
         self.L = L
 
     def check(self, rc: int) -> None:
@@ -151,6 +152,12 @@ class Lmm:
     def set_valuation_threads(self, threads: int) -> None:
         """Host threads that value the calibration products of step() (the reference test uses one, T-ATM:319)."""
         self.lib.check(self.lib.L.fmd_lmm_set_valuation_threads(self.h, int(threads)))
+
+    def set_price_products(self, on: bool) -> None:
+        """How step() takes the averages: False (default) one blocking getAverage() per product while the next is recorded
+        (implied-volatility products, T-ATM:261,511); True all product value vectors first, their averages in a second loop
+        (price products, the objective function's own loop) — the runtime then batches the reductions."""
+        self.lib.check(self.lib.L.fmd_lmm_set_price_products(self.h, 1 if on else 0))
 
     def libor(self, time_index: int, libor_index: int) -> np.ndarray:
         out = np.empty(self.local_paths)

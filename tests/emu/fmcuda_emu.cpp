@@ -509,6 +509,16 @@ cudaError_t launch_reduce(const ReduceParams& P, int, cudaStream_t) {
     if (P.host_result) { P.host_result[0] = c; P.host_result[1] = v; P.host_result[2] = m2; P.host_result[3] = P.ticket; }
     return cudaSuccess;
 }
+cudaError_t launch_batch_sum(const BatchSumParams& P, cudaStream_t) {
+    if (std::getenv("FMC_EMU_NOEXEC")) { P.host_out[BATCH_MAX] = P.ticket; return cudaSuccess; }
+    for (int j = 0; j < P.k; j++) {
+        double s = 0;
+        for (long long i = 0; i < P.n; i++) s += (double)P.x[j][i];
+        P.host_out[j] = s;
+    }
+    P.host_out[BATCH_MAX] = P.ticket;
+    return cudaSuccess;
+}
 int reduce_tile_elems() { return 4096; }
 // FMC_EMU_FAKE_BROWNIAN=1 (tape-shape studies of the workload drivers only): increments from a throw-away generator,
 // NOT the MT19937 stream — the Brownian parity tests are never run against the emulator.

@@ -614,6 +614,58 @@ def test_fuzzed_programs_match_the_oracle(fc, O):
         for k_, v_ in SCHED_DEFAULTS.items(): fc.set_option(k_, v_)
 
 
+@pytest.mark.parametrize("n", [5, 4099, 70001])
+def test_batched_averages_equal_single_reductions(fc, O, n):
+    """A caller that builds many result vectors first and averages them afterwards (finmath-lib's calibration objective:
+    all product values, then value.getAverage() in a second loop): the vectors one flush materialised together are summed
+    in ONE launch at the first getAverage() and the other sums are handed out by the calls that follow. The sums must be
+    bit-identical to the single-vector reduction, survive released / re-used handles, and never serve a consumed vector."""
+    rng = np.random.default_rng(n)
+    base = [rng.standard_normal(n) for _ in range(3)]
+
+    def products(leaves, k):
+        return [leaves[j % 3].mult(0.25 + 0.125 * j).add(leaves[(j + 1) % 3]).floor(-0.5).div(1.0 + 0.5 * j) for j in range(k)]
+
+    try:
+        results = {}
+        for batch in (0, 1):
+            fc.set_option("batch_reduce", batch)
+            leaves = [fc.RandomVariableCuda(0.0, b) for b in base]
+            k0 = fc.stats()["n_kernels"]
+            vs = products(leaves, 12)
+            fc.flush()
+            k1 = fc.stats()["n_kernels"]
+            got = [v.getAverage() for v in vs[:6]]
+            del vs[7]                                   # released before its turn: the slot may be re-used by the next vector
+            w = leaves[0].mult(3.0)                     # recorded between two averages: not part of any batch
+            got.append(w.getAverage())
+            got += [v.getAverage() for v in vs[6:]]
+            got.append(vs[0].getAverage())              # asked twice
+            c = vs[1].add(1.0)                          # a consumer of a batched vector: its own average is a new reduction
+            got.append(c.getAverage())
+            got.append(vs[1].getAverage())
+            k2 = fc.stats()["n_kernels"]
+            results[batch] = got
+            if batch:
+                assert k2 - k1 <= 6, "12 averages after one flush must not cost 12 launches"
+            assert k1 > k0
+        assert all(a == b for a, b in zip(results[0], results[1])), (results[0], results[1])
+        # against the oracle
+        fl = [O.from_f64(b) for b in base]
+        for j in range(6):
+            po = O.op_vs(O.DIV, O.op_vs(O.FLOOR, O.op_vv(O.ADD, O.op_vs(O.MULT, fl[j % 3], 0.25 + 0.125 * j), fl[(j + 1) % 3]), -0.5), 1.0 + 0.5 * j)
+            want = O.average(po)
+            assert abs(results[1][j] - want) <= 1e-10 * abs(want) + 1e-300, (j, results[1][j], want)
+        # a series of averages whose tail was never flushed: the first is a fused chain -> reduce, results stay the same
+        fc.set_option("batch_reduce", 1)
+        leaves = [fc.RandomVariableCuda(0.0, b) for b in base]
+        vs = products(leaves, 5)
+        lazy = [v.getAverage() for v in vs]
+        assert all(abs(a - b) <= 1e-12 * abs(b) for a, b in zip(lazy, results[1][:5]))
+    finally:
+        fc.set_option("batch_reduce", 1)
+
+
 def test_tape_cache_replays_are_bit_exact(fc):
     """a cone whose structure was lowered before is replayed from the tape cache with the new buffers and
     immediates patched in. Replays must be indistinguishable from fresh code generation: same structure, three sets of

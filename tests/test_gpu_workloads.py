@@ -54,6 +54,17 @@ def test_lmm_simulation_and_swaptions_match_oracle(libs, paths):
     mg.set_valuation_threads(3)
     assert np.array_equal(mg.step(p), vg_p)
     mg.set_valuation_threads(1)
+    # price products: all value vectors first, the averages in a second loop (the runtime sums them in batches) — the same
+    # values, a handful of reduction launches instead of one per product
+    mg.set_price_products(True)
+    import finmath_cuda as fcm
+    k0 = fcm.stats()["n_kernels"]
+    v2 = mg.step(p)
+    k1 = fcm.stats()["n_kernels"]
+    mg.set_price_products(False)
+    assert np.allclose(v2, vg_p, rtol=1e-12, atol=0)
+    mg.step(p)
+    assert k1 - k0 < fcm.stats()["n_kernels"] - k1, "batched averages must launch fewer kernels than one reduction per product"
     # model reproduces its own flat 0.5% volatility to MC accuracy
     iv = mg.implied_vols(mg.step(mg.parameters() * 0 + 0.005))
     assert np.all(np.abs(iv - 0.005) < 0.0015)
