@@ -180,8 +180,10 @@ def run_reference(args) -> None:
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (an LMM Euler-step launch of the tape
 # interpreter at 1 Mi paths) from one `ncu --set full` capture; NOT measured in this run, NOT comparable with the per-step
 # algorithmic bytes: reported under its own name with the capture it came from (None until this round's capture exists).
-NCU_DRAM_BYTES_DOMINANT_LAUNCH = None
-NCU_CAPTURE_FILE = None
+NCU_DRAM_BYTES_DOMINANT_LAUNCH = 532_298_240     # 294.57 MB read + 237.73 MB written, second launch of profiles/prof_sim_r2.txt (101.95 us)
+NCU_ALGORITHMIC_BYTES_OF_THAT_LAUNCH = 289_406_976   # its tape: 2 leaf vectors + 67 result vectors x 4 MiB (the 69 rates of the previous
+                                                     # step it re-reads were stored by the launch before it in the same flush: not algorithmic)
+NCU_CAPTURE_FILE = "profiles/prof_sim_r2.txt (ncu --set full --clock-control none -k regex:tape_kernel -s 234 -c 3 of bench.py --steps 2 --warmup 1; launch list profiles/launches_r2.txt)"
 
 PARITY_REL_TOL = 1e-4       # north star: "Monte-Carlo prices ... match within 1e-4 relative on identical seeds"
 
@@ -449,6 +451,7 @@ def run_ours(args) -> None:
                 "achieved_touched": touched.value / (prof["tape_ms"] * 1e-3) / 1e9 if prof["tape_ms"] > 0 else 0.0,
                 "frac_touched": (touched.value / (prof["tape_ms"] * 1e-3) / 1e9) / peak if prof["tape_ms"] > 0 else 0.0}
     roofline["ncu_dram_bytes_dominant_launch"] = NCU_DRAM_BYTES_DOMINANT_LAUNCH
+    roofline["ncu_algorithmic_bytes_of_that_launch"] = NCU_ALGORITHMIC_BYTES_OF_THAT_LAUNCH
     roofline["ncu_capture"] = NCU_CAPTURE_FILE
 
     # ---- parity of what was timed: the CPU oracle on a bounded sample, the GPU on exactly the same paths ----
