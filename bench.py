@@ -171,7 +171,7 @@ def run_reference(args) -> None:
         "cpu_double_array": {"value": value64, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{total} paths, 1 step; C++ restatement of finmath-lib's RandomVariableFromDoubleArray (not part of the ratio)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "calibration": calibration, "extras": extras,
+        "calibration": calibration,
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)

@@ -215,3 +215,17 @@ def test_java_shim_binds_only_declared_symbols_with_matching_arity():
     assert len(re.findall(r"@Override", rvc)) >= 64                          # RandomVariableCuda.java:785-1701 overrides 64 methods
     assert "serialVersionUID = 7620120320663270600L" in rvc and "transient long" in rvc
     assert rvc.count("{") == rvc.count("}") and src.count("{") == src.count("}")
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) on a tiny sample: one JSON line with the
+    contract's keys. Runs the oracle only — no GPU needed."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--ref-paths-per-thread", "64",
+                        "--steps", "1", "--warmup", "0", "--no-calibration"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "lmm_atm_path_steps_per_s" and line["unit"] == "path-steps/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
