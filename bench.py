@@ -408,6 +408,7 @@ def run_ours(args) -> None:
                    "payoff chain -> getAverage": (lambda: x.sub(0.5).floor(0.0).div(1.1).mult(0.9).getAverage(), 4)}
             extras["raw_ops_1e8"] = {k: raw(f, b) for k, (f, b) in ops.items()}
             del xs, x, y, z
+            fc.pool_trim(); capi.check(capi.load().fmc_sync())   # the 400 MB blocks go back to the driver outside the timings below
             # Brownian generation (MT19937 + inverse normal), 1 Mi paths x 80 steps
             td = fc.TimeDiscretization(0.0, N_PERIODS, DELTA)
             tsb = []
