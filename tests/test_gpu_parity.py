@@ -88,6 +88,25 @@ def test_unary_ops(fc, O, data, name, exact):
             assert ulp_diff(got, want) <= 1, (name, ulp_diff(got, want))
 
 
+@pytest.mark.parametrize("name", ["exp", "log"])
+def test_exp_log_bit_equal_to_the_oracle_on_a_dense_sample_of_all_floats(fc, O, name):
+    """exp / log are range reduction + a double-precision FMA polynomial written out in the interpreter, rounded once to float
+    (RVF:903-921: (float)Math.exp((double)x)). The same sequence agrees with glibc on ALL 2^32 inputs on the CPU
+    (benchmarks/micro/explog_exhaustive.c); here every 256th float bit pattern (plus the neighbourhood of the special values)
+    goes through the GPU and must be bit-equal to the oracle; benchmarks/explog_gpu_exhaustive.py runs all 2^32."""
+    bits = np.arange(0, 1 << 32, 256, dtype=np.uint64).astype(np.uint32)
+    special = np.array([0x00000000, 0x80000000, 0x00000001, 0x007fffff, 0x00800000, 0x3f800000, 0x3f7fffff, 0x3f800001, 0x7f7fffff, 0x7f800000,
+                        0xff800000, 0x7fc00000, 0x42b17218, 0x42b17217, 0x42b17219, 0xc2cff1b5, 0xc2cff1b4, 0xc2aeac50, 0xc2aeac4f], dtype=np.uint32)
+    bits = np.concatenate([bits, special, special + np.uint32(1), special - np.uint32(1)])
+    x = bits.view(np.float32)
+    X = fc.RandomVariableCuda(0.0, x)
+    got = getattr(X, name)().getRealizationsFloat()
+    want = O.op_v(O.EXP if name == "exp" else O.LOG, x)
+    same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+    bad = np.flatnonzero(~same)
+    assert bad.size == 0, (name, bad.size, [(hex(int(bits[i])), float(got[i]), float(want[i])) for i in bad[:5]])
+
+
 @pytest.mark.parametrize("e", [2.0, 0.5, 3.0, -1.5, 1.0 / 3.0, 0.0, 1.0])
 def test_pow(fc, O, data, e):
     x, _, _ = data
