@@ -403,7 +403,7 @@ int fmc_sync(void) {
 }
 static void set_option_locked(Runtime& rt, const char* key, double value) {
     // everything that steers the code generator invalidates the cached tapes
-    static const char* const keeps_cache[] = {"flush_threshold", "profile", "tape_upload_stream", "exchange", "exchange_timeout_s", "p2p_reduce", "zero_copy_reduce", "leaf_reduce_kernel", "batch_reduce"};
+    static const char* const keeps_cache[] = {"flush_threshold", "profile", "tape_upload_stream", "exchange", "exchange_timeout_s", "p2p_reduce", "zero_copy_reduce", "leaf_reduce_kernel", "batch_reduce", "regression_float_products"};
     bool keep = false;
     for (const char* k : keeps_cache) keep = keep || !std::strcmp(key, k);
     if (!keep) tape_cache_clear();
@@ -423,6 +423,7 @@ static void set_option_locked(Runtime& rt, const char* key, double value) {
     else if (!std::strcmp(key, "grid_limit")) rt.opt.grid_limit = std::max(0, (int)value);
     else if (!std::strcmp(key, "fuse_ops")) rt.opt.fuse_ops = value != 0.0;
     else if (!std::strcmp(key, "fuse_ops2")) rt.opt.fuse_ops2 = value != 0.0;
+    else if (!std::strcmp(key, "regression_float_products")) rt.opt.regression_float_products = value != 0.0;
     else if (!std::strcmp(key, "batch_reduce")) { rt.opt.batch_reduce = value != 0.0; rt.flush_batches.clear(); rt.prefetched.clear(); }
     else if (!std::strcmp(key, "tape_upload_stream")) rt.opt.tape_upload_stream = value != 0.0;
     else if (!std::strcmp(key, "p2p_reduce")) rt.opt.p2p_reduce = value != 0.0;
@@ -474,6 +475,7 @@ int fmc_get_option(const char* key, double* value) {
         else if (!std::strcmp(key, "grid_limit")) *value = rt.opt.grid_limit;
         else if (!std::strcmp(key, "fuse_ops")) *value = rt.opt.fuse_ops ? 1.0 : 0.0;
         else if (!std::strcmp(key, "fuse_ops2")) *value = rt.opt.fuse_ops2 ? 1.0 : 0.0;
+        else if (!std::strcmp(key, "regression_float_products")) *value = rt.opt.regression_float_products ? 1.0 : 0.0;
         else if (!std::strcmp(key, "batch_reduce")) *value = rt.opt.batch_reduce ? 1.0 : 0.0;
         else if (!std::strcmp(key, "p2p_reduce")) *value = rt.opt.p2p_reduce ? 1.0 : 0.0;
         else if (!std::strcmp(key, "p2p_ready")) *value = rt.p2p_ready ? 1.0 : 0.0;
@@ -567,6 +569,7 @@ int fmc_regression_normal_eq(const fmc_vec* basis, const double* scalars, int k,
             P.scalars[i] = bidx[i] >= 0 ? 0.f : (float)scalars[i];
         }
         P.partials = rt.d_partials; P.counter = rt.d_counter + 1; P.result = rt.d_result + 64;
+        P.float_products = rt.opt.regression_float_products ? 1 : 0;
         static int per_sm_k[REG_MAX_K + 1] = {0};
         if (!per_sm_k[k]) per_sm_k[k] = regression_max_blocks_per_sm(k);
         const int per_sm = per_sm_k[k];

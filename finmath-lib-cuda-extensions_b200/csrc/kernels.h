@@ -67,6 +67,7 @@ struct RegressionParams {
     double* partials;                // [gridDim.x][REG_MAX_K*(REG_MAX_K+1)/2 + REG_MAX_K]
     unsigned int* counter;
     double* result;                  // [k*(k+1)/2 + k] sums (not yet divided by n)
+    int float_products;              // != 0: sums of the float products fl32(a*b) (RandomVariableFromFloatArray); 0: of the exact products
 };
 cudaError_t launch_regression(const RegressionParams& P, int grid, cudaStream_t stream);
 int regression_max_blocks_per_sm(int k);

@@ -16,6 +16,8 @@
 // ~n * 2^-48 of the sum of magnitudes for the n terms of one thread. Merging is in double: warp shuffles, warps in order,
 // last block over the block partials in a fixed order (deterministic for a given grid).
 #include <cuda_runtime.h>
+#include <algorithm>
+#include <stdint.h>
 
 #include "kernels.h"
 
@@ -24,11 +26,44 @@ namespace fmc {
 namespace {
 
 constexpr int RTHREADS = 256;
-constexpr int RU_MAX = 2;                        // float4 loads per vector per thread and iteration (1 for k > 4: registers)
-constexpr int RTILE = RTHREADS * RU_MAX * 4;     // 2048 paths per block iteration
+constexpr int RTILE = RTHREADS * 4;              // 1024 paths per tile: one 128-bit group per thread and vector
+constexpr int RTILE_BYTES = RTILE * 4;           // 4 KB per vector and tile
+constexpr int RSTAGES_MAX = 6;
+constexpr int RSMEM_BUDGET = 200 * 1024;         // dynamic shared memory the ring may take (one CTA per SM)
 
-struct Sum {                                     // double sum of exact products + float sum of the float-rounding errors
+// Feeding. One thread cannot keep enough loads in flight from registers: 44 running sums (k = 8) leave room for one 128-bit
+// load per vector, 28-36 KB per SM in flight against the ~45 KB that HBM latency x bandwidth asks for — the register-fed
+// version of this kernel sat at 43-45 % of the roofline for k >= 6 with the SM idle two thirds of the time. Tiles now arrive
+// by TMA bulk copies (cp.async.bulk, one per vector and tile, issued by one thread) into a ring of up to 6 stages in shared
+// memory (k = 6: 4 stages x 28 KB), each guarded by an mbarrier; the threads read their 128-bit group of every vector from
+// the stage, fold it, and a block barrier hands the stage back for the tile RSTAGES ahead.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "RWAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra RDONE;\n"
+        "bra RWAIT;\n"
+        "RDONE:\n"
+        "}\n" :: "r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+// FLOATP = true: the sum of the FLOAT products fl32(a*b), what RandomVariableFromFloatArray's mult + getAverage give: double sum
+// of exact products + float sum of the float-rounding errors (header). FLOATP = false: the sum of the EXACT products — what
+// RandomVariableFromDoubleArray (finmath-lib's default CPU type) computes from the same float-valued inputs: one DFMA per
+// product and nothing else. The two differ by sum(r), ~2^-24 / sqrt(n) of the sum; the three float operations per product
+// that reproduce it make the kernel compute-bound (k = 6: 49 % of the roofline; without them: HBM-bound).
+template <bool FLOATP> struct Sum;
+template <> struct Sum<true> {
     double d; float r;
+    __device__ __forceinline__ void zero() { d = 0.0; r = 0.0f; }
     __device__ __forceinline__ void add(float a, float b, double A, double B) {
         const float p = __fmul_rn(a, b);
         r = __fadd_rn(r, __fmaf_rn(a, b, -p));
@@ -36,21 +71,32 @@ struct Sum {                                     // double sum of exact products
     }
     __device__ __forceinline__ double value() const { return d - (double)r; }
 };
+template <> struct Sum<false> {
+    double d;
+    __device__ __forceinline__ void zero() { d = 0.0; }
+    __device__ __forceinline__ void add(float, float, double A, double B) { d = __fma_rn(A, B, d); }
+    __device__ __forceinline__ double value() const { return d; }
+};
 
-template <int K>
-__global__ void __launch_bounds__(RTHREADS)
-regression_kernel(const __grid_constant__ RegressionParams P)
+template <int K, bool FLOATP>
+__global__ void __launch_bounds__(RTHREADS, 1)
+regression_kernel(const __grid_constant__ RegressionParams P, const int n_stages)
 {
     constexpr int M = K * (K + 1) / 2 + K;
-    constexpr int RU = K <= 4 ? RU_MAX : 1;
-    constexpr int SUB = RU_MAX / RU;                 // sub-tiles of RTHREADS * RU * 4 paths per tile
-    Sum acc[M];
+    extern __shared__ __align__(128) unsigned char ring[];          // [n_stages][K + 1][RTILE_BYTES], then the mbarriers
+    Sum<FLOATP> acc[M];
 #pragma unroll
-    for (int t = 0; t < M; t++) { acc[t].d = 0.0; acc[t].r = 0.0f; }
+    for (int t = 0; t < M; t++) acc[t].zero();
 
     const int tid = threadIdx.x;
     const long long n = P.n;
-    const long long n_tiles = (n + RTILE - 1) / RTILE;
+    const long long n_full = n / RTILE;                              // full tiles go through the ring
+    const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(ring);
+    const uint32_t stage_bytes = (uint32_t)(K + 1) * RTILE_BYTES;
+    const uint32_t mbar0 = ring0 + (uint32_t)n_stages * stage_bytes;
+    int n_vec = 1;                                                   // vectors that are really loaded (scalars are not)
+#pragma unroll
+    for (int i = 0; i < K; i++) n_vec += P.basis[i] ? 1 : 0;
 
     auto fold = [&](const float (&b)[K], const float y) {
         double B[K];
@@ -65,51 +111,65 @@ regression_kernel(const __grid_constant__ RegressionParams P)
 #pragma unroll
         for (int i = 0; i < K; i++, t++) acc[t].add(y, b[i], Y, B[i]);
     };
+    auto issue = [&](long long tile, int stage) {                    // thread 0: arm the stage's barrier, one bulk copy per vector
+        const uint32_t mbar = mbar0 + 8u * (uint32_t)stage;
+        const uint32_t dst = ring0 + (uint32_t)stage * stage_bytes;
+        mbar_expect_tx(mbar, (uint32_t)n_vec * RTILE_BYTES);
+#pragma unroll
+        for (int i = 0; i < K; i++)
+            if (P.basis[i]) bulk_load(dst + (uint32_t)i * RTILE_BYTES, P.basis[i] + tile * RTILE, RTILE_BYTES, mbar);
+        bulk_load(dst + (uint32_t)K * RTILE_BYTES, P.y + tile * RTILE, RTILE_BYTES, mbar);
+    };
 
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if ((tile + 1) * RTILE <= n) {
-#pragma unroll
-            for (int sub = 0; sub < SUB; sub++) {
-                const long long base0 = tile * RTILE + (long long)sub * (RTHREADS * RU * 4) + (long long)tid * 4;
-                // full tile: all (K + 1) * RU 128-bit loads of the thread are issued before the first use
-                float4 vb[K][RU], vy[RU];
-#pragma unroll
-                for (int u = 0; u < RU; u++) {
-                    const long long base = base0 + (long long)u * RTHREADS * 4;
-#pragma unroll
-                    for (int i = 0; i < K; i++) {
-                        const float* p = P.basis[i];
-                        vb[i][u] = p ? __ldg(reinterpret_cast<const float4*>(p + base)) : make_float4(P.scalars[i], P.scalars[i], P.scalars[i], P.scalars[i]);
-                    }
-                    vy[u] = __ldg(reinterpret_cast<const float4*>(P.y + base));
-                }
-#pragma unroll
-                for (int u = 0; u < RU; u++) {
-                    float b[K];
-#pragma unroll
-                    for (int i = 0; i < K; i++) b[i] = vb[i][u].x;
-                    fold(b, vy[u].x);
-#pragma unroll
-                    for (int i = 0; i < K; i++) b[i] = vb[i][u].y;
-                    fold(b, vy[u].y);
-#pragma unroll
-                    for (int i = 0; i < K; i++) b[i] = vb[i][u].z;
-                    fold(b, vy[u].z);
-#pragma unroll
-                    for (int i = 0; i < K; i++) b[i] = vb[i][u].w;
-                    fold(b, vy[u].w);
-                }
-            }
-        } else {
-            // ragged last tile: element by element
-            for (long long idx = tile * RTILE + tid; idx < n; idx += RTHREADS) {
-                float b[K];
-#pragma unroll
-                for (int i = 0; i < K; i++) b[i] = P.basis[i] ? P.basis[i][idx] : P.scalars[i];
-                fold(b, P.y[idx]);
-            }
+    if (tid == 0) {
+        for (int s = 0; s < n_stages; s++) mbar_init(mbar0 + 8u * (uint32_t)s, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int s = 0; s < n_stages; s++) {
+            const long long tile = blockIdx.x + (long long)s * gridDim.x;
+            if (tile < n_full) issue(tile, s);
         }
     }
+    __syncthreads();
+
+    int stage = 0;
+    uint32_t parity = 0u;
+    for (long long tile = blockIdx.x; tile < n_full; tile += gridDim.x) {
+        mbar_wait(mbar0 + 8u * (uint32_t)stage, parity);
+        const unsigned char* st = ring + (size_t)stage * stage_bytes + (size_t)tid * 16;
+        float4 vb[K];
+#pragma unroll
+        for (int i = 0; i < K; i++)
+            vb[i] = P.basis[i] ? *reinterpret_cast<const float4*>(st + (size_t)i * RTILE_BYTES) : make_float4(P.scalars[i], P.scalars[i], P.scalars[i], P.scalars[i]);
+        const float4 vy = *reinterpret_cast<const float4*>(st + (size_t)K * RTILE_BYTES);
+        __syncthreads();                                             // everybody has read the stage: it may be refilled
+        if (tid == 0) {
+            const long long next = tile + (long long)n_stages * gridDim.x;
+            if (next < n_full) issue(next, stage);
+        }
+        float b[K];
+#pragma unroll
+        for (int i = 0; i < K; i++) b[i] = vb[i].x;
+        fold(b, vy.x);
+#pragma unroll
+        for (int i = 0; i < K; i++) b[i] = vb[i].y;
+        fold(b, vy.y);
+#pragma unroll
+        for (int i = 0; i < K; i++) b[i] = vb[i].z;
+        fold(b, vy.z);
+#pragma unroll
+        for (int i = 0; i < K; i++) b[i] = vb[i].w;
+        fold(b, vy.w);
+        if (++stage == n_stages) { stage = 0; parity ^= 1u; }
+    }
+    // ragged tail (less than one tile): block 0, element by element
+    if (blockIdx.x == 0)
+        for (long long idx = n_full * RTILE + tid; idx < n; idx += RTHREADS) {
+            float b[K];
+#pragma unroll
+            for (int i = 0; i < K; i++) b[i] = P.basis[i] ? P.basis[i][idx] : P.scalars[i];
+            fold(b, P.y[idx]);
+        }
 
     // block reduction in double: warp shuffle tree, then warps in order (deterministic)
     __shared__ double smem[RTHREADS / 32][M];
@@ -149,10 +209,24 @@ regression_kernel(const __grid_constant__ RegressionParams P)
     if (tid == 0) *P.counter = 0u;
 }
 
+inline int stages_for(int k) { return std::max(2, std::min(RSTAGES_MAX, RSMEM_BUDGET / ((k + 1) * RTILE_BYTES))); }
+
+template <int K, bool FLOATP>
+cudaError_t launch_kf(const RegressionParams& P, int grid, cudaStream_t s) {
+    const int n_stages = stages_for(K);
+    const size_t smem = (size_t)n_stages * (K + 1) * RTILE_BYTES + 8 * RSTAGES_MAX;
+    static bool opted = false;                                       // per instantiation
+    if (!opted) {
+        cudaError_t e = cudaFuncSetAttribute(regression_kernel<K, FLOATP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        opted = true;
+    }
+    regression_kernel<K, FLOATP><<<grid, RTHREADS, smem, s>>>(P, n_stages);
+    return cudaGetLastError();
+}
 template <int K>
 cudaError_t launch_k(const RegressionParams& P, int grid, cudaStream_t s) {
-    regression_kernel<K><<<grid, RTHREADS, 0, s>>>(P);
-    return cudaGetLastError();
+    return P.float_products ? launch_kf<K, true>(P, grid, s) : launch_kf<K, false>(P, grid, s);
 }
 
 }  // namespace
@@ -175,17 +249,7 @@ cudaError_t launch_regression(const RegressionParams& P, int grid, cudaStream_t 
     }
 }
 
-int regression_max_blocks_per_sm(int k) {
-    int nb = 0;
-    cudaError_t e;
-    switch (k) {
-    case 1: case 2: case 3: case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, regression_kernel<4>, RTHREADS, 0); break;
-    case 5: case 6: case 7: case 8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, regression_kernel<8>, RTHREADS, 0); break;
-    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, regression_kernel<12>, RTHREADS, 0); break;
-    }
-    if (e != cudaSuccess) nb = 1;
-    return nb > 0 ? nb : 1;
-}
+int regression_max_blocks_per_sm(int) { return 1; }                  // the ring takes most of the SM's shared memory
 int regression_tile_elems() { return RTILE; }
 
 }  // namespace fmc

@@ -134,6 +134,10 @@ struct Options {
                                     // let a few kernels drop to one CTA per SM (8.36 ms simulation); 8: 8.14 ms, 4: 8.00 ms but more spills
     bool tape_upload_stream = true; // long tapes reach the device through the copy stream, ahead of the kernels queued on the compute stream
     bool tape_cache = true;         // replay the launches of a cone whose structure was lowered before (codegen.cpp)
+    bool regression_float_products = true;    // normal equations from the float products fl32(a*b) like RandomVariableFromFloatArray (the reference's
+                                    // float class: coefficients within 1e-5 of it even for ill-conditioned bases; compute-bound, 45-49 % of the
+                                    // roofline at k = 6..8). false: from the exact products (RandomVariableFromDoubleArray's value for the same
+                                    // inputs; sums differ by ~2^-24 / sqrt(n) relative; HBM-bound, 80 % of the roofline)
     bool batch_reduce = true;       // getAverage() of a vector that one flush materialised together with others: the sums of all of them in one
                                     // launch, the others' results kept for the calls that follow (Runtime::reduce_batch)
 };

@@ -1,0 +1,5 @@
+for o in "regression_float_products=0" "regression_float_products=1"; do
+echo "== $o"
+FMC_OPTIONS=$o timeout -s KILL 600 python benchmarks/raw_ops.py 2>&1 | grep -i -E "regress" | tail -6
+done
+FMC_OPTIONS=regression_float_products=1 timeout -s KILL 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_workloads.py -m gpu -x -q -k "regression or fuzzed_statistics or bermudan" 2>&1 | tail -3

@@ -454,8 +454,8 @@ cudaError_t launch_regression(const RegressionParams& P, int, cudaStream_t) {
         float b[REG_MAX_K];
         for (int i = 0; i < k; i++) b[i] = P.basis[i] ? P.basis[i][p] : P.scalars[i];
         int t = 0;
-        for (int i = 0; i < k; i++) for (int j = i; j < k; j++, t++) { const float x = b[i] * b[j]; acc[t] += (double)x; }
-        for (int i = 0; i < k; i++, t++) { const float x = P.y[p] * b[i]; acc[t] += (double)x; }
+        for (int i = 0; i < k; i++) for (int j = i; j < k; j++, t++) { const float x = b[i] * b[j]; acc[t] += P.float_products ? (double)x : (double)b[i] * (double)b[j]; }
+        for (int i = 0; i < k; i++, t++) { const float x = P.y[p] * b[i]; acc[t] += P.float_products ? (double)x : (double)P.y[p] * (double)b[i]; }
     }
     for (size_t t = 0; t < acc.size(); t++) P.result[t] = acc[t];
     return cudaSuccess;

@@ -402,8 +402,43 @@ def test_brownian_moments(fc):
     assert abs(inc.getVariance() - dt) < 3.0 * dt / math.sqrt(n)
 
 
+def _exact_normal_equations(basis_o, y):
+    """The normal equations from EXACT products of the float-valued columns: what RandomVariableFromDoubleArray (finmath-lib's
+    default CPU type) computes for the same inputs; deterministic x deterministic entries are the plain double product."""
+    k, n = len(basis_o), len(y)
+    cols = [np.full(n, float(np.float32(b)), dtype=np.float64) if np.isscalar(b) else np.asarray(b, dtype=np.float64) for b in basis_o]
+    yd = np.asarray(y, dtype=np.float64)
+    XtX = np.empty((k, k)); XtY = np.empty(k)
+    for i in range(k):
+        for j in range(k):
+            XtX[i, j] = float(basis_o[i]) * float(basis_o[j]) if (np.isscalar(basis_o[i]) and np.isscalar(basis_o[j])) else math.fsum(cols[i] * cols[j]) / n
+        XtY[i] = math.fsum(cols[i] * yd) / n
+    return XtX, XtY
+
+
+@pytest.fixture(params=[1, 0], ids=["float_products", "exact_products"])
+def regression_mode(fc, request):
+    """Option regression_float_products: 1 (default) sums the float products like RandomVariableFromFloatArray (the oracle);
+    0 sums the exact products — RandomVariableFromDoubleArray's value for the same inputs: HBM-bound instead of compute-bound,
+    but an ill-conditioned basis (k = 8 below) turns the ~1e-8 difference of the sums into > 1e-5 in the coefficients, outside
+    the tolerance towards the float class. Opt-in."""
+    fc.set_option("regression_float_products", request.param)
+    yield request.param
+    fc.set_option("regression_float_products", 1)
+
+
+def _check_normal_equations(mode, XtX, XtY, basis_o, y, XtX_o, XtY_o, atol):
+    if mode == 1:      # the float class's sums: as tight as the summation order allows
+        assert np.allclose(XtX, XtX_o, rtol=1e-9, atol=atol) and np.allclose(XtY, XtY_o, rtol=1e-9, atol=atol)
+    else:              # exact products: tight against their own definition, inside the north-star tolerance against the float class
+        XtX_e, XtY_e = _exact_normal_equations(basis_o, y)
+        assert np.allclose(XtX, XtX_e, rtol=1e-12, atol=1e-15) and np.allclose(XtY, XtY_e, rtol=1e-12, atol=1e-15)
+        scale = max(1.0, float(np.max(np.abs(XtX_o))))
+        assert np.allclose(XtX, XtX_o, rtol=1e-6, atol=1e-7 * scale) and np.allclose(XtY, XtY_o, rtol=1e-6, atol=1e-7 * scale)
+
+
 @pytest.mark.parametrize("k", [3, 6, 8])
-def test_regression_normal_equations(fc, O, data, k):
+def test_regression_normal_equations(fc, O, data, k, regression_mode):
     x, y, z = data
     xf, yf, zf = O.from_f64(x), O.from_f64(y), O.from_f64(z)
     X, Y, Z = (fc.RandomVariableCuda(0.0, v) for v in (x, y, z))
@@ -413,12 +448,16 @@ def test_regression_normal_equations(fc, O, data, k):
     from finmath_cuda.conditional_expectation import normal_equations
     XtX, XtY = normal_equations(basis, Z)
     XtX_o, XtY_o = O.regression_normal_eq(basis_o, zf)
-    assert np.allclose(XtX, XtX_o, rtol=1e-9, atol=1e-14)
-    assert np.allclose(XtY, XtY_o, rtol=1e-9, atol=1e-14)
+    _check_normal_equations(regression_mode, XtX, XtY, basis_o, zf, XtX_o, XtY_o, 1e-14)
     est = fc.MonteCarloConditionalExpectationRegression(basis)
     c = est.getLinearRegressionParameters(Z)
     c_o = np.linalg.lstsq(XtX_o, XtY_o, rcond=None)[0]
-    assert np.allclose(c, c_o, rtol=1e-5, atol=1e-8)
+    if regression_mode == 1:
+        assert np.allclose(c, c_o, rtol=1e-5, atol=1e-8)
+    else:
+        c_e = np.linalg.lstsq(*_exact_normal_equations(basis_o, zf), rcond=None)[0]
+        assert np.allclose(c, c_e, rtol=1e-5, atol=1e-8)
+        assert np.allclose(c, c_o, rtol=1e-3, atol=1e-6)
     ce = Z.getConditionalExpectation(est)
     want = O.op_vs(O.MULT, np.full(N, 1.0, dtype=np.float32), c_o[0]) if False else None
     # estimate = basis[0]*c0 + sum c_i*basis[i] (float arithmetic); compare against the oracle evaluation of the same chain
@@ -775,10 +814,14 @@ def test_fuzzed_statistics_regression_and_brownian(fc, O):
         y = rng.uniform(-1.0, 1.0, n).astype(np.float32)
         basis = [fc.RandomVariableCuda(0.0, float(c[0])) if d else fc.RandomVariableCuda(0.0, c.astype(np.float64)) for c, d in zip(cols, det)]
         basis_o = [float(np.float64(c[0])) if d else c for c, d in zip(cols, det)]
-        XtX, XtY = normal_equations(basis, fc.RandomVariableCuda(0.0, y.astype(np.float64)))
         XtX_o, XtY_o = O.regression_normal_eq(basis_o, y)
-        assert np.allclose(XtX, XtX_o, rtol=1e-9, atol=1e-13), (case, n, k, det)
-        assert np.allclose(XtY, XtY_o, rtol=1e-9, atol=1e-13), (case, n, k, det)
+        for mode in (0, 1):
+            fc.set_option("regression_float_products", mode)
+            try:
+                XtX, XtY = normal_equations(basis, fc.RandomVariableCuda(0.0, y.astype(np.float64)))
+            finally:
+                fc.set_option("regression_float_products", 1)
+            _check_normal_equations(mode, XtX, XtY, basis_o, y, XtX_o, XtY_o, 1e-13)
     for case in range(10):
         T, F = int(rng.integers(1, 30)), int(rng.integers(1, 5))
         n = int(rng.choice([1, 33, 1000, 20_011]))
