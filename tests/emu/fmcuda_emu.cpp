@@ -168,7 +168,9 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
         const long long base = chunk * C;
         const long long next = chunk + stride * P.n_sets;
         float acc[CMAX]; bool pred[CMAX];
-        for (int e = 0; e < C; e++) { acc[e] = 0.f; pred[e] = false; }
+        // the kernel does not clear acc between chunks: a tape that read it before defining it would see the previous chunk's
+        // values. Poisoned here so that such a tape fails the value comparison.
+        for (int e = 0; e < C; e++) { acc[e] = std::nanf(""); pred[e] = false; }
         std::fill(w.reg_written.begin(), w.reg_written.end(), 0);
         const float* endb = nullptr;
         for (int pc = P.n_prologue + 1;; pc++) {
