@@ -17,7 +17,7 @@ from finmath_cuda import _capi as capi  # noqa: E402
 fc.ensure_init()
 L = capi.load()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
-m = 20
+m = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 rng = np.random.default_rng(3)
 base = (0.02 + 0.01 * rng.random(n)).astype(np.float32)
 libor = [fc.RandomVariableCuda(0.0, base).add(0.0001 * i).add(0.0) for i in range(m)]
@@ -35,10 +35,11 @@ def chain(kind):
         elif kind == "payoff only":   v = v.add(li.sub(0.02).mult(0.5))
         elif kind == "sum of leaves": v = v.add(li)
     if kind == "empty": v = libor[0].add(1.0)
+    if kind == "leaf (streaming reduce kernel)": return libor[0].getAverage()
     return v.floor(0.0).div(numeraire).mult(1.0 / n).getAverage()
 
 
-for kind in ("full", "no discount", "accrue instead", "payoff only", "sum of leaves", "empty"):
+for kind in ("full", "no discount", "accrue instead", "payoff only", "sum of leaves", "empty", "leaf (streaming reduce kernel)"):
     for _ in range(3):
         chain(kind)
     capi.set_option("profile", 1); capi.profile_read()
@@ -46,4 +47,4 @@ for kind in ("full", "no discount", "accrue instead", "payoff only", "sum of lea
     for _ in range(reps):
         chain(kind)
     pr = capi.profile_read(); capi.set_option("profile", 0)
-    print(f"n={n} {kind:16s} kernel {pr['tape_ms'] / reps * 1e3:7.1f} us per valuation ({pr['tape_launches'] // reps} launch)")
+    print(f"n={n} {kind:32s} kernel {pr['tape_ms'] / reps * 1e3:7.1f} us per valuation ({pr['tape_launches'] // reps} launch)")

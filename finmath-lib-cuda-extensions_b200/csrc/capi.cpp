@@ -412,6 +412,10 @@ static void set_option_locked(Runtime& rt, const char* key, double value) {
     else if (!std::strcmp(key, "max_regs")) rt.opt.max_regs = std::max(4, std::min((int)value, (int)TAPE_REGS));
     else if (!std::strcmp(key, "fuse")) { rt.opt.fuse = value != 0.0; if (rt.initialized) rt.flush_all(); }
     else if (!std::strcmp(key, "profile")) rt.opt.profile = value != 0.0;
+    else if (!std::strcmp(key, "window_levels")) rt.opt.window_levels = (int)value;
+    else if (!std::strcmp(key, "window_elems")) rt.opt.window_elems = (int)value;
+    else if (!std::strcmp(key, "window_cta_warps")) rt.opt.window_cta_warps = std::max(0, std::min((int)value, (int)TAPE_MAX_WARPS));
+    else if (!std::strcmp(key, "window_ring_extra")) rt.opt.window_ring_extra = std::max(1, (int)value);
     else if (!std::strcmp(key, "ring_max")) rt.opt.ring_max = std::max(1, std::min((int)value, (int)TAPE_MAX_RING));
     else if (!std::strcmp(key, "ring_min")) rt.opt.ring_min = std::max(1, std::min((int)value, (int)TAPE_MAX_RING));
     else if (!std::strcmp(key, "target_ctas")) rt.opt.target_ctas = std::max(0, (int)value);
@@ -464,6 +468,7 @@ int fmc_get_option(const char* key, double* value) {
         else if (!std::strcmp(key, "tape_cache_entries")) *value = (double)c_entries;
         else if (!std::strcmp(key, "fuse")) *value = rt.opt.fuse ? 1.0 : 0.0;
         else if (!std::strcmp(key, "profile")) *value = rt.opt.profile ? 1.0 : 0.0;
+        else if (!std::strcmp(key, "window_levels")) *value = (double)rt.opt.window_levels;
         else if (!std::strcmp(key, "ring_max")) *value = rt.opt.ring_max;
         else if (!std::strcmp(key, "ring_min")) *value = rt.opt.ring_min;
         else if (!std::strcmp(key, "target_ctas")) *value = rt.opt.target_ctas;

@@ -17,7 +17,9 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <string>
 #include <unordered_map>
+#include <unordered_set>
 
 #include "runtime.h"
 
@@ -161,7 +163,8 @@ struct Gen {
             f.slot = (int16_t)ptrs.size();
             ptrs.push_back(f.buf);
             slotted.push_back(L);
-            if (!f.lazy) n_leaf_slots++;
+            // (algorithmic traffic: a value an earlier window of the same flush stored is a re-read, not an input)
+            if (!f.lazy && !(rt.windowing && rt.window_stored.count(f.buf))) n_leaf_slots++;
         }
         return f.slot;
     }
@@ -453,7 +456,12 @@ struct Gen {
                 i += 1;
                 continue;
             }
-            if (i + 1 < A.size() && a.op == (A_BIN | B_ADD) && a.kind == K_REG && A[i + 1].op == T_STR && A[i + 1].kind == K_REG && A[i + 1].arg == a.arg) {
+            // (not when the STR opens an ADDPROD: "ADD_S r ; STR r ; MOV x ; MUL_I a ; ADD_S r" is ADD_S r ; ADDPROD x, a)
+            if (i + 1 < A.size() && a.op == (A_BIN | B_ADD) && a.kind == K_REG && A[i + 1].op == T_STR && A[i + 1].kind == K_REG && A[i + 1].arg == a.arg
+                && !(i + 4 < A.size() && A[i + 2].op == (A_BIN | B_MOV) && (A[i + 2].kind == K_REG || A[i + 2].kind == K_LEAF)
+                     && !(A[i + 2].kind == K_REG && A[i + 2].arg == a.arg)
+                     && A[i + 3].op == (A_BIN | B_MUL) && A[i + 3].kind == K_IMM
+                     && A[i + 4].op == (A_BIN | B_ADD) && A[i + 4].kind == K_REG && A[i + 4].arg == a.arg && reg_dead_after(i + 5, a.arg))) {
                 out.push_back(mk((uint16_t)T_ACCUM_S, K_REG, a.arg, 0u));
                 i += 1;
                 continue;
@@ -507,6 +515,17 @@ struct Gen {
                     && out[i + 4].op == T_ACCUM_S && out[i + 4].kind == K_REG && !(a.kind == K_REG && a.arg == out[i + 4].arg)) {
                     const AIns& r = out[i + 1];
                     A.push_back(mk((uint16_t)T_RATIOACC_S, a.kind, a.arg, r.y, r.src, 0));
+                    A.push_back(mk(A_EXT, K_NONE, 0, (uint32_t)r.arg, r.src2));
+                    A.push_back(out[i + 2]);
+                    A.push_back(mk(A_EXT, K_REG, out[i + 4].arg, out[i + 3].y, out[i + 3].src));
+                    i += 4;
+                    continue;
+                }
+                //   STR t ; RATIO a, b, c, d ; ACCUM_S r                        -> RATIOACC_A t, a, b, c, d | r   (the state is in acc)
+                if (a.op == T_STR && a.kind == K_REG && i + 4 < out.size() && out[i + 1].op == T_RATIO && out[i + 2].op == A_EXT && out[i + 3].op == A_EXT
+                    && out[i + 4].op == T_ACCUM_S && out[i + 4].kind == K_REG && a.arg != out[i + 4].arg) {
+                    const AIns& r = out[i + 1];
+                    A.push_back(mk((uint16_t)T_RATIOACC_A, K_REG, a.arg, r.y, r.src, 0));
                     A.push_back(mk(A_EXT, K_NONE, 0, (uint32_t)r.arg, r.src2));
                     A.push_back(out[i + 2]);
                     A.push_back(mk(A_EXT, K_REG, out[i + 4].arg, out[i + 3].y, out[i + 3].src));
@@ -728,6 +747,31 @@ struct Gen {
             if (pro_leaf[s] >= 0 && !loadn_done[s]) fail(FMC_ERR_UNSUPPORTED, "internal: ring slot %u not re-armed", s);
     }
 
+    // FMC_DUMP_TAPES=1: the abstract code of every kernel after fusion, one instruction per line (development aid)
+    void dump_abstract() const {
+        static const char* const bin[] = {"MOV", "ADD", "SUB", "BUS", "MUL", "DIV", "VID", "MIN", "MAX", "SEL", "ADDPROD", "ACCRUE", "DISCOUNT"};
+        auto name = [&](uint16_t op) -> std::string {
+            if (op == A_EXT) return "  ext";
+            if (op & A_BIN) return bin[op & 0xff];
+            switch (op) {
+            case T_END: return "END"; case T_STG: return "STG"; case T_STGS: return "STGS"; case T_STR: return "STR"; case T_SETP: return "SETP";
+            case T_SQR: return "SQR"; case T_MULADD_II: return "MULADD_II"; case T_ACCUM_S: return "ACCUM_S"; case T_ADDMUL_II: return "ADDMUL_II";
+            case T_ADDAFF_S: return "ADDAFF"; case T_MULADDMUL: return "MULADDMUL"; case T_RATIO: return "RATIO"; case T_ADDAFFDISC_S: return "ADDAFFDISC";
+            case T_RATIOACC_S: return "RATIOACC"; case T_AXPYST_S: return "AXPYST"; case T_RATIOACC_A: return "RATIOACC_A";
+            default: return "op" + std::to_string(op);
+            }
+        };
+        std::fprintf(stderr, "[fmc dump] kernel: %zu abstract instructions\n", A.size());
+        for (const AIns& a : A) {
+            std::string arg;
+            if (a.kind == K_REG) arg = "r" + std::to_string(a.arg);
+            else if (a.kind == K_LEAF) arg = "leaf" + std::to_string(a.arg) + (info[a.arg].lazy ? "*" : "");
+            else if (a.kind == K_IMM) arg = "imm";
+            else if (a.kind == K_RELOAD) arg = "reload";
+            std::fprintf(stderr, "[fmc dump]   %-12s %s%s\n", name(a.op).c_str(), arg.c_str(), (a.op == T_STG || a.op == T_STGS) ? (" -> p" + std::to_string(a.y)).c_str() : "");
+        }
+    }
+
     std::vector<KernelPlan> plans;      // the launches of this cone, in order (kept for the tape cache)
     bool keep_plans = false;
 
@@ -745,15 +789,20 @@ struct Gen {
         if (A.size() <= 1 && reduce_mode == RM_NONE) return;   // nothing to do
         { PhaseTimer pt(3); if (rt.opt.fuse_ops) peephole(); }
 
+        static const bool dump_tapes = std::getenv("FMC_DUMP_TAPES") != nullptr;
+        if (dump_tapes) dump_abstract();
         std::vector<TapeInstr> prologue, body;
         KernelPlan kp;
         int n_ring = 0;
-        const int n_warps = std::max(1, std::min(rt.opt.cta_warps, TAPE_MAX_WARPS));
+        const int n_warps = std::max(1, std::min(rt.windowing && rt.opt.window_cta_warps > 0 ? rt.opt.window_cta_warps : rt.opt.cta_warps, TAPE_MAX_WARPS));
         // Chunk geometry (elements per lane, tape_interp.cuh). A warp interprets one chunk of 32 E paths at a time, so a vector
         // of n paths is n / (32 E) warps' worth of work per pass: the largest E that still gives every SM `min_warps` warps
         // (16-element chunks amortise the dispatch best; below that the GPU's warp slots stay empty and the interpreter runs
         // at the latency of a lone warp, so more, shorter warps win).
         int elems = rt.opt.tape_elems;
+        // a window kernel carries a register-file slot per level and chain state: halving the slot size doubles the warps that fit
+        if (!tape_valid_elems(elems) && rt.windowing && tape_valid_elems(rt.opt.window_elems) && n >= (int64_t)rt.opt.min_warps * rt.sm_count * tape_chunk(rt.opt.window_elems))
+            elems = rt.opt.window_elems;
         if (!tape_valid_elems(elems)) {
             elems = 4;
             for (int e = TAPE_E_MAX; e > 4; e >>= 1)
@@ -777,11 +826,29 @@ struct Gen {
         const int64_t need = (chunks + (int64_t)n_warps * rt.sm_count - 1) / ((int64_t)n_warps * rt.sm_count);
         int target = (int)std::max<int64_t>(1, std::min<int64_t>(need, hw_max));
         if (rt.opt.target_ctas > 0) target = std::min(rt.opt.target_ctas, hw_max);          // tests / tuning: forced
-        const size_t cta_share = rt.smem_per_sm / (size_t)target;
-        const long budget_bytes = (long)std::min(cta_share, rt.smem_per_cta_max) - 1024 - (long)est_tables;
-        const int slot_budget = (int)std::max<long>(1, budget_bytes / (n_warps * slot_bytes));
+        int ring_want = TAPE_MAX_RING;
+        auto slots_for = [&](int ctas) {
+            const size_t cta_share = rt.smem_per_sm / (size_t)ctas;
+            const long budget_bytes = (long)std::min(cta_share, rt.smem_per_cta_max) - 1024 - (ctas > 1 ? 1024 : 0) - (long)est_tables;
+            return (int)std::max<long>(1, budget_bytes / (n_warps * slot_bytes));
+        };
+        if (rt.windowing && rt.opt.target_ctas <= 0) {
+            // a window keeps some leaves in the ring for the whole kernel (the Brownian increment of each of its time steps is read
+            // once per component): the ring needs a slot for each of them plus a few for the leaves that stream through, or every
+            // access becomes a fresh copy. Occupancy gives way until that fits.
+            static thread_local std::vector<int32_t> cnt_leaf;
+            cnt_leaf.clear();
+            int n_hot = 0;
+            for (const AIns& a : A) if (a.kind == K_LEAF) {
+                if ((size_t)a.arg >= cnt_leaf.size()) cnt_leaf.resize((size_t)a.arg + 1, 0);
+                if (++cnt_leaf[(size_t)a.arg] == 4) n_hot++;
+            }
+            ring_want = std::min(n_hot + rt.opt.window_ring_extra, TAPE_MAX_RING);
+            while (target > 1 && slots_for(target) - regs_used < ring_want) target--;
+        }
+        const int slot_budget = slots_for(target);
         int ring_max = std::max(1, std::min<int>(rt.opt.ring_max, TAPE_MAX_RING));
-        ring_max = std::min(ring_max, std::max(rt.opt.ring_min, slot_budget - regs_used));
+        ring_max = std::min(ring_max, std::max(rt.opt.ring_min, std::min(slot_budget - regs_used, ring_want)));
         { PhaseTimer pt(4); schedule(ring_max, rt.opt.pipeline, rt.opt.horizon, tape_slot_shift(elems), prologue, body, n_ring, kp.patches); }
         PhaseTimer pt_prep(5);
         const size_t total = prologue.size() + 1 + body.size();
@@ -878,6 +945,86 @@ struct Gen {
 
 void tape_cache_clear() { g_cache.clear(); }
 void tape_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* entries) { *hits = g_cache.hits; *misses = g_cache.misses; *entries = g_cache.entries; }
+
+// Windows (option window_levels). A flush that covers several dependency levels of still-referenced values — the time steps of a
+// simulation, each reading what the step before stored — is cut into windows of W levels, and inside a window the targets of the
+// LAST level are visited first. The post-order walk of run_cone then emits every chain (a model component) through all W levels
+// before it starts the next chain, so what a level hands to the next one stays in the accumulator / register file and only the
+// state shared between chains (running sums, one per level) waits in register-file slots: a value a step stores is not read back
+// from HBM by the next step of the same window. Level of a target = the longest chain of still-referenced pending values below it.
+// hold_last (automatic flushes): the flush threshold falls in the middle of a time step and of a window; what is incomplete stays
+// pending, so that windows begin and end on whole levels. Returns true when something was held back.
+bool Runtime::run_windows(const std::vector<int32_t>& targets, bool hold_last) {
+    const int W = std::max(1, opt.window_levels);
+    epoch++;
+    if (epoch == 0) { for (auto& nd : nodes) nd.epoch = 0; epoch = 1; }
+    static thread_local std::vector<std::pair<int32_t, int>> lstack;
+    int max_level = 0;
+    for (int32_t t : targets) {
+        if (nodes[t].state != NS_LAZY || nodes[t].epoch == epoch) continue;
+        nodes[t].epoch = epoch; nodes[t].local = 0;
+        lstack.clear();
+        lstack.emplace_back(t, 0);
+        while (!lstack.empty()) {
+            auto& top = lstack.back();
+            const int32_t v = top.first;
+            if (top.second < 3) {
+                const int32_t u = nodes[v].in[top.second++];
+                if (u >= 0 && nodes[u].state == NS_LAZY && nodes[u].epoch != epoch) { nodes[u].epoch = epoch; nodes[u].local = 0; lstack.emplace_back(u, 0); }
+            } else {
+                int32_t lev = 0;
+                for (int k = 0; k < 3; k++) {
+                    const int32_t u = nodes[v].in[k];
+                    if (u >= 0 && nodes[u].state == NS_LAZY) lev = std::max(lev, nodes[u].local + (nodes[u].ext_refs > 0 ? 1 : 0));
+                }
+                nodes[v].local = lev;
+                max_level = std::max(max_level, (int)lev);
+                lstack.pop_back();
+            }
+        }
+    }
+    const int n_win = max_level / W + 1;
+    // held back: the top three levels and with them the window they belong to. The handles a caller holds only for the duration of
+    // a step (its vector of drifts, the running state of the component being updated) are still-referenced values too: they make
+    // the step in progress look up to three levels deep, and flushing them would store and re-read values nobody asks for
+    const int n_run = hold_last ? std::max(0, (max_level - 2) / W) : n_win;
+    if (n_run == 0) return true;
+    if (n_win == 1) {
+        run_cone(targets, nullptr);
+        return false;
+    }
+    std::vector<std::vector<int32_t>> win((size_t)n_win);
+    // visiting order inside a window: first the ends of the chains — targets that no pending value reads (a component that leaves
+    // the simulation at a lower level) and the targets of the window's last level — then the rest, each in recording order
+    for (int pass = 0; pass < 2; pass++)
+        for (int32_t t : targets) {
+            if (nodes[t].state != NS_LAZY) continue;
+            const int lev = nodes[t].local, w = lev / W;
+            const bool end = lev == std::min(max_level, w * W + W - 1) || nodes[t].int_refs == 0;
+            if (end == (pass == 0)) win[(size_t)w].push_back(t);
+        }
+    static const bool log_windows = std::getenv("FMC_LOG_TAPES") != nullptr;
+    if (log_windows) {
+        std::fprintf(stderr, "[fmc windows] %zu targets, %lld pending, levels 0..%d, W=%d, runs %d of:", targets.size(), (long long)n_lazy, max_level, W, n_run);
+        for (auto& wt : win) std::fprintf(stderr, " %zu", wt.size());
+        std::vector<int> per_level((size_t)max_level + 1, 0);
+        for (int32_t t : targets) if (nodes[t].state == NS_LAZY) per_level[(size_t)nodes[t].local]++;
+        if (std::getenv("FMC_LOG_LEVEL0")) for (int32_t t : targets) if (nodes[t].state == NS_LAZY && nodes[t].local == 0)
+            std::fprintf(stderr, "\n   L0 target node %d op %d ext %u int %u in %d/%d/%d states %d/%d", t, (int)nodes[t].op, nodes[t].ext_refs, nodes[t].int_refs, nodes[t].in[0], nodes[t].in[1], nodes[t].in[2],
+                         nodes[t].in[0] >= 0 ? (int)nodes[nodes[t].in[0]].state : -1, nodes[t].in[1] >= 0 ? (int)nodes[nodes[t].in[1]].state : -1);
+        std::fprintf(stderr, "   per level:");
+        for (int c : per_level) std::fprintf(stderr, " %d", c);
+        std::fprintf(stderr, "\n");
+    }
+    struct Guard { bool& f; explicit Guard(bool& f_) : f(f_) { f = true; } ~Guard() { f = false; } } guard(windowing);
+    struct Clear { std::unordered_set<const float*>& s; ~Clear() { s.clear(); } } clear_stored{window_stored};
+    for (int w = 0; w < n_run; w++) {
+        if (win[(size_t)w].empty()) continue;
+        run_cone(win[(size_t)w], nullptr);
+        if (w + 1 < n_run) for (int32_t t : win[(size_t)w]) if (nodes[t].state == NS_MAT) window_stored.insert(nodes[t].buf);
+    }
+    return n_run < n_win;
+}
 
 void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* red) {
     require_init();
@@ -1083,7 +1230,9 @@ void Runtime::run_cone(const std::vector<int32_t>& targets, const ReduceSpec* re
     for (int32_t L = 0; L < n_cone; L++) {
         // margins: one node emits < 16 instructions / < 8 new pointers; a cut stores at most TAPE_REGS + 1 live values;
         // ring scheduling adds at most two instructions per leaf reference plus two per ring slot
-        if ((int)g.A.size() + 2 * g.n_leaf_refs + 2 * TAPE_MAX_RING + 64 > TAPE_MAX_INSTR || (int)g.ptrs.size() + 28 > TAPE_MAX_PTRS) g.cut();
+        // (outside a window the kernels stay at the size the default path was tuned for)
+        const int instr_limit = windowing ? TAPE_MAX_INSTR : std::min(TAPE_MAX_INSTR, 2046), ptr_limit = windowing ? TAPE_MAX_PTRS : std::min(TAPE_MAX_PTRS, 384);
+        if ((int)g.A.size() + 2 * g.n_leaf_refs + 2 * TAPE_MAX_RING + 64 > instr_limit || (int)g.ptrs.size() + 28 > ptr_limit) g.cut();
         else if (!g.operands_available(L)) g.cut();
         g.emit_node(L);
     }
@@ -1255,7 +1404,10 @@ bool Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
                 if (q != cudaErrorNotReady) { cuda_err = q; break; }
             }
         }
-        const double r0 = h[0], r1 = h[1], r2 = h[2];
+        // sums of an unsharded vector come as {h[2] = value, h[3] = ticket} in one store (reduce_common.cuh: finish_reduction)
+        const bool sum_pair = comm_size == 1 && (spec.mode == RM_SUM || spec.mode == RM_DOT || spec.mode == RM_WSQ);
+        std::atomic_thread_fence(std::memory_order_acquire);
+        const double r0 = sum_pair ? (double)nodes[idx].n : h[0], r1 = sum_pair ? h[2] : h[1], r2 = sum_pair ? 0.0 : h[2];
         if (mine) { mine->lock(); held = mine; }
         if (err) fail(err_code, "%s", err);
         FMC_CUDA(cuda_err);

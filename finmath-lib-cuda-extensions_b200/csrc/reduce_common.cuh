@@ -103,6 +103,12 @@ static __device__ __noinline__ void finish_reduction(int mode, Part q, const Exc
         q = g;
     }
     result[0] = q.c; result[1] = q.v; result[2] = q.m;
+    if (host && X.nranks <= 1 && mode == RM_SUM) {
+        // sums of an unsharded vector (every getAverage of a valuation): the host knows the count; value and ticket travel in ONE
+        // 16-byte store to {host[2], host[3]} — they become visible together, no system-wide fence between them (2.4 us per reduction)
+        asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" :: "l"(host + 2), "d"(q.v), "d"(ticket) : "memory");
+        return;
+    }
     if (host) {
         volatile double* h = host;
         h[0] = q.c; h[1] = q.v; h[2] = q.m;

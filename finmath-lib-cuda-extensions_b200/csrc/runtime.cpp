@@ -201,20 +201,33 @@ void Runtime::release_int(int32_t idx) {
 }
 
 void Runtime::auto_flush() {
-    if (!opt.fuse || n_lazy > opt.flush_threshold) flush_all();
+    if (!opt.fuse || n_lazy > opt.flush_threshold + flush_floor) flush_all(true);
 }
 
-void Runtime::flush_all() {
-    if (n_lazy == 0) { pending.clear(); return; }
+void Runtime::flush_all(bool automatic) {
+    if (n_lazy == 0) { pending.clear(); flush_floor = 0; return; }
     std::vector<int32_t> targets;
     targets.reserve(pending.size());
     for (int32_t idx : pending) {
         const Node& nd = nodes[idx];
         if (nd.state == NS_LAZY && nd.ext_refs > 0) targets.push_back(idx);
     }
-    pending.clear();
+    const bool windows = opt.fuse && opt.window_levels > 0 && targets.size() > 1;
+    // an automatic flush leaves its last, incomplete window pending (run_windows) unless the graph has grown far beyond the threshold
+    const bool hold = windows && automatic && n_lazy <= 4 * opt.flush_threshold;
+    if (!hold) { pending.clear(); flush_floor = 0; }
     if (targets.empty()) return;
-    run_cone(targets, nullptr);
+    if (windows) {
+        const bool held = run_windows(targets, hold);
+        if (hold) {
+            if (held) {
+                size_t k = 0;
+                for (int32_t idx : pending) if (nodes[idx].state == NS_LAZY) pending[k++] = idx;
+                pending.resize(k);
+                flush_floor = n_lazy;
+            } else { pending.clear(); flush_floor = 0; }
+        }
+    } else run_cone(targets, nullptr);
     // the vectors this flush materialised together (see runtime.h: batched averages)
     if (opt.batch_reduce && comm_size == 1 && targets.size() >= 2) {
         FlushBatch fb;

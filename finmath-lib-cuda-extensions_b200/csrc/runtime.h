@@ -11,6 +11,7 @@
 #include <thread>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <cstring>
 #include <deque>
 #include <vector>
@@ -138,6 +139,13 @@ struct Options {
                                     // float class: coefficients within 1e-5 of it even for ill-conditioned bases; compute-bound, 45-49 % of the
                                     // roofline at k = 6..8). false: from the exact products (RandomVariableFromDoubleArray's value for the same
                                     // inputs; sums differ by ~2^-24 / sqrt(n) relative; HBM-bound, 80 % of the roofline)
+    int window_levels = 3;          // > 0: a flush without a reduction is cut into windows of this many dependency levels of still-referenced
+                                    // values (time steps of a simulation) and each window is emitted chain by chain (component-major) with the
+                                    // chains' running state kept on chip, so a value a step stores is not read back from HBM by the next step
+                                    // inside the window (codegen.cpp: Runtime::run_cone)
+    int window_elems = 0;           // chunk geometry of window kernels (0: the rule of tape_elems / min_warps)
+    int window_cta_warps = 0;       // warps per CTA of window kernels (0: cta_warps)
+    int window_ring_extra = 3;      // ring slots of a window kernel beyond the ones its long-lived leaves occupy
     bool batch_reduce = true;       // getAverage() of a vector that one flush materialised together with others: the sums of all of them in one
                                     // launch, the others' results kept for the calls that follow (Runtime::reduce_batch)
 };
@@ -272,9 +280,13 @@ public:
     void maybe_free(int32_t idx);
 
     // execution
-    void flush_all();                                     // materialise every referenced pending node
+    void flush_all(bool automatic = false);               // materialise every referenced pending node (automatic: may hold back an incomplete window)
     void materialize(int32_t idx);                        // make node idx NS_MAT
     void run_cone(const std::vector<int32_t>& targets, const ReduceSpec* red);   // core scheduler
+    bool run_windows(const std::vector<int32_t>& targets, bool hold_last);       // a flush in windows of opt.window_levels levels (codegen.cpp)
+    bool windowing = false;                               // run_cone is working through the windows of a flush
+    std::unordered_set<const float*> window_stored;       // ... buffers the earlier windows of this flush wrote (traffic accounting)
+    int64_t flush_floor = 0;                              // pending nodes the last automatic flush held back: the next one waits for flush_threshold more
     // {count, value, M2} of the LOCAL slice; with several ranks the partials of ALL ranks are left in h_result[4 * r + 0..2]
     // (one ncclAllGather behind the reduction kernel, one copy, one synchronisation)
     // returns true when `out` already is the merged result of all ranks (in-kernel exchange)

@@ -41,8 +41,8 @@ constexpr int tape_slot_bytes(int elems) { return 128 * elems; }           // 2 
 constexpr int tape_slot_shift(int elems) { return elems == 16 ? 11 : elems == 8 ? 10 : 9; }
 constexpr int TAPE_MAX_RING = 16;                      // ring slots per warp (mbarriers per warp)
 constexpr int TAPE_REGS = 16;                          // register-file slots the code generator may use
-constexpr int TAPE_MAX_INSTR = 2046;
-constexpr int TAPE_MAX_PTRS = 384;
+constexpr int TAPE_MAX_INSTR = 6142;            // a window of several time steps in one launch (codegen.cpp); single-step kernels stay below 2046
+constexpr int TAPE_MAX_PTRS = 768;
 
 // binary ops: opcode = T_BIN0 + 3 * k + {0: _I, 1: _S, 2: _W}, k = position in this list
 #define FMC_TAPE_BINOPS(X) X(MOV) X(ADD) X(SUB) X(BUS) X(MUL) X(DIV) X(VID) X(MIN) X(MAX) X(SEL) X(ADDPROD) X(ACCRUE) X(DISCOUNT)
@@ -78,6 +78,9 @@ enum TapeOp : uint32_t {
     T_AXPYST_S,      // acc = (acc * imm + imm2) * imm3 + slot + slot2 * imm4; ptrs[p] = acc; then slot is re-armed with ptrs[q] unless
                      //   q == 0xffffffff   (six words: imm, imm2, imm3, imm4 | slot2, p, q: one LMM state update = MULADDMUL ; ADD_S ;
                      //   ADDPROD_S ; STG and the T_LOAD behind the slot's last use)
+    T_RATIOACC_A,    // slot = acc; acc = (imm3 / (acc * imm + imm2)) * imm4 + slot2; slot2 = acc   (four words like T_RATIOACC_S; slot and slot2
+                     //   are register-file slots: the drift term of a state that an earlier instruction of the same kernel left in acc — a
+                     //   time step inside a window, codegen.cpp — parked for the state update that follows = STR ; RATIO ; ACCUM_S)
     T_NUM_OPS
 };
 constexpr uint32_t T_BIN0 = 20;
@@ -86,7 +89,7 @@ constexpr uint32_t T_BIN0 = 20;
 //   MIN Math.min(acc, b)   MAX Math.max(acc, b)   (NaN propagating, -0 < +0)      SEL p ? acc : b
 //   ADDPROD  acc + b * s        ACCRUE  acc * (1 + b * s)        DISCOUNT  acc / (1 + b * s)     (_S/_W only)
 static_assert(T_MOV_I == T_BIN0, "binary opcode layout");
-static_assert(T_ADDMUL_II == T_BIN0 + 39 && T_ADDAFF_W == T_BIN0 + 41 && T_ADDAFFDISC_W == T_BIN0 + 45 && T_AXPYST_S == T_BIN0 + 50 && T_NUM_OPS == T_BIN0 + 51, "binary opcode layout");
+static_assert(T_ADDMUL_II == T_BIN0 + 39 && T_ADDAFF_W == T_BIN0 + 41 && T_ADDAFFDISC_W == T_BIN0 + 45 && T_AXPYST_S == T_BIN0 + 50 && T_RATIOACC_A == T_BIN0 + 51 && T_NUM_OPS == T_BIN0 + 52, "binary opcode layout");
 
 enum ReduceMode : int {
     RM_NONE = 0,
@@ -143,6 +146,13 @@ constexpr int TAPE_INLINE_PTRS = 64;
 constexpr int TAPE_INLINE_INSTR = 426;     // words including the closing T_END and the two padding words
 struct TapeArgsInline { TapeHeader h; float* ptrs[TAPE_INLINE_PTRS]; TapeInstr instr[TAPE_INLINE_INSTR]; };
 struct TapeArgsDev { TapeHeader h; float* const* ptrs; const TapeInstr* instr; };
+// ... and the launch latency still grows with the size of the argument block below 4 KB: the tape of a short valuation (a swaption
+// of a few periods: a few dozen words) travels in a block of under 1 KB
+constexpr int TAPE_SMALL_PTRS = 16;
+constexpr int TAPE_SMALL_INSTR = 80;
+struct TapeArgsSmall { TapeHeader h; float* ptrs[TAPE_SMALL_PTRS]; TapeInstr instr[TAPE_SMALL_INSTR]; };
+static_assert(sizeof(TapeArgsSmall) <= 1024, "the small argument block");
 static_assert(sizeof(TapeArgsInline) <= 4096, "the inline argument block must stay within the 4 KB fast path");
+constexpr bool tape_fits_inline(int n_ptrs, int n_instr) { return n_instr + 2 <= TAPE_INLINE_INSTR && n_ptrs <= TAPE_INLINE_PTRS; }   // which of the two a launch gets
 
 }  // namespace fmc

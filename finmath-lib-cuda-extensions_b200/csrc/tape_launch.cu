@@ -11,6 +11,7 @@ namespace fmc {
 
 #define FMC_DECL_GEOMETRY(E)                                                                                                             \
     cudaError_t tape_launch_inline_e##E(int rk, const TapeArgsInline& a, int grid, int threads, size_t smem, cudaStream_t stream);       \
+    cudaError_t tape_launch_small_e##E(int rk, const TapeArgsSmall& a, int grid, int threads, size_t smem, cudaStream_t stream);         \
     cudaError_t tape_launch_dev_e##E(int rk, const TapeArgsDev& a, int grid, int threads, size_t smem, cudaStream_t stream);             \
     cudaError_t tape_optin_e##E(int dyn_smem);                                                                                           \
     int tape_occupancy_e##E(int rk, int threads, size_t smem_bytes);
@@ -56,7 +57,16 @@ cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t
     const size_t smem = tape_smem_bytes(P.n_ptrs, P.n_instr, P.n_slots, P.n_sets, n_warps, E);
     const int rk = reduce_kind(P.reduce_mode);
     const int words = P.n_instr + 2;
-    if (words <= TAPE_INLINE_INSTR && P.n_ptrs <= TAPE_INLINE_PTRS) {
+    if (words <= TAPE_SMALL_INSTR && P.n_ptrs <= TAPE_SMALL_PTRS) {
+        TapeArgsSmall a;
+        a.h = static_cast<const TapeHeader&>(P);
+        std::memcpy(a.ptrs, P.ptrs, sizeof(float*) * (size_t)P.n_ptrs);
+        std::memcpy(a.instr, P.instr, sizeof(TapeInstr) * (size_t)words);
+        return E == 16 ? tape_launch_small_e16(rk, a, grid, n_warps * 32, smem, stream)
+             : E == 8  ? tape_launch_small_e8(rk, a, grid, n_warps * 32, smem, stream)
+                       : tape_launch_small_e4(rk, a, grid, n_warps * 32, smem, stream);
+    }
+    if (tape_fits_inline(P.n_ptrs, P.n_instr)) {
         TapeArgsInline a;
         a.h = static_cast<const TapeHeader&>(P);
         std::memcpy(a.ptrs, P.ptrs, sizeof(float*) * (size_t)P.n_ptrs);

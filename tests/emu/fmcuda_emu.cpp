@@ -196,13 +196,13 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
                 continue;
             }
             if (op == T_MULADDMUL || op == T_RATIO || op == T_ADDAFFDISC_S || op == T_ADDAFFDISC_W || op == T_ADDAFFDISC_SL || op == T_ADDAFFDISC_WL
-                || op == T_RATIOACC_S || op == T_RATIOACC_W || op == T_AXPYST_S) {
-                const int ext = (op == T_AXPYST_S) ? 5 : (op == T_RATIO || op == T_ADDAFFDISC_SL || op == T_ADDAFFDISC_WL || op == T_RATIOACC_S || op == T_RATIOACC_W) ? 3 : 2;
+                || op == T_RATIOACC_S || op == T_RATIOACC_W || op == T_AXPYST_S || op == T_RATIOACC_A) {
+                const int ext = (op == T_AXPYST_S) ? 5 : (op == T_RATIO || op == T_ADDAFFDISC_SL || op == T_ADDAFFDISC_WL || op == T_RATIOACC_S || op == T_RATIOACC_W || op == T_RATIOACC_A) ? 3 : 2;
                 if (pc + ext >= P.n_instr) bad("multi-word instruction at the end of the tape");
                 float im[6] = {imm, 0.f, 0.f, 0.f, 0.f, 0.f};
                 uint32_t ey[6] = {in.y, 0, 0, 0, 0, 0}, ex[6] = {0, 0, 0, 0, 0, 0};
                 for (int k = 1; k <= ext; k++) {
-                    const bool names_slot = (k == 3) && (op == T_RATIOACC_S || op == T_RATIOACC_W || op == T_AXPYST_S);
+                    const bool names_slot = (k == 3) && (op == T_RATIOACC_S || op == T_RATIOACC_W || op == T_AXPYST_S || op == T_RATIOACC_A);
                     if ((P.instr[pc + k].x & ((1u << SHIFT) - 1u)) != T_END) bad("extension word %d of opcode %d carries an opcode", k, (int)op);
                     if (!names_slot && P.instr[pc + k].x != T_END) bad("extension word %d of opcode %d is not a plain T_END word", k, (int)op);
                     std::memcpy(&im[k], &P.instr[pc + k].y, 4);
@@ -218,6 +218,17 @@ void run_warp(const TapeParams& P, long long first_chunk, long long stride, std:
                     const uint32_t s2 = ex[3];
                     if ((int)s2 < P.n_ring) bad("T_RATIOACC accumulates into a ring slot");
                     for (int e = 0; e < C; e++) { float t = b[e] * im[0]; t = t + im[1]; t = im[2] / t; acc[e] = t * im[3]; }
+                    const float* c2 = w.read(s2, chunk);
+                    for (int e = 0; e < C; e++) acc[e] = acc[e] + c2[e];
+                    std::memcpy(&w.slots[(size_t)s2 * C], acc, sizeof(float) * (size_t)C);
+                } else if (op == T_RATIOACC_A) {
+                    const uint32_t s2 = ex[3];
+                    if ((int)slot < P.n_ring || (int)slot >= P.n_slots) bad("T_RATIOACC_A parks acc in slot %d outside the register file", (int)slot);
+                    if ((int)s2 < P.n_ring) bad("T_RATIOACC_A accumulates into a ring slot");
+                    if (s2 == slot) bad("T_RATIOACC_A with both operands in one slot");
+                    std::memcpy(&w.slots[(size_t)slot * C], acc, sizeof(float) * (size_t)C);
+                    w.reg_written[slot] = 1;
+                    for (int e = 0; e < C; e++) { float t = acc[e] * im[0]; t = t + im[1]; t = im[2] / t; acc[e] = t * im[3]; }
                     const float* c2 = w.read(s2, chunk);
                     for (int e = 0; e < C; e++) acc[e] = acc[e] + c2[e];
                     std::memcpy(&w.slots[(size_t)s2 * C], acc, sizeof(float) * (size_t)C);
@@ -372,6 +383,7 @@ void dump_tape(const TapeParams& P, int grid) {
         else if (op == T_ADDAFFDISC_SL || op == T_ADDAFFDISC_WL) std::fprintf(stderr, "  %4d ADDAFFDISC_%cL s%u %g\n", i, op == T_ADDAFFDISC_SL ? 'S' : 'W', slot, imm);
         else if (op == T_RATIOACC_S || op == T_RATIOACC_W) std::fprintf(stderr, "  %4d RATIOACC_%c s%u %g\n", i, op == T_RATIOACC_S ? 'S' : 'W', slot, imm);
         else if (op == T_AXPYST_S) std::fprintf(stderr, "  %4d AXPYST_S s%u %g\n", i, slot, imm);
+        else if (op == T_RATIOACC_A) std::fprintf(stderr, "  %4d RATIOACC_A s%u %g\n", i, slot, imm);
         else if (op == T_ADDAFFDISC_S || op == T_ADDAFFDISC_W) std::fprintf(stderr, "  %4d ADDAFFDISC_%c s%u %g\n", i, op == T_ADDAFFDISC_S ? 'S' : 'W', slot, imm);
         else if (op == T_ADDMUL_II) std::fprintf(stderr, "  %4d ADDMUL_II %g\n", i, imm);
         else if (op == T_ADDAFF_S || op == T_ADDAFF_W) std::fprintf(stderr, "  %4d ADDAFF_%c s%u %g\n", i, op == T_ADDAFF_S ? 'S' : 'W', slot, imm);
@@ -420,7 +432,9 @@ cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t
                 v = mean; part.c = (double)values.size();
             }
             P.result[0] = part.c; P.result[1] = v; P.result[2] = m2;
-            if (P.host_result) { P.host_result[0] = part.c; P.host_result[1] = v; P.host_result[2] = m2; P.host_result[3] = P.ticket; }
+            // (sums of an unsharded vector: the kernel publishes {host[2] = value, host[3] = ticket}, reduce_common.cuh)
+            const bool sum_pair = P.xchg.nranks <= 1 && (P.reduce_mode == RM_SUM || P.reduce_mode == RM_DOT || P.reduce_mode == RM_WSQ);
+            if (P.host_result) { P.host_result[0] = part.c; P.host_result[1] = v; P.host_result[2] = sum_pair ? v : m2; P.host_result[3] = P.ticket; }
         }
         return cudaSuccess;
     } catch (const Check& c) {
@@ -508,7 +522,8 @@ cudaError_t launch_reduce(const ReduceParams& P, int, cudaStream_t) {
         for (double x : vals) m2 += (x - v) * (x - v);
     }
     P.result[0] = c; P.result[1] = v; P.result[2] = m2;
-    if (P.host_result) { P.host_result[0] = c; P.host_result[1] = v; P.host_result[2] = m2; P.host_result[3] = P.ticket; }
+    const bool sum_pair = P.xchg.nranks <= 1 && (P.mode == RM_SUM || P.mode == RM_DOT || P.mode == RM_WSQ);
+    if (P.host_result) { P.host_result[0] = c; P.host_result[1] = v; P.host_result[2] = sum_pair ? v : m2; P.host_result[3] = P.ticket; }
     return cudaSuccess;
 }
 cudaError_t launch_batch_sum(const BatchSumParams& P, cudaStream_t) {

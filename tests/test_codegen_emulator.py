@@ -39,3 +39,13 @@ def test_parity_suite_on_the_emulator(emulator):
                                   "grid_limit=1", "grid_limit=3,max_sets=2", "grid_limit=2,max_sets=3,ring_max=2,ring_min=1"])
 def test_parity_suite_on_the_emulator_with_scheduler_knobs(emulator, opts):
     run_parity(emulator, {"FMC_TEST_OPTIONS": opts}, select="compound or ragged or reductions or fused or long_tape or unfused")
+
+
+def test_windows_of_time_steps_on_the_emulator(emulator):
+    """Option window_levels: the LMM simulation emitted in windows of several time steps (component-major, running sums kept in the
+    register file, T_RATIOACC_A) gives bit-identical LIBORs to one launch per step, in every geometry; the emulator also checks the
+    ring / register-file discipline of the long window tapes."""
+    env = dict(os.environ, LD_PRELOAD=emulator, FMC_EMU_FAKE_BROWNIAN="1")
+    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "run_window_check.py"), "700"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+    assert r.stdout.count("LIBORs bit-identical True") >= 6, r.stdout

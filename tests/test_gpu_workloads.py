@@ -70,6 +70,45 @@ def test_lmm_simulation_and_swaptions_match_oracle(libs, paths):
     assert np.all(np.abs(iv - 0.005) < 0.0015)
 
 
+@pytest.mark.parametrize("paths", [700, 70_000])
+def test_windows_of_time_steps_give_the_same_simulation(libs, paths):
+    """Option window_levels (several Euler time steps per launch, emitted component by component with the running sums of the
+    window's steps kept on chip): same arithmetic per path in a different schedule — the LIBORs are bit-identical
+    to one launch per time step, with fewer launches; every geometry; the oracle agrees."""
+    import finmath_cuda as fcm
+    gpu, cpu = libs
+    probes = ((1, 5), (2, 2), (7, 7), (7, 8), (8, 79), (33, 34), (40, 60), (41, 41), (79, 79), (80, 79))
+
+    def run(window, elems):
+        fcm.set_option("window_levels", window)
+        fcm.set_option("tape_elems", elems)
+        m = gpu.lmm(paths)
+        k0 = fcm.stats()["n_kernels"]
+        m.simulate()
+        fcm.sync()
+        k1 = fcm.stats()["n_kernels"]
+        vals = m.step()
+        out = [m.libor(t, i).copy() for (t, i) in probes]
+        m.close()
+        return out, k1 - k0, vals
+    try:
+        ref, launches0, vals0 = run(0, 0)
+        mc = cpu.lmm(paths)
+        mc.step()
+        for (t, i), a in zip(probes, ref):
+            assert np.array_equal(a, mc.libor(t, i)), (t, i)
+        for window, elems in ((1, 0), (2, 0), (3, 0), (4, 16), (3, 8), (6, 8), (2, 4), (5, 4)):
+            got, launches, vals = run(window, elems)
+            for (t, i), a, b in zip(probes, got, ref):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (window, elems, t, i)
+            assert np.allclose(vals, vals0, rtol=1e-12, atol=0), (window, elems)
+            if window >= 2:
+                assert launches < launches0, (window, elems, launches, launches0)
+    finally:
+        fcm.set_option("window_levels", 3)
+        fcm.set_option("tape_elems", 0)
+
+
 def test_bermudan_swaption_matches_oracle(libs):
     """BASELINE config 3 (small): backward induction with conditional-expectation regression and choose()."""
     gpu, cpu = libs
