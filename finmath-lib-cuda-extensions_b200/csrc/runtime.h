@@ -143,8 +143,8 @@ struct Options {
                                     // values (time steps of a simulation) and each window is emitted chain by chain (component-major) with the
                                     // chains' running state kept on chip, so a value a step stores is not read back from HBM by the next step
                                     // inside the window (codegen.cpp: Runtime::run_cone)
-    int window_elems = 0;           // chunk geometry of window kernels (0: the rule of tape_elems / min_warps)
-    int window_cta_warps = 0;       // warps per CTA of window kernels (0: cta_warps)
+    int window_elems = 8;           // chunk geometry of window kernels (0: the rule of tape_elems / min_warps)
+    int window_cta_warps = 8;       // warps per CTA of window kernels (0: cta_warps)
     int window_ring_extra = 3;      // ring slots of a window kernel beyond the ones its long-lived leaves occupy
     bool batch_reduce = true;       // getAverage() of a vector that one flush materialised together with others: the sums of all of them in one
                                     // launch, the others' results kept for the calls that follow (Runtime::reduce_batch)
