@@ -180,10 +180,12 @@ def run_reference(args) -> None:
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (an LMM Euler-step launch of the tape
 # interpreter at 1 Mi paths) from one `ncu --set full` capture; NOT measured in this run, NOT comparable with the per-step
 # algorithmic bytes: reported under its own name with the capture it came from (None until this round's capture exists).
-NCU_DRAM_BYTES_DOMINANT_LAUNCH = 532_298_240     # 294.57 MB read + 237.73 MB written, second launch of profiles/prof_sim_r2.txt (101.95 us)
-NCU_ALGORITHMIC_BYTES_OF_THAT_LAUNCH = 289_406_976   # its tape: 2 leaf vectors + 67 result vectors x 4 MiB (the 69 rates of the previous
-                                                     # step it re-reads were stored by the launch before it in the same flush: not algorithmic)
-NCU_CAPTURE_FILE = "profiles/prof_sim_r2.txt (ncu --set full --clock-control none -k regex:tape_kernel -s 234 -c 3 of bench.py --steps 2 --warmup 1; launch list profiles/launches_r2.txt)"
+NCU_DRAM_BYTES_DOMINANT_LAUNCH = 872_502_784     # 244.66 MB read + 627.84 MB written, first launch of profiles/prof_sim_r3.txt (227.7 us): one
+                                                 # window of three Euler time steps (round 1 / early round 2: 533 MB for ONE time step)
+NCU_ALGORITHMIC_BYTES_OF_THAT_LAUNCH = 1_266_679_808   # its tape: 78 leaf vectors (75 rates + 3 Brownian increments) + 224 result vectors x 4 MiB.
+                                                 # The DRAM traffic is BELOW it: part of the stores still sits in the L2 when the kernel ends and
+                                                 # some leaves are hit there; the rates a step stores are no longer read back inside the window
+NCU_CAPTURE_FILE = "profiles/prof_sim_r3.txt (ncu --set full --clock-control none -k regex:tape_kernel -s 173 -c 3 of bench.py --steps 2 --warmup 1; launch list profiles/launches_r3.txt)"
 
 PARITY_REL_TOL = 1e-4       # north star: "Monte-Carlo prices ... match within 1e-4 relative on identical seeds"
 
@@ -447,7 +449,7 @@ def run_ours(args) -> None:
                 "kernel_share_of_step": (prof["tape_ms"] / args.steps) / step_ms if step_ms > 0 else None,
                 "algorithmic_bytes_per_step": prof["tape_algorithmic_bytes"] / args.steps,
                 # every vector the kernels read or wrote, INCLUDING the re-read of results an earlier kernel of the same
-                # flush stored (each Euler-step kernel re-reads the rates the previous one wrote): what HBM actually moves
+                # flush stored (the first time step of a window re-reads the rates the window before it wrote): what HBM actually moves
                 "touched_bytes_per_step": touched.value / args.steps,
                 "achieved_touched": touched.value / (prof["tape_ms"] * 1e-3) / 1e9 if prof["tape_ms"] > 0 else 0.0,
                 "frac_touched": (touched.value / (prof["tape_ms"] * 1e-3) / 1e9) / peak if prof["tape_ms"] > 0 else 0.0}
