@@ -21,9 +21,11 @@ D = DriverLib()
 probes = [(1, 5), (2, 2), (7, 7), (7, 8), (8, 79), (33, 34), (40, 60), (41, 41), (79, 79), (80, 79)]
 
 
-def run(w, elems=0):
+def run(w, elems=0, threshold=4096, reduce_min=2048):
     fc.set_option("window_levels", w)
     fc.set_option("tape_elems", elems)
+    fc.set_option("flush_threshold", threshold)
+    fc.set_option("window_reduce_min", reduce_min)
     m = D.lmm(paths, 80, 0.5, 1, 31415, 0, (0, paths))
     vals = np.asarray(m.step()).copy()
     libors = [m.libor(t, i).copy() for (t, i) in probes]
@@ -40,5 +42,11 @@ for w, e in ((2, 0), (3, 0), (4, 0), (3, 8), (5, 8), (2, 4)):
     same_l = all(np.array_equal(a.view(np.uint32), b.view(np.uint32)) for a, b in zip(libors, ref_libors))
     print(f"window_levels={w} tape_elems={e}: swaption values identical {same_v}, LIBORs bit-identical {same_l}")
     ok = ok and same_v and same_l
-fc.set_option("window_levels", 3); fc.set_option("tape_elems", 0)
+# no automatic flush at all: the whole simulation is still pending when the first swaption is valued and goes through the windows there
+vals, libors = run(3, 0, threshold=10_000_000, reduce_min=0)
+same_v = np.array_equal(vals, ref_vals)
+same_l = all(np.array_equal(a.view(np.uint32), b.view(np.uint32)) for a, b in zip(libors, ref_libors))
+print(f"window_levels=3, simulation flushed by the first valuation: swaption values identical {same_v}, LIBORs bit-identical {same_l}")
+ok = ok and same_v and same_l
+fc.set_option("window_levels", 3); fc.set_option("tape_elems", 0); fc.set_option("flush_threshold", 4096); fc.set_option("window_reduce_min", 2048)
 sys.exit(0 if ok else 1)

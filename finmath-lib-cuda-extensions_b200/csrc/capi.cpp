@@ -415,6 +415,7 @@ static void set_option_locked(Runtime& rt, const char* key, double value) {
     else if (!std::strcmp(key, "window_levels")) rt.opt.window_levels = (int)value;
     else if (!std::strcmp(key, "window_elems")) rt.opt.window_elems = (int)value;
     else if (!std::strcmp(key, "window_cta_warps")) rt.opt.window_cta_warps = std::max(0, std::min((int)value, (int)TAPE_MAX_WARPS));
+    else if (!std::strcmp(key, "window_reduce_min")) rt.opt.window_reduce_min = std::max(0, (int)value);
     else if (!std::strcmp(key, "window_ring_extra")) rt.opt.window_ring_extra = std::max(1, (int)value);
     else if (!std::strcmp(key, "ring_max")) rt.opt.ring_max = std::max(1, std::min((int)value, (int)TAPE_MAX_RING));
     else if (!std::strcmp(key, "ring_min")) rt.opt.ring_min = std::max(1, std::min((int)value, (int)TAPE_MAX_RING));

@@ -954,15 +954,33 @@ void tape_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* entries) { *hi
 // from HBM by the next step of the same window. Level of a target = the longest chain of still-referenced pending values below it.
 // hold_last (automatic flushes): the flush threshold falls in the middle of a time step and of a window; what is incomplete stays
 // pending, so that windows begin and end on whole levels. Returns true when something was held back.
-bool Runtime::run_windows(const std::vector<int32_t>& targets, bool hold_last) {
+bool Runtime::run_windows(const std::vector<int32_t>& targets, const std::vector<int32_t>& recorded, bool hold_last) {
     const int W = std::max(1, opt.window_levels);
     epoch++;
     if (epoch == 0) { for (auto& nd : nodes) nd.epoch = 0; epoch = 1; }
+    // levels in ONE linear pass over the pending list: it is in recording order, so a node's operands come before it (an entry whose
+    // slot was recycled by a later node can come before ITS operands: such a node is walked depth-first on the spot)
     static thread_local std::vector<std::pair<int32_t, int>> lstack;
     int max_level = 0;
-    for (int32_t t : targets) {
-        if (nodes[t].state != NS_LAZY || nodes[t].epoch == epoch) continue;
-        nodes[t].epoch = epoch; nodes[t].local = 0;
+    auto level_of = [&](const Node& nd) {
+        int32_t lev = 0;
+        for (int k = 0; k < 3; k++) {
+            const int32_t u = nd.in[k];
+            if (u >= 0 && nodes[u].state == NS_LAZY) lev = std::max(lev, nodes[u].local + (nodes[u].ext_refs > 0 ? 1 : 0));
+        }
+        return lev;
+    };
+    for (int32_t t : recorded) {
+        Node& nt = nodes[t];
+        if (nt.state != NS_LAZY || nt.epoch == epoch) continue;
+        bool ready = true;
+        for (int k = 0; k < 3; k++) { const int32_t u = nt.in[k]; if (u >= 0 && nodes[u].state == NS_LAZY && nodes[u].epoch != epoch) ready = false; }
+        if (ready) {
+            nt.epoch = epoch; nt.local = level_of(nt);
+            max_level = std::max(max_level, (int)nt.local);
+            continue;
+        }
+        nt.epoch = epoch; nt.local = 0;
         lstack.clear();
         lstack.emplace_back(t, 0);
         while (!lstack.empty()) {
@@ -972,13 +990,8 @@ bool Runtime::run_windows(const std::vector<int32_t>& targets, bool hold_last) {
                 const int32_t u = nodes[v].in[top.second++];
                 if (u >= 0 && nodes[u].state == NS_LAZY && nodes[u].epoch != epoch) { nodes[u].epoch = epoch; nodes[u].local = 0; lstack.emplace_back(u, 0); }
             } else {
-                int32_t lev = 0;
-                for (int k = 0; k < 3; k++) {
-                    const int32_t u = nodes[v].in[k];
-                    if (u >= 0 && nodes[u].state == NS_LAZY) lev = std::max(lev, nodes[u].local + (nodes[u].ext_refs > 0 ? 1 : 0));
-                }
-                nodes[v].local = lev;
-                max_level = std::max(max_level, (int)lev);
+                nodes[v].local = level_of(nodes[v]);
+                max_level = std::max(max_level, (int)nodes[v].local);
                 lstack.pop_back();
             }
         }
@@ -1335,6 +1348,36 @@ bool Runtime::reduce(int32_t idx, const ReduceSpec& spec_in, double out[3]) {
         if (opt.profile) profile_end(4ull * (uint64_t)P.n * (P.w ? 2u : 1u));
         stats.n_kernels++; stats.n_flushes++;
     } else {
+        // The pending part of a simulation that this valuation reads (what the last automatic flush held back, and the steps
+        // recorded since) goes through the windows first: the still-referenced pending values below idx, in recording order.
+        // The valuation's own chain stays fused with its reduction; pending values it does not read stay pending.
+        if (opt.fuse && opt.window_levels > 0 && n_lazy > opt.window_reduce_min && !windowing) {
+            epoch++;
+            if (epoch == 0) { for (auto& nd : nodes) nd.epoch = 0; epoch = 1; }
+            static thread_local std::vector<int32_t> walk, below;
+            walk.clear(); below.clear();
+            nodes[idx].epoch = epoch; walk.push_back(idx);
+            size_t n_ext = 0;
+            while (!walk.empty()) {
+                const int32_t v = walk.back(); walk.pop_back();
+                for (int k = 0; k < 3; k++) {
+                    const int32_t u = nodes[v].in[k];
+                    if (u < 0 || nodes[u].state != NS_LAZY || nodes[u].epoch == epoch) continue;
+                    nodes[u].epoch = epoch; walk.push_back(u);
+                    if (nodes[u].ext_refs > 0) n_ext++;
+                }
+            }
+            if (n_ext >= 32) {                                  // a simulation's worth, not the few cached numeraires a valuation extends
+                const uint32_t mark = epoch;
+                for (int32_t t : pending) if (t != idx && nodes[t].state == NS_LAZY && nodes[t].epoch == mark && nodes[t].ext_refs > 0) {
+                    below.push_back(t);
+                    nodes[t].epoch = mark - 1;                 // a recycled slot can appear twice in the list
+                }
+                static thread_local std::vector<int32_t> order;
+                order = pending;                               // run_cone compacts nothing, but the walk must not alias a list that changes
+                if (below.size() >= 32) run_windows(below, order, false);
+            }
+        }
         std::vector<int32_t> t{idx};
         last_tape_xhost = false;
         run_cone(t, &spec);                   // the fused chain -> reduce launch sets params->ticket (Gen::launch)

@@ -215,10 +215,12 @@ void Runtime::flush_all(bool automatic) {
     const bool windows = opt.fuse && opt.window_levels > 0 && targets.size() > 1;
     // an automatic flush leaves its last, incomplete window pending (run_windows) unless the graph has grown far beyond the threshold
     const bool hold = windows && automatic && n_lazy <= 4 * opt.flush_threshold;
-    if (!hold) { pending.clear(); flush_floor = 0; }
+    static thread_local std::vector<int32_t> order;      // the pending list of this flush (run_windows walks it; run_cone may record nothing, but stay safe)
+    order.clear();
+    if (!hold) { order.swap(pending); flush_floor = 0; }
     if (targets.empty()) return;
     if (windows) {
-        const bool held = run_windows(targets, hold);
+        const bool held = run_windows(targets, hold ? pending : order, hold);
         if (hold) {
             if (held) {
                 size_t k = 0;

@@ -145,6 +145,8 @@ struct Options {
                                     // inside the window (codegen.cpp: Runtime::run_cone)
     int window_elems = 8;           // chunk geometry of window kernels (0: the rule of tape_elems / min_warps)
     int window_cta_warps = 8;       // warps per CTA of window kernels (0: cta_warps)
+    int window_reduce_min = 2048;   // a reduction whose target is pending first sends the still-referenced pending values below it through the
+                                    // windows when more than this many nodes are pending (the tail of a simulation that the first valuation reads)
     int window_ring_extra = 3;      // ring slots of a window kernel beyond the ones its long-lived leaves occupy
     bool batch_reduce = true;       // getAverage() of a vector that one flush materialised together with others: the sums of all of them in one
                                     // launch, the others' results kept for the calls that follow (Runtime::reduce_batch)
@@ -283,7 +285,7 @@ public:
     void flush_all(bool automatic = false);               // materialise every referenced pending node (automatic: may hold back an incomplete window)
     void materialize(int32_t idx);                        // make node idx NS_MAT
     void run_cone(const std::vector<int32_t>& targets, const ReduceSpec* red);   // core scheduler
-    bool run_windows(const std::vector<int32_t>& targets, bool hold_last);       // a flush in windows of opt.window_levels levels (codegen.cpp)
+    bool run_windows(const std::vector<int32_t>& targets, const std::vector<int32_t>& recorded, bool hold_last);       // a flush in windows of opt.window_levels levels (codegen.cpp)
     bool windowing = false;                               // run_cone is working through the windows of a flush
     std::unordered_set<const float*> window_stored;       // ... buffers the earlier windows of this flush wrote (traffic accounting)
     int64_t flush_floor = 0;                              // pending nodes the last automatic flush held back: the next one waits for flush_threshold more

@@ -104,9 +104,23 @@ def test_windows_of_time_steps_give_the_same_simulation(libs, paths):
             assert np.allclose(vals, vals0, rtol=1e-12, atol=0), (window, elems)
             if window >= 2:
                 assert launches < launches0, (window, elems, launches, launches0)
+        # no automatic flush: the whole simulation is still pending when the first swaption is valued and goes through the
+        # windows there (Runtime::reduce)
+        fcm.set_option("window_levels", 3)
+        fcm.set_option("tape_elems", 0)
+        fcm.set_option("flush_threshold", 10_000_000)
+        fcm.set_option("window_reduce_min", 0)
+        m = gpu.lmm(paths)
+        vals = m.step()
+        for (t, i), b in zip(probes, ref):
+            assert np.array_equal(m.libor(t, i).view(np.uint32), b.view(np.uint32)), ("flushed by the first valuation", t, i)
+        assert np.allclose(vals, vals0, rtol=1e-12, atol=0)
+        m.close()
     finally:
         fcm.set_option("window_levels", 3)
         fcm.set_option("tape_elems", 0)
+        fcm.set_option("flush_threshold", 4096)
+        fcm.set_option("window_reduce_min", 2048)
 
 
 def test_bermudan_swaption_matches_oracle(libs):
