@@ -443,6 +443,9 @@ struct Gen {
                 i += 3;
                 continue;
             }
+            // x * 1.0f and x / 1.0f are x for every float (NaN stays NaN, -0 stays -0): no instruction (a swaption value is multiplied
+            // by the numeraire at time 0, the scalar 1). The tape-cache key records which scalar operands equal 1.0f.
+            if ((a.op == (A_BIN | B_MUL) || a.op == (A_BIN | B_DIV)) && a.kind == K_IMM && a.y == f2u(1.0f)) continue;
             if (i + 1 < A.size() && a.op == (A_BIN | B_MUL) && a.kind == K_IMM && A[i + 1].op == (A_BIN | B_ADD) && A[i + 1].kind == K_IMM) {
                 out.push_back(mk((uint16_t)T_MULADD_II, K_IMM, (int32_t)A[i + 1].y, a.y, a.src, 0, A[i + 1].src));   // arg carries the second immediate's bits
                 i += 1;
