@@ -608,6 +608,12 @@ int fmc_regression_normal_eq(const fmc_vec* basis, const double* scalars, int k,
     });
 }
 
+#ifdef FMC_TAPE_TIMING
+int fmc_debug_stamps(unsigned long long* out) {
+    return guarded([&](Runtime& rt) { rt.require_init(); FMC_CUDA(cudaStreamSynchronize(rt.stream)); FMC_CUDA(fmc::tape_read_stamps_e16(out)); });
+}
+#endif
+
 // ---- Brownian ----
 int fmc_brownian_generate(int seed_mode, int64_t seed, int T, int F, int64_t p0, int64_t p1, const double* sqrt_dt, fmc_vec* out) {
     return guarded([&](Runtime& rt) {

@@ -12,6 +12,9 @@ namespace fmc {
 cudaError_t launch_tape(const TapeParams& P, int grid, int n_warps, cudaStream_t stream, cudaStream_t copy_stream);
 cudaError_t tape_kernel_setup(size_t* max_smem_per_cta);   // opts the kernels in to the device's full shared memory, allocates the tape ring
 void tape_kernel_teardown();
+#ifdef FMC_TAPE_TIMING
+cudaError_t tape_read_stamps_e16(unsigned long long* out);   // development aid (Makefile: timing): globaltimer stamps of the last fused reduction
+#endif
 size_t tape_smem_bytes(int n_ptrs, int n_instr, int n_slots, int n_sets, int n_warps, int elems);   // dynamic shared memory of one CTA
 int tape_max_blocks_per_sm(size_t smem_bytes, int reduce_mode, int n_warps, int elems);
 

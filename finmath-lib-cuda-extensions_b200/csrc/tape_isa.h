@@ -154,5 +154,7 @@ struct TapeArgsSmall { TapeHeader h; float* ptrs[TAPE_SMALL_PTRS]; TapeInstr ins
 static_assert(sizeof(TapeArgsSmall) <= 1024, "the small argument block");
 static_assert(sizeof(TapeArgsInline) <= 4096, "the inline argument block must stay within the 4 KB fast path");
 constexpr bool tape_fits_inline(int n_ptrs, int n_instr) { return n_instr + 2 <= TAPE_INLINE_INSTR && n_ptrs <= TAPE_INLINE_PTRS; }   // which of the two a launch gets
+template <typename ARGS> struct tape_args_in_global { static constexpr bool value = false; };
+template <> struct tape_args_in_global<TapeArgsDev> { static constexpr bool value = true; };
 
 }  // namespace fmc

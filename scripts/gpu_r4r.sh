@@ -1,0 +1,6 @@
+timeout -s KILL 1700 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for m in 4 20; do timeout -s KILL 300 python benchmarks/kernel_timeline.py 1048576 $m 2>&1 | tail -12; done
+for rep in 1 2; do timeout -s KILL 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-calibration --no-extras 2>/dev/null | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print('ms_per_step',round(d['ms_per_step'],3),'kernel',round(d['roofline']['kernel_ms_per_step'],3),'frac',round(d['roofline']['frac'],4),'e2e',round(d['e2e']['ms_per_step'],2),'pp',round(d['price_products_step']['ms_per_step'],2))"; done
+for p in 10000; do FMC_OPTIONS=$o timeout -s KILL 300 python benchmarks/lmm_phases.py $p 2>&1 | grep -A3 "timing off" | tail -3; done
