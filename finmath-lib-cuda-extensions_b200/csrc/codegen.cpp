@@ -797,7 +797,7 @@ struct Gen {
         std::vector<TapeInstr> prologue, body;
         KernelPlan kp;
         int n_ring = 0;
-        const int n_warps = std::max(1, std::min(rt.windowing && rt.opt.window_cta_warps > 0 ? rt.opt.window_cta_warps : rt.opt.cta_warps, TAPE_MAX_WARPS));
+        int n_warps = std::max(1, std::min(rt.windowing && rt.opt.window_cta_warps > 0 ? rt.opt.window_cta_warps : rt.opt.cta_warps, TAPE_MAX_WARPS));
         // Chunk geometry (elements per lane, tape_interp.cuh). A warp interprets one chunk of 32 E paths at a time, so a vector
         // of n paths is n / (32 E) warps' worth of work per pass: the largest E that still gives every SM `min_warps` warps
         // (16-element chunks amortise the dispatch best; below that the GPU's warp slots stay empty and the interpreter runs
@@ -811,6 +811,7 @@ struct Gen {
             for (int e = TAPE_E_MAX; e > 4; e >>= 1)
                 if (n >= (int64_t)rt.opt.min_warps * rt.sm_count * tape_chunk(e)) { elems = e; break; }
         }
+        n_warps = std::min(n_warps, elems == 16 ? 16 : elems == 8 ? 28 : 32);       // 64 K registers per CTA at 128 / 72 / 40 per thread
         const int slot_bytes = tape_slot_bytes(elems);
         const int64_t chunks = (n + tape_chunk(elems) - 1) / tape_chunk(elems);
         // Shared-memory budget of one warp, in slots, if `target` CTAs are to be resident per SM: as many as the vector needs

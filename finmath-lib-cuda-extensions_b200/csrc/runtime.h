@@ -144,7 +144,7 @@ struct Options {
                                     // chains' running state kept on chip, so a value a step stores is not read back from HBM by the next step
                                     // inside the window (codegen.cpp: Runtime::run_cone)
     int window_elems = 8;           // chunk geometry of window kernels (0: the rule of tape_elems / min_warps)
-    int window_cta_warps = 8;       // warps per CTA of window kernels (0: cta_warps)
+    int window_cta_warps = 16;      // warps per CTA of window kernels (0: cta_warps)
     int window_reduce_min = 2048;   // a reduction whose target is pending first sends the still-referenced pending values below it through the
                                     // windows when more than this many nodes are pending (the tail of a simulation that the first valuation reads)
     int window_ring_extra = 3;      // ring slots of a window kernel beyond the ones its long-lived leaves occupy

@@ -34,7 +34,7 @@ namespace fmc {
 // chunk geometry: E elements per lane (16, 8 or 4), chosen per launch
 constexpr int TAPE_E_MAX = 16;
 constexpr int TAPE_WARPS = 4;                          // warps per CTA (default)
-constexpr int TAPE_MAX_WARPS = 8;                      // ... upper bound (block reduction scratch)
+constexpr int TAPE_MAX_WARPS = 32;                     // ... upper bound (block reduction scratch; codegen.cpp also caps it by the register file: 65536 / (32 * registers per thread))
 constexpr bool tape_valid_elems(int e) { return e == 16 || e == 8 || e == 4; }
 constexpr int tape_chunk(int elems) { return 32 * elems; }                 // paths per warp iteration: 512 / 256 / 128
 constexpr int tape_slot_bytes(int elems) { return 128 * elems; }           // 2 KB / 1 KB / 512 B
