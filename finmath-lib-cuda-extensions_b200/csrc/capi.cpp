@@ -412,7 +412,7 @@ static void set_option_locked(Runtime& rt, const char* key, double value) {
     else if (!std::strcmp(key, "max_regs")) rt.opt.max_regs = std::max(4, std::min((int)value, (int)TAPE_REGS));
     else if (!std::strcmp(key, "fuse")) { rt.opt.fuse = value != 0.0; if (rt.initialized) rt.flush_all(); }
     else if (!std::strcmp(key, "profile")) rt.opt.profile = value != 0.0;
-    else if (!std::strcmp(key, "window_levels")) rt.opt.window_levels = (int)value;
+    else if (!std::strcmp(key, "window_levels")) { rt.opt.window_levels = (int)value; rt.window_levels_now = 0; }
     else if (!std::strcmp(key, "window_elems")) rt.opt.window_elems = (int)value;
     else if (!std::strcmp(key, "window_cta_warps")) rt.opt.window_cta_warps = std::max(0, std::min((int)value, (int)TAPE_MAX_WARPS));
     else if (!std::strcmp(key, "window_reduce_min")) rt.opt.window_reduce_min = std::max(0, (int)value);

@@ -959,7 +959,12 @@ void tape_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* entries) { *hi
 // hold_last (automatic flushes): the flush threshold falls in the middle of a time step and of a window; what is incomplete stays
 // pending, so that windows begin and end on whole levels. Returns true when something was held back.
 bool Runtime::run_windows(const std::vector<int32_t>& targets, const std::vector<int32_t>& recorded, bool hold_last) {
-    const int W = std::max(1, opt.window_levels);
+    // W adapts: a model whose chains share more state per level than the register file holds (a three-factor LMM: three running sums
+    // and three Brownian increments per time step) makes the generator spill and cut a window into many small launches — more than
+    // one per level, i.e. worse than no window. Such a window lowers W for the flushes that follow (never below 1: one launch per
+    // level, the order of round 1); setting the option window_levels starts over.
+    if (window_levels_now <= 0 || window_levels_now > opt.window_levels) window_levels_now = opt.window_levels;
+    const int W = std::max(1, window_levels_now);
     epoch++;
     if (epoch == 0) { for (auto& nd : nodes) nd.epoch = 0; epoch = 1; }
     // levels in ONE linear pass over the pending list: it is in recording order, so a node's operands come before it (an entry whose
@@ -1037,7 +1042,14 @@ bool Runtime::run_windows(const std::vector<int32_t>& targets, const std::vector
     struct Clear { std::unordered_set<const float*>& s; ~Clear() { s.clear(); } } clear_stored{window_stored};
     for (int w = 0; w < n_run; w++) {
         if (win[(size_t)w].empty()) continue;
+        const uint64_t launches0 = stats.n_tape_kernels;
         run_cone(win[(size_t)w], nullptr);
+        const int levels_here = std::min(W, max_level + 1 - w * W);
+        if (W > 1 && stats.n_tape_kernels - launches0 > (uint64_t)levels_here + 1 && window_levels_now == W) {
+            window_levels_now = W - 1;
+            if (log_windows) std::fprintf(stderr, "[fmc windows] a window of %d levels took %llu launches: W -> %d\n", levels_here,
+                                          (unsigned long long)(stats.n_tape_kernels - launches0), window_levels_now);
+        }
         if (w + 1 < n_run) for (int32_t t : win[(size_t)w]) if (nodes[t].state == NS_MAT) window_stored.insert(nodes[t].buf);
     }
     return n_run < n_win;

@@ -286,6 +286,7 @@ public:
     void materialize(int32_t idx);                        // make node idx NS_MAT
     void run_cone(const std::vector<int32_t>& targets, const ReduceSpec* red);   // core scheduler
     bool run_windows(const std::vector<int32_t>& targets, const std::vector<int32_t>& recorded, bool hold_last);       // a flush in windows of opt.window_levels levels (codegen.cpp)
+    int window_levels_now = 0;                            // levels per window in use (<= opt.window_levels; lowered when windows spill, codegen.cpp: run_windows)
     bool windowing = false;                               // run_cone is working through the windows of a flush
     std::unordered_set<const float*> window_stored;       // ... buffers the earlier windows of this flush wrote (traffic accounting)
     int64_t flush_floor = 0;                              // pending nodes the last automatic flush held back: the next one waits for flush_threshold more

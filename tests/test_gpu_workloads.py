@@ -123,6 +123,41 @@ def test_windows_of_time_steps_give_the_same_simulation(libs, paths):
         fcm.set_option("window_reduce_min", 2048)
 
 
+def test_windows_adapt_to_a_three_factor_model(libs):
+    """Three running sums and three Brownian increments per time step do not fit the register file for windows of three levels:
+    the window size adapts (Runtime::run_windows) — LIBORs bit-identical to one launch per time step and to the oracle, and about
+    as many launches."""
+    import finmath_cuda as fcm
+    gpu, cpu = libs
+    paths = 5000
+    probes = ((1, 5), (7, 8), (20, 30), (39, 39), (40, 39))
+
+    def run(window):
+        fcm.set_option("window_levels", window)
+        m = gpu.lmm(paths, 40, 0.5, 3)
+        for _ in range(2):
+            m.simulate()
+            fcm.sync()
+        k0 = fcm.stats()["n_kernels"]
+        m.simulate()
+        fcm.sync()
+        launches = fcm.stats()["n_kernels"] - k0
+        out = [m.libor(t, i).copy() for (t, i) in probes]
+        m.close()
+        return launches, out
+    try:
+        l0, ref = run(0)
+        l3, got = run(3)
+        mc = cpu.lmm(paths, 40, 0.5, 3)
+        mc.simulate()
+        for (t, i), a, b in zip(probes, got, ref):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (t, i)
+            assert np.array_equal(a, mc.libor(t, i)), (t, i)
+        assert l3 <= l0 + 8, (l3, l0)
+    finally:
+        fcm.set_option("window_levels", 3)
+
+
 def test_bermudan_swaption_matches_oracle(libs):
     """BASELINE config 3 (small): backward induction with conditional-expectation regression and choose()."""
     gpu, cpu = libs
