@@ -1031,9 +1031,6 @@ bool Runtime::run_windows(const std::vector<int32_t>& targets, const std::vector
         for (auto& wt : win) std::fprintf(stderr, " %zu", wt.size());
         std::vector<int> per_level((size_t)max_level + 1, 0);
         for (int32_t t : targets) if (nodes[t].state == NS_LAZY) per_level[(size_t)nodes[t].local]++;
-        if (std::getenv("FMC_LOG_LEVEL0")) for (int32_t t : targets) if (nodes[t].state == NS_LAZY && nodes[t].local == 0)
-            std::fprintf(stderr, "\n   L0 target node %d op %d ext %u int %u in %d/%d/%d states %d/%d", t, (int)nodes[t].op, nodes[t].ext_refs, nodes[t].int_refs, nodes[t].in[0], nodes[t].in[1], nodes[t].in[2],
-                         nodes[t].in[0] >= 0 ? (int)nodes[nodes[t].in[0]].state : -1, nodes[t].in[1] >= 0 ? (int)nodes[nodes[t].in[1]].state : -1);
         std::fprintf(stderr, "   per level:");
         for (int c : per_level) std::fprintf(stderr, " %d", c);
         std::fprintf(stderr, "\n");
