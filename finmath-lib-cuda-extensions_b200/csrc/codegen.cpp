@@ -881,6 +881,7 @@ struct Gen {
         for (;;) {
             smem = tape_smem_bytes((int)ptrs.size(), kp.n_instr, kp.n_slots, n_sets, n_warps, elems);
             if (smem > rt.smem_per_cta_max && n_sets > 1) { n_sets--; continue; }
+            if (smem > rt.smem_per_cta_max && n_warps > 1) { n_warps = std::max(1, n_warps / 2); kp.n_warps = n_warps; continue; }   // a wide CTA of a forced geometry
             if (smem > rt.smem_per_cta_max) fail(FMC_ERR_UNSUPPORTED, "internal: tape needs %zu bytes of shared memory per CTA", smem);
             per_sm = blocks_per_sm(smem);
             grid = (int)std::min<int64_t>((chunks + n_warps - 1) / n_warps, (int64_t)per_sm * rt.sm_count);
@@ -961,7 +962,7 @@ void tape_cache_stats(uint64_t* hits, uint64_t* misses, uint64_t* entries) { *hi
 bool Runtime::run_windows(const std::vector<int32_t>& targets, const std::vector<int32_t>& recorded, bool hold_last) {
     // W adapts: a model whose chains share more state per level than the register file holds (a three-factor LMM: three running sums
     // and three Brownian increments per time step) makes the generator spill and cut a window into many small launches — more than
-    // one per level, i.e. worse than no window. Such a window lowers W for the flushes that follow (never below 1: one launch per
+    // two per level, i.e. worse than no window. Such a window lowers W for the flushes that follow (never below 1: one launch per
     // level, the order of round 1); setting the option window_levels starts over.
     if (window_levels_now <= 0 || window_levels_now > opt.window_levels) window_levels_now = opt.window_levels;
     const int W = std::max(1, window_levels_now);
@@ -1042,7 +1043,8 @@ bool Runtime::run_windows(const std::vector<int32_t>& targets, const std::vector
         const uint64_t launches0 = stats.n_tape_kernels;
         run_cone(win[(size_t)w], nullptr);
         const int levels_here = std::min(W, max_level + 1 - w * W);
-        if (W > 1 && stats.n_tape_kernels - launches0 > (uint64_t)levels_here + 1 && window_levels_now == W) {
+        // (a launch or two more than levels is normal: the chains that end inside the window, a ragged first level)
+        if (W > 1 && stats.n_tape_kernels - launches0 > 2u * (uint64_t)levels_here + 2u && window_levels_now == W) {
             window_levels_now = W - 1;
             if (log_windows) std::fprintf(stderr, "[fmc windows] a window of %d levels took %llu launches: W -> %d\n", levels_here,
                                           (unsigned long long)(stats.n_tape_kernels - launches0), window_levels_now);
