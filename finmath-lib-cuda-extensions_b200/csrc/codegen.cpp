@@ -1006,6 +1006,14 @@ bool Runtime::run_windows(const std::vector<int32_t>& targets, const std::vector
             }
         }
     }
+    // Windows pay when a level is WIDE — many chains advancing side by side, each handing its value to the next level — so that one
+    // launch per window replaces one per level. A deep, narrow graph (one chain with every intermediate still referenced: a
+    // Black-Scholes path, the forward pass of an AAD tape) would be cut into a launch per W levels instead of one per flush:
+    // below eight still-referenced values per level the flush runs as one cone, as it always did.
+    if ((long long)targets.size() < 8ll * (max_level + 1)) {
+        run_cone(targets, nullptr);
+        return false;
+    }
     const int n_win = max_level / W + 1;
     // held back: the top three levels and with them the window they belong to. The handles a caller holds only for the duration of
     // a step (its vector of drifts, the running state of the component being updated) are still-referenced values too: they make
