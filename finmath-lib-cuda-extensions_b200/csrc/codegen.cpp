@@ -1010,7 +1010,25 @@ bool Runtime::run_windows(const std::vector<int32_t>& targets, const std::vector
     // launch per window replaces one per level. A deep, narrow graph (one chain with every intermediate still referenced: a
     // Black-Scholes path, the forward pass of an AAD tape) would be cut into a launch per W levels instead of one per flush:
     // below eight still-referenced values per level the flush runs as one cone, as it always did.
-    if ((long long)targets.size() < 8ll * (max_level + 1)) {
+    // Nor do they pay when most pending values are still referenced (a differentiable wrapper keeps every intermediate for its
+    // reverse sweep: a "level" is then one operation, not a time step, and everything is stored anyway; measured: the forward pass
+    // of an AAD LMM vega ran 2x slower in windows).
+    static thread_local std::vector<char> level_used;
+    level_used.assign((size_t)max_level + 1, 0);
+    long long n_levels_used = 0, n_targets = 0;
+    // (the pending list names a recycled node slot once per life: count each target once)
+    epoch++;
+    if (epoch == 0) { for (auto& nd : nodes) nd.epoch = 0; epoch = 1; }
+    for (int32_t t : targets) {
+        Node& nt = nodes[t];
+        if (nt.state != NS_LAZY || nt.epoch == epoch) continue;
+        nt.epoch = epoch;
+        n_targets++;
+        if (!level_used[(size_t)nt.local]) { level_used[(size_t)nt.local] = 1; n_levels_used++; }
+    }
+    if (n_targets < 8 * n_levels_used || 4 * n_targets > (long long)n_lazy) {
+        static const bool log_cone = std::getenv("FMC_LOG_TAPES") != nullptr;
+        if (log_cone) std::fprintf(stderr, "[fmc windows] one cone: %lld targets, %lld levels used of %d, %lld pending\n", n_targets, n_levels_used, max_level + 1, (long long)n_lazy);
         run_cone(targets, nullptr);
         return false;
     }
