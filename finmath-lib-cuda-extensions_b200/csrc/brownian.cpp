@@ -132,8 +132,11 @@ void brownian_generate(Runtime& rt, int seed_mode, int64_t seed, int T, int F, i
         if (PT * TF < 320) PT = (320 + TF - 1) / TF;             // a regeneration (312 elements) may span at most 2 tiles
         if (PT % 2 == 0) PT += 1;
         if ((size_t)(2 * PT * TF) * sizeof(float) > 200 * 1024) fail(FMC_ERR_UNSUPPORTED, "T*F = %d too large for the Brownian tile buffer", TF);
-        // block decomposition: contiguous path ranges, 5 blocks per SM (one wave; the blocks' barrier-separated phases overlap)
-        int64_t target_blocks = (int64_t)rt.sm_count * 5;
+        // block decomposition: contiguous path ranges, as many blocks as are resident at once (ONE wave; the blocks' barrier-separated
+        // phases overlap). The register file admits 4 blocks of 10 warps per SM: 5 per SM left a second wave a quarter full.
+        int per_sm = rt.opt.brownian_blocks_per_sm > 0 ? rt.opt.brownian_blocks_per_sm : brownian_max_blocks_per_sm(T, F, (int)PT);
+        if (per_sm <= 0) per_sm = 4;
+        int64_t target_blocks = (int64_t)rt.sm_count * per_sm;
         int64_t ppb = (np + target_blocks - 1) / target_blocks;
         ppb = std::max<int64_t>((ppb + PT - 1) / PT * PT, PT);
         // keep the block-relative element index inside 32 bits

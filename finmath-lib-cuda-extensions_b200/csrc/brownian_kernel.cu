@@ -330,6 +330,14 @@ cudaError_t launch_mt_raw(const uint32_t* block_states, const long long* chunk_o
     return cudaGetLastError();
 }
 
+int brownian_max_blocks_per_sm(int T, int F, int PT) {
+    const size_t smem = sizeof(float) * 2 * (size_t)T * F * PT;
+    if (cudaFuncSetAttribute(brownian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, brownian_kernel, BTHREADS, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 cudaError_t launch_brownian(const BrownianParams& B, cudaStream_t stream) {
     BrownianLaunch P;
     P.block_states = B.block_states; P.chunk_of_block = B.chunk_of_block; P.paths_per_block = B.paths_per_block;

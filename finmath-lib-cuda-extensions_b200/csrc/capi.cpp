@@ -426,6 +426,7 @@ static void set_option_locked(Runtime& rt, const char* key, double value) {
     else if (!std::strcmp(key, "pipeline")) rt.opt.pipeline = value != 0.0;
     else if (!std::strcmp(key, "max_sets")) rt.opt.max_sets = std::max(1, std::min((int)value, 4));
     else if (!std::strcmp(key, "grid_limit")) rt.opt.grid_limit = std::max(0, (int)value);
+    else if (!std::strcmp(key, "brownian_blocks_per_sm")) rt.opt.brownian_blocks_per_sm = std::max(0, (int)value);
     else if (!std::strcmp(key, "fuse_ops")) rt.opt.fuse_ops = value != 0.0;
     else if (!std::strcmp(key, "fuse_ops2")) rt.opt.fuse_ops2 = value != 0.0;
     else if (!std::strcmp(key, "regression_float_products")) rt.opt.regression_float_products = value != 0.0;
@@ -479,6 +480,7 @@ int fmc_get_option(const char* key, double* value) {
         else if (!std::strcmp(key, "pipeline")) *value = rt.opt.pipeline ? 1.0 : 0.0;
         else if (!std::strcmp(key, "max_sets")) *value = rt.opt.max_sets;
         else if (!std::strcmp(key, "grid_limit")) *value = rt.opt.grid_limit;
+        else if (!std::strcmp(key, "brownian_blocks_per_sm")) *value = rt.opt.brownian_blocks_per_sm;
         else if (!std::strcmp(key, "fuse_ops")) *value = rt.opt.fuse_ops ? 1.0 : 0.0;
         else if (!std::strcmp(key, "fuse_ops2")) *value = rt.opt.fuse_ops2 ? 1.0 : 0.0;
         else if (!std::strcmp(key, "regression_float_products")) *value = rt.opt.regression_float_products ? 1.0 : 0.0;

@@ -91,6 +91,7 @@ struct BrownianParams {
     float* const* out;              // [T*F] device array of device pointers, each np floats
 };
 cudaError_t launch_brownian(const BrownianParams& P, cudaStream_t stream);
+int brownian_max_blocks_per_sm(int T, int F, int PT);     // resident blocks per SM for this tile geometry (occupancy query)
 // out_states[b] = seeded state advanced by chunk_of_block[b] * MT_CHUNK_WORDS words
 cudaError_t launch_mt_jump(const uint32_t* base_state, const uint32_t* polys, int npoly, const long long* chunk_of_block,
                            uint32_t* out_states, int n_blocks, cudaStream_t stream);

@@ -130,6 +130,7 @@ struct Options {
                                     // chunks win down to ~400 k paths, 8-element chunks below)
     bool fuse_ops = true;           // peephole fusion of the abstract code (MULADD_II, ACCUM_S, ADDPROD)
     bool fuse_ops2 = true;          // ... and the one-dispatch forms on top of it (RATIOACC, AXPYST, ADDAFFDISC with its slot's reload)
+    int brownian_blocks_per_sm = 0; // blocks per SM the Brownian generator sizes its grid for (0: what the occupancy query reports, one wave)
     int grid_limit = 0;             // > 0: cap the interpreter grid (tests: many chunks per warp at small sizes)
     int max_regs = 8;               // register-file slots the code generator may use, <= TAPE_REGS. Measured on the LMM step: 16 slots
                                     // let a few kernels drop to one CTA per SM (8.36 ms simulation); 8: 8.14 ms, 4: 8.00 ms but more spills

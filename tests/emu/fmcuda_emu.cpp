@@ -540,6 +540,7 @@ int reduce_tile_elems() { return 4096; }
 // FMC_EMU_FAKE_BROWNIAN=1 (tape-shape studies of the workload drivers only): increments from a throw-away generator,
 // NOT the MT19937 stream — the Brownian parity tests are never run against the emulator.
 static bool fake_brownian() { return std::getenv("FMC_EMU_FAKE_BROWNIAN") != nullptr; }
+int brownian_max_blocks_per_sm(int, int, int) { return 4; }
 cudaError_t launch_brownian(const BrownianParams& P, cudaStream_t) {
     if (!fake_brownian()) return cudaErrorNotSupported;
     uint64_t s = 0x9E3779B97F4A7C15ull;
