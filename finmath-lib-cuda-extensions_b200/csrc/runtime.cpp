@@ -382,40 +382,65 @@ public:
     static HostWorkers& get() { static HostWorkers* w = new HostWorkers(); return *w; }   // leaked like Runtime
     // fn(begin, end) over [0, n) split into contiguous blocks; returns when all blocks are done
     void parallel_for(int64_t n, const std::function<void(int64_t, int64_t)>& fn) {
-        const int64_t min_block = 1 << 16;
-        const int parts = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)threads_.size() + 1, n / min_block));
-        if (parts <= 1) { fn(0, n); return; }
+        // blocks of 32 Ki elements, four per thread at most, handed out one at a time: a worker that wakes up late (a futex wake-up on a
+        // virtual CPU takes tens of microseconds, a third of what a 4 MiB chunk costs) takes fewer blocks instead of holding up the call
+        const int64_t min_block = 1 << 15;
+        const int parts = (int)std::max<int64_t>(1, std::min<int64_t>(blocks_per_thread_ * ((int64_t)threads_.size() + 1), n / min_block));
+        if (parts <= 1 || threads_.empty()) { fn(0, n); return; }
         {
             std::lock_guard<std::mutex> lk(mu_);
-            fn_ = &fn; n_ = n; parts_ = parts; next_ = 0; pending_ = parts; gen_++;
+            fn_ = &fn; n_ = n; parts_ = parts; next_ = 0; pending_.store(parts, std::memory_order_relaxed);
+            gen_.fetch_add(1, std::memory_order_release);
         }
-        cv_.notify_all();
+        if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
         work();                                  // the caller takes blocks too
+        // the last blocks are a few microseconds from done: look before sleeping
+        for (int spin = 0; spin < 20000 && pending_.load(std::memory_order_acquire) != 0; spin++) cpu_relax();
         std::unique_lock<std::mutex> lk(mu_);
-        done_.wait(lk, [&] { return pending_ == 0; });
+        done_.wait(lk, [&] { return pending_.load(std::memory_order_acquire) == 0; });
         fn_ = nullptr;
     }
 private:
     HostWorkers() {
         unsigned hc = std::thread::hardware_concurrency();
-        // measured on the 16-vCPU single-B200 box: 8 threads beat 16+ (the loop is bound by host memory bandwidth);
-        // one process per GPU shares the host: the cores are divided by the number of local ranks (torchrun's
-        // LOCAL_WORLD_SIZE). Measured at 4 ranks on 32 vCPUs, end-to-end LMM step: 4 threads 52.0 ms, 8: 44.6 ms, 12: 44.2 ms
+        // measured on the 16-vCPU single-B200 box, end-to-end LMM step with blocks handed out dynamically and spinning workers
+        // (gpurun_out/r5e.log): 6 threads 27-28 ms, 8: 25-26, 12: 23.6, 16: 22.7-23.2 (with one static block per thread and
+        // sleeping workers 8 threads were the best: 26 ms). One process per GPU shares the host: the cores are divided by the number
+        // of local ranks (torchrun's LOCAL_WORLD_SIZE). Measured at 4 ranks on 32 vCPUs: 4 threads 52.0 ms, 8: 44.6 ms, 12: 44.2 ms
         unsigned local_ranks = 1;
         if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) local_ranks = (unsigned)std::max(1, std::atoi(e));
-        int want = (int)std::min<unsigned>(std::max<unsigned>((hc ? hc : 8u) / local_ranks, 2u), 8u) - 1;   // FMC_HOST_THREADS overrides
+        int want = (int)std::min<unsigned>(std::max<unsigned>((hc ? hc : 8u) / local_ranks, 2u), local_ranks == 1 ? 16u : 8u) - 1;   // FMC_HOST_THREADS overrides
         if (const char* e = std::getenv("FMC_HOST_THREADS")) want = std::max(0, std::atoi(e) - 1);
+        spin_us_ = local_ranks == 1 ? 200 : 0;                                                            // FMC_HOST_SPIN_US overrides
+        if (const char* e = std::getenv("FMC_HOST_SPIN_US")) spin_us_ = std::max(0, std::atoi(e));
+        if (const char* e = std::getenv("FMC_HOST_BLOCKS_PER_THREAD")) blocks_per_thread_ = std::max(1, std::atoi(e));
         for (int i = 0; i < want; i++) threads_.emplace_back([this] { loop(); });
         for (auto& t : threads_) t.detach();
+    }
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
     }
     void loop() {
         uint64_t seen = 0;
         for (;;) {
-            {
-                std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return gen_ != seen; });
-                seen = gen_;
+            // uploads come in bursts (one vector per time step of a simulation being recorded): a worker keeps looking for the next
+            // call for spin_us_ before it goes to sleep. Only when this process has the host to itself (one local rank).
+            if (spin_us_ > 0) {
+                const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us_);
+                while (gen_.load(std::memory_order_acquire) == seen) {
+                    for (int k = 0; k < 64 && gen_.load(std::memory_order_relaxed) == seen; k++) cpu_relax();
+                    if (std::chrono::steady_clock::now() >= t_end) break;
+                }
             }
+            if (gen_.load(std::memory_order_acquire) == seen) {
+                std::unique_lock<std::mutex> lk(mu_);
+                sleepers_.fetch_add(1, std::memory_order_acq_rel);
+                cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+                sleepers_.fetch_sub(1, std::memory_order_acq_rel);
+            }
+            seen = gen_.load(std::memory_order_acquire);
             work();
         }
     }
@@ -430,9 +455,9 @@ private:
             const int64_t per = (n + parts - 1) / parts;
             const int64_t b = std::min<int64_t>(n, per * part), e = std::min<int64_t>(n, b + per);
             if (b < e) (*fn)(b, e);
-            {
+            if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
                 std::lock_guard<std::mutex> lk(mu_);
-                if (--pending_ == 0) done_.notify_all();
+                done_.notify_all();
             }
         }
     }
@@ -441,8 +466,10 @@ private:
     std::condition_variable cv_, done_;
     const std::function<void(int64_t, int64_t)>* fn_ = nullptr;
     int64_t n_ = 0;
-    int parts_ = 0, next_ = 0, pending_ = 0;
-    uint64_t gen_ = 0;
+    int parts_ = 0, next_ = 0;
+    std::atomic<int> pending_{0}, sleepers_{0};
+    std::atomic<uint64_t> gen_{0};
+    int spin_us_ = 0, blocks_per_thread_ = 4;
 };
 
 constexpr size_t kChunkElems = 4u << 20;   // 16 MiB of floats per staging half
