@@ -14,6 +14,8 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <memory>
+#include <typeinfo>
 #include <utility>
 
 #include "RandomVariable.hpp"
@@ -48,6 +50,37 @@ inline double java_pow(double x, double y) {
     if (std::isinf(y) && std::fabs(x) == 1.0) return NAN;
     return std::pow(x, y);
 }
+// Every operation returns a new RandomVariable object: one heap block (object + shared_ptr control block) per recorded operation,
+// 50 000 per LMM step. The blocks are recycled through a per-thread free list instead of malloc / free (a block freed by another
+// thread joins that thread's list; the list is bounded).
+template <class T>
+struct RecycleAlloc {
+    using value_type = T;
+    RecycleAlloc() = default;
+    template <class U> RecycleAlloc(const RecycleAlloc<U>&) noexcept {}
+    struct Cache {
+        void* head = nullptr; size_t count = 0;
+        ~Cache() { while (head) { void* next = *static_cast<void**>(head); ::operator delete(head); head = next; } count = 0; }
+    };
+    static Cache& cache() { static thread_local Cache c; return c; }
+    T* allocate(std::size_t n) {
+        static_assert(sizeof(T) >= sizeof(void*), "a free block holds the link to the next one");
+        if (n == 1) {
+            Cache& c = cache();
+            if (c.head) { void* p = c.head; c.head = *static_cast<void**>(p); c.count--; return static_cast<T*>(p); }
+        }
+        return static_cast<T*>(::operator new(n * sizeof(T)));
+    }
+    void deallocate(T* p, std::size_t n) noexcept {
+        if (n == 1) {
+            Cache& c = cache();
+            if (c.count < (1u << 16)) { *reinterpret_cast<void**>(p) = c.head; c.head = p; c.count++; return; }
+        }
+        ::operator delete(p);
+    }
+    template <class U> bool operator==(const RecycleAlloc<U>&) const noexcept { return true; }
+    template <class U> bool operator!=(const RecycleAlloc<U>&) const noexcept { return false; }
+};
 }  // namespace detail
 
 template <class B>
@@ -66,8 +99,8 @@ public:
     RandomVariableImpl(const RandomVariableImpl&) = delete;
     RandomVariableImpl& operator=(const RandomVariableImpl&) = delete;
 
-    static RV of(double time, double value) { return std::make_shared<Self>(time, value); }                       // RVC:643-646
-    static RV of(double time, Vec&& vec, int64_t n) { return std::make_shared<Self>(time, std::move(vec), n); }    // RVC:631-634
+    static RV of(double time, double value) { return std::allocate_shared<Self>(detail::RecycleAlloc<Self>(), time, value); }                       // RVC:643-646
+    static RV of(double time, Vec&& vec, int64_t n) { return std::allocate_shared<Self>(detail::RecycleAlloc<Self>(), time, std::move(vec), n); }    // RVC:631-634
     static RV of(double time, const double* values, int64_t n) { return of(time, B::from_f64(values, n), n); }     // RVC:723-725
 
     const Vec& vec() const { return vec_; }
@@ -93,7 +126,7 @@ public:
     double getAverage() const override { return det_ ? value_ : B::reduce(R_AVERAGE, vec_, n_, nullptr); }
     double getAverage(const RV& p) const override {
         if (det_) return value_ * p->getAverage();                                                                 // RVF:338-340
-        auto q = as_self(p);
+        auto q = ref(p);
         if (q->det_) return this->mult(q->value_)->getAverage();
         return B::reduce(R_AVERAGE_W, vec_, n_, &q->vec_);
     }
@@ -134,65 +167,65 @@ public:
         if (r->getTypePriority() > priority_) return r->add(self());
         const double t = std::max(time_, r->getFiltrationTime());
         if (det_ && r->isDeterministic()) return of(t, value_ + r->doubleValue());
-        if (det_) return as_self(r)->vs(OP_ADD, value_, t);                                                        // RVF:974-979
+        if (det_) return ref(r)->vs(OP_ADD, value_, t);                                                        // RVF:974-979
         if (r->isDeterministic()) return vs(OP_ADD, r->doubleValue(), t);
-        return vv(OP_ADD, *as_self(r), t);
+        return vv(OP_ADD, *ref(r), t);
     }
     RV sub(const RV& r) const override {
         if (r->getTypePriority() > priority_) return r->bus(self());
         const double t = std::max(time_, r->getFiltrationTime());
         if (det_ && r->isDeterministic()) return of(t, value_ - r->doubleValue());
-        if (det_) return as_self(r)->vs(OP_BUS, value_, t);                                                        // RVF:1003-1008
+        if (det_) return ref(r)->vs(OP_BUS, value_, t);                                                        // RVF:1003-1008
         if (r->isDeterministic()) return vs(OP_SUB, r->doubleValue(), t);
-        return vv(OP_SUB, *as_self(r), t);
+        return vv(OP_SUB, *ref(r), t);
     }
     RV bus(const RV& r) const override {
         if (r->getTypePriority() > priority_) return r->sub(self());
         const double t = std::max(time_, r->getFiltrationTime());
         if (det_ && r->isDeterministic()) return of(t, -value_ + r->doubleValue());
-        if (det_) return as_self(r)->vs(OP_SUB, value_, t);                                                        // RVF:1033-1038
+        if (det_) return ref(r)->vs(OP_SUB, value_, t);                                                        // RVF:1033-1038
         if (r->isDeterministic()) return vs(OP_BUS, r->doubleValue(), t);
-        return vv(OP_BUS, *as_self(r), t);
+        return vv(OP_BUS, *ref(r), t);
     }
     RV mult(const RV& r) const override {
         if (r->getTypePriority() > priority_) return r->mult(self());
         const double t = std::max(time_, r->getFiltrationTime());
         if (det_ && r->isDeterministic()) return of(t, value_ * r->doubleValue());
         if (r->isDeterministic()) return vs(OP_MULT, r->doubleValue(), t);
-        if (det_) return as_self(r)->vs(OP_MULT, value_, t);                                                       // RVF:1065-1070
-        return vv(OP_MULT, *as_self(r), t);
+        if (det_) return ref(r)->vs(OP_MULT, value_, t);                                                       // RVF:1065-1070
+        return vv(OP_MULT, *ref(r), t);
     }
     RV div(const RV& r) const override {
         if (r->getTypePriority() > priority_) return r->vid(self());
         const double t = std::max(time_, r->getFiltrationTime());
         if (det_ && r->isDeterministic()) return of(t, value_ / r->doubleValue());
-        if (det_) return as_self(r)->vs(OP_VID, value_, t);                                                        // RVF:1098-1103
+        if (det_) return ref(r)->vs(OP_VID, value_, t);                                                        // RVF:1098-1103
         if (r->isDeterministic()) return vs(OP_DIV, r->doubleValue(), t);
-        return vv(OP_DIV, *as_self(r), t);
+        return vv(OP_DIV, *ref(r), t);
     }
     RV vid(const RV& r) const override {
         if (r->getTypePriority() > priority_) return r->div(self());                                               // RVF:1116-1119
         const double t = std::max(time_, r->getFiltrationTime());
         if (det_ && r->isDeterministic()) return of(t, r->doubleValue() / value_);
-        if (det_) return as_self(r)->vs(OP_DIV, value_, t);                                                        // RVF:1128-1133
+        if (det_) return ref(r)->vs(OP_DIV, value_, t);                                                        // RVF:1128-1133
         if (r->isDeterministic()) return vs(OP_VID, r->doubleValue(), t);
-        return vv(OP_VID, *as_self(r), t);
+        return vv(OP_VID, *ref(r), t);
     }
     RV cap(const RV& r) const override {
         if (r->getTypePriority() > priority_) return r->cap(self());
         const double t = std::max(time_, r->getFiltrationTime());
         if (det_ && r->isDeterministic()) return of(t, detail::java_min(value_, r->doubleValue()));
-        if (det_) return as_self(r)->vs(OP_CAP, value_, t);                                                        // RVF:1158-1163
+        if (det_) return ref(r)->vs(OP_CAP, value_, t);                                                        // RVF:1158-1163
         if (r->isDeterministic()) return vs(OP_CAP, r->doubleValue(), t);                                          // missing in RVC:1546-1555 (NPE)
-        return vv(OP_CAP, *as_self(r), t);
+        return vv(OP_CAP, *ref(r), t);
     }
     RV floor(const RV& r) const override {
         if (r->getTypePriority() > priority_) return r->floor(self());
         const double t = std::max(time_, r->getFiltrationTime());
         if (det_ && r->isDeterministic()) return of(t, detail::java_max(value_, r->doubleValue()));
-        if (det_) return as_self(r)->vs(OP_FLOOR, value_, t);                                                      // RVF:1187-1192
+        if (det_) return ref(r)->vs(OP_FLOOR, value_, t);                                                      // RVF:1187-1192
         if (r->isDeterministic()) return vs(OP_FLOOR, r->doubleValue(), t);
-        return vv(OP_FLOOR, *as_self(r), t);
+        return vv(OP_FLOOR, *ref(r), t);
     }
 
     // ---- accrue / discount (RVC:1582-1624, RVF:1202-1256) ----
@@ -200,7 +233,7 @@ public:
         if (rate->getTypePriority() > priority_) return rate->mult(p)->add(1.0)->mult(self());
         const double t = std::max(time_, rate->getFiltrationTime());
         if (rate->isDeterministic()) return mult(1.0 + rate->doubleValue() * p);
-        auto r = as_self(rate);
+        auto r = ref(rate);
         if (det_) return cast(cast(r->vs(OP_MULT, p))->vs(OP_ADD, 1.0))->vs(OP_MULT, value_, t);                   // RVF:1214-1219
         return of(t, B::vvs(OP_ACCRUE, vec_, r->vec_, p, n_), n_);
     }
@@ -208,7 +241,7 @@ public:
         if (rate->getTypePriority() > priority_) return rate->mult(p)->add(1.0)->vid(self());                      // RVF:1232-1235
         const double t = std::max(time_, rate->getFiltrationTime());
         if (rate->isDeterministic()) return div(1.0 + rate->doubleValue() * p);
-        auto r = as_self(rate);
+        auto r = ref(rate);
         if (det_) return cast(cast(r->vs(OP_MULT, p))->vs(OP_ADD, 1.0))->vs(OP_VID, value_, t);                    // RVF:1242-1247, RVC:1614-1618
         return of(t, B::vvs(OP_DISCOUNT, vec_, r->vec_, p, n_), n_);
     }
@@ -217,14 +250,14 @@ public:
     RV choose(const RV& a, const RV& b) const override {
         const double t = std::max(std::max(time_, a->getFiltrationTime()), b->getFiltrationTime());
         if (det_) return value_ >= 0 ? a : b;                                                                      // RVF:1270-1276
-        auto ca = as_self(a), cb = as_self(b);
+        auto ca = ref(a), cb = ref(b);
         return of(t, B::choose(vec_, ca->det_ ? nullptr : &ca->vec_, ca->value_, cb->det_ ? nullptr : &cb->vec_, cb->value_, n_), n_);
     }
     RV addProduct(const RV& f1, double f2) const override {
         if (f1->getTypePriority() > priority_) return f1->mult(f2)->add(self());
         const double t = std::max(time_, f1->getFiltrationTime());
         if (f1->isDeterministic()) return add(f1->doubleValue() * f2);
-        auto c1 = as_self(f1);
+        auto c1 = ref(f1);
         if (det_) return cast(c1->vs(OP_MULT, f2))->vs(OP_ADD, value_, t);                                         // RVF:1329-1334
         return of(t, B::vvs(OP_ADDPRODUCT, vec_, c1->vec_, f2, n_), n_);
     }
@@ -236,7 +269,7 @@ public:
         if (f2->isDeterministic()) return addProduct(f1, f2->doubleValue());
         if (f1->isDeterministic()) return addProduct(f2, f1->doubleValue());
         if (!det_) {
-            auto c1 = as_self(f1), c2 = as_self(f2);
+            auto c1 = ref(f1), c2 = ref(f2);
             return of(t, B::vvv(OP_ADDPRODUCT, vec_, c1->vec_, c2->vec_, n_), n_);
         }
         return add(f1->mult(f2));                                                                                  // RVF:1379-1381
@@ -258,6 +291,21 @@ public:
         return cast(of(r->getFiltrationTime(), v.data(), (int64_t)v.size()));
     }
 
+    // the same for an operand that is only read during the call: an object of this class is borrowed from the caller's reference
+    // (no reference-count traffic, no dynamic_pointer_cast: 100 000 operands per LMM step), a foreign one is converted and kept alive
+    struct Ref {
+        const Self* p; std::shared_ptr<const Self> keep;
+        const Self* operator->() const { return p; }
+        const Self& operator*() const { return *p; }
+    };
+    static Ref ref(const RV& r) {
+        const RandomVariable* raw = r.get();
+        if (typeid(*raw) == typeid(Self)) return Ref{static_cast<const Self*>(raw), nullptr};
+        std::shared_ptr<const Self> s = as_self(r);
+        const Self* q = s.get();
+        return Ref{q, std::move(s)};
+    }
+
 private:
     double time_;
     bool det_;
@@ -267,7 +315,7 @@ private:
     int priority_;
 
     static std::shared_ptr<const Self> cast(const RV& r) { return std::static_pointer_cast<const Self>(r); }
-    RV det(double value) const { return std::make_shared<Self>(time_, value, priority_); }
+    RV det(double value) const { return std::allocate_shared<Self>(detail::RecycleAlloc<Self>(), time_, value, priority_); }
     RV vs(int op, double s) const { return of(time_, B::vs(op, vec_, s, n_), n_); }
     RV vs(int op, double s, double t) const { return of(t, B::vs(op, vec_, s, n_), n_); }
     RV v(int op) const { return of(time_, B::v(op, vec_, n_), n_); }
@@ -275,13 +323,13 @@ private:
     RV ratio(const RV& num, const RV& den, int op, double sign) const {
         const double t = std::max(std::max(time_, num->getFiltrationTime()), den->getFiltrationTime());
         if (det_ && num->isDeterministic() && den->isDeterministic()) return of(t, value_ + sign * (num->doubleValue() / den->doubleValue()));
-        auto n = as_self(num), d = as_self(den);
+        auto n = ref(num), d = ref(den);
         if (!det_ && !n->det_ && !d->det_) return of(t, B::vvv(op, vec_, n->vec_, d->vec_, n_), n_);
         if (n->det_ && d->det_) {                        // RVF:1408-1413: (float)n / (float)d in float, then added to the vector
             const float q = (float)n->value_ / (float)d->value_;
             return vs(sign > 0 ? OP_ADD : OP_SUB, (double)q, t);
         }
-        RV q = n->div(d);
+        RV q = n->div(den);
         return sign > 0 ? q->add(self()) : q->bus(self());
     }
 };
