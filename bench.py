@@ -180,12 +180,12 @@ def run_reference(args) -> None:
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (an LMM Euler-step launch of the tape
 # interpreter at 1 Mi paths) from one `ncu --set full` capture; NOT measured in this run, NOT comparable with the per-step
 # algorithmic bytes: reported under its own name with the capture it came from (None until this round's capture exists).
-NCU_DRAM_BYTES_DOMINANT_LAUNCH = 869_222_656     # 245.40 MB read + 623.82 MB written, first launch of profiles/prof_sim_r3.txt (229.1 us): one
+NCU_DRAM_BYTES_DOMINANT_LAUNCH = 869_150_976     # 245.40 MB read + 623.75 MB written, first launch of profiles/prof_sim_r5.txt (226.4 us): one
                                                  # window of three Euler time steps (round 1 / early round 2: 533 MB for ONE time step)
 NCU_ALGORITHMIC_BYTES_OF_THAT_LAUNCH = 1_266_679_808   # its tape: 78 leaf vectors (75 rates + 3 Brownian increments) + 224 result vectors x 4 MiB.
                                                  # The DRAM traffic is BELOW it: part of the stores still sits in the L2 when the kernel ends and
                                                  # some leaves are hit there; the rates a step stores are no longer read back inside the window
-NCU_CAPTURE_FILE = "profiles/prof_sim_r3.txt (ncu --set full --clock-control none -k regex:tape_kernel -s 173 -c 3 of bench.py --steps 2 --warmup 1; launch list profiles/launches_r3.txt)"
+NCU_CAPTURE_FILE = "profiles/prof_sim_r5.txt (ncu --set full --clock-control none -k regex:tape_kernel -s 173 -c 3 of bench.py --steps 2 --warmup 1; launch list profiles/launches_r5.txt)"
 
 PARITY_REL_TOL = 1e-4       # north star: "Monte-Carlo prices ... match within 1e-4 relative on identical seeds"
 
