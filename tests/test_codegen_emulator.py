@@ -49,3 +49,13 @@ def test_windows_of_time_steps_on_the_emulator(emulator):
     r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "run_window_check.py"), "700"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert r.stdout.count("LIBORs bit-identical True") >= 6, r.stdout
+
+
+@pytest.mark.parametrize("env", [{}, {"FMC_HOST_THREADS": "4", "FMC_HOST_SPIN_US": "0"}, {"FMC_HOST_THREADS": "3", "FMC_HOST_SPIN_US": "300", "FMC_HOST_BLOCKS_PER_THREAD": "7"},
+                                 {"FMC_HOST_AVX": "0", "FMC_HOST_THREADS": "1"}])
+def test_host_staging_pool_on_the_emulator(emulator, env):
+    """createRandomVariable(time, double[]) -> getRealizations() through the host worker pool (csrc/runtime.cpp: HostWorkers): ragged sizes,
+    special values, both conversion loops, spinning and sleeping workers."""
+    e = dict(os.environ, LD_PRELOAD=emulator, **env)
+    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "run_upload_check.py")], env=e, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "round trips ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
