@@ -406,12 +406,15 @@ private:
         // measured on the 16-vCPU single-B200 box, end-to-end LMM step with blocks handed out dynamically and spinning workers
         // (gpurun_out/r5e.log): 6 threads 27-28 ms, 8: 25-26, 12: 23.6, 16: 22.7-23.2 (with one static block per thread and
         // sleeping workers 8 threads were the best: 26 ms). One process per GPU shares the host: the cores are divided by the number
-        // of local ranks (torchrun's LOCAL_WORLD_SIZE). Measured at 4 ranks on 32 vCPUs: 4 threads 52.0 ms, 8: 44.6 ms, 12: 44.2 ms
+        // of local ranks (torchrun's LOCAL_WORLD_SIZE). Measured at 4 ranks on 32 vCPUs: 4 threads 52.0 ms, 8: 44.6 ms, 12: 44.2 ms;
+        // at 2 ranks on 24 vCPUs (r5j.log): 8 threads 28.9 ms, 12 threads 28.7 ms, 12 spinning 26.4 ms. Workers spin only where a rank
+        // has 12 or more cores to itself (8 ranks on 32 vCPUs would fill every core with spinning threads).
         unsigned local_ranks = 1;
         if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) local_ranks = (unsigned)std::max(1, std::atoi(e));
-        int want = (int)std::min<unsigned>(std::max<unsigned>((hc ? hc : 8u) / local_ranks, 2u), local_ranks == 1 ? 16u : 8u) - 1;   // FMC_HOST_THREADS overrides
+        const unsigned per_rank = (hc ? hc : 8u) / local_ranks;
+        int want = (int)std::min<unsigned>(std::max<unsigned>(per_rank, 2u), 16u) - 1;   // FMC_HOST_THREADS overrides
         if (const char* e = std::getenv("FMC_HOST_THREADS")) want = std::max(0, std::atoi(e) - 1);
-        spin_us_ = local_ranks == 1 ? 500 : 0;                                                            // FMC_HOST_SPIN_US overrides
+        spin_us_ = per_rank >= 12 ? 500 : 0;                                                               // FMC_HOST_SPIN_US overrides
         if (const char* e = std::getenv("FMC_HOST_SPIN_US")) spin_us_ = std::max(0, std::atoi(e));
         if (const char* e = std::getenv("FMC_HOST_BLOCKS_PER_THREAD")) blocks_per_thread_ = std::max(1, std::atoi(e));
         for (int i = 0; i < want; i++) threads_.emplace_back([this] { loop(); });
