@@ -229,3 +229,18 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["higher_is_better"] is True and line["gpu_launches"] == 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_host_mirror_objects_recycled_across_valuation_threads():
+    """The C++ host mirror (include/finmath/RandomVariableImpl.hpp) takes the object of every recorded operation from a per-thread free
+    list; products valued by several host threads free objects on another thread than the one that made them. Run on the oracle twin
+    of the driver (same mirror source, CPU backend): the values do not depend on the number of valuation threads, repeatedly."""
+    import numpy as np
+    from oracle.workloads_oracle import driver
+    m = driver().lmm(257)
+    ref = np.asarray(m.step()).copy()
+    for threads in (3, 1, 4, 2):
+        m.set_valuation_threads(threads)
+        for _ in range(2):
+            assert np.array_equal(np.asarray(m.step()), ref), threads
+    m.close()
