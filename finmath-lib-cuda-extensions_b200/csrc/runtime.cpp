@@ -429,7 +429,7 @@ private:
         uint64_t seen = 0;
         for (;;) {
             // uploads come in bursts (one vector per time step of a simulation being recorded): a worker keeps looking for the next
-            // call for spin_us_ before it goes to sleep. Only when this process has the host to itself (one local rank).
+            // call for spin_us_ before it goes to sleep (0 where the ranks of a host have fewer than 12 cores each: see the constructor).
             if (spin_us_ > 0) {
                 const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us_);
                 while (gen_.load(std::memory_order_acquire) == seen) {
