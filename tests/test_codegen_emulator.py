@@ -59,3 +59,11 @@ def test_host_staging_pool_on_the_emulator(emulator, env):
     e = dict(os.environ, LD_PRELOAD=emulator, **env)
     r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "run_upload_check.py")], env=e, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "round trips ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_launch_count_of_a_repeated_lmm_step_is_stable(emulator):
+    """The objective function of the calibration records the same graph thousands of times: every repetition must be cut into the same
+    windows (Runtime::run_windows counts each still-referenced target once, however often its recycled node slot is listed)."""
+    env = dict(os.environ, LD_PRELOAD=emulator, FMC_EMU_FAKE_BROWNIAN="1")
+    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "run_launch_count.py"), "1024"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "launch count stable True" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
